@@ -1,0 +1,45 @@
+"""Host-side helpers shared by the API mirrors."""
+
+from __future__ import annotations
+
+import warnings
+
+import torch
+
+from . import _lib
+
+_warned_cpu = False
+
+GRID_KINDS = {"catmull_rom": 0, "bspline": 1}
+
+
+def resolve_device(image: torch.Tensor, device) -> torch.device:
+    """Reference semantics: ``device=None`` means ``image.device``.  There is no CPU path
+    (north star: no CPU fallback): CPU requests run on the current CUDA device and results
+    stay on CUDA."""
+    global _warned_cpu
+    _lib.require_cuda()
+    dev = torch.device(device) if device is not None else image.device
+    if dev.type != "cuda":
+        if not _warned_cpu:
+            warnings.warn(
+                "torch_motion_correction_b200 has no CPU path: running on the current CUDA device; "
+                "results are returned as CUDA tensors.",
+                stacklevel=3,
+            )
+            _warned_cpu = True
+        dev = torch.device("cuda", torch.cuda.current_device())
+    elif dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def as_f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def grid_kind(grid_type: str) -> int:
+    try:
+        return GRID_KINDS[grid_type]
+    except KeyError:
+        raise ValueError(f"Invalid grid type: {grid_type}. Must be 'catmull_rom' or 'bspline'.") from None

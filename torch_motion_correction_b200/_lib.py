@@ -1,0 +1,106 @@
+"""ctypes binding of the C-ABI CUDA library ``libtmc_b200.so`` (declared in ``include/tmc_b200.h``).
+
+There is NO CPU fallback: if the library is missing or no CUDA device is present every
+entry point raises.  PyTorch is used for device memory and streams only.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_long, c_void_p
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libtmc_b200.so")
+
+_lib = None
+
+P = c_void_p
+I = c_int
+L = c_long
+F = c_float
+D = c_double
+
+# name -> (restype, argtypes); the trailing stream argument is always a cudaStream_t
+_SIGNATURES = {
+    "tmc_version": (I, []),
+    "tmc_last_error": (c_char_p, []),
+    "tmc_sm_count": (I, []),
+    "tmc_stack_stats_workspace_doubles": (I, []),
+    "tmc_stack_stats": (I, [P, I, I, I, I, I, I, I, P, P, P]),
+    "tmc_spline_workspace_floats": (L, [I, I, I, I]),
+    "tmc_spline_eval": (I, [P, I, I, I, I, I, P, L, P, P, P]),
+    "tmc_spline_eval_backward": (I, [I, I, I, I, I, P, L, P, F, P, P, P]),
+    "tmc_spline_lattice": (I, [P, I, I, I, I, I, P, I, I, I, I, I, I, I, I, I, P, P, P]),
+    "tmc_warp_workspace_floats": (L, [I, I, I]),
+    "tmc_warp_lattice": (I, [P, I, I, I, P, I, I, F, P, P, P, I, P, P]),
+    "tmc_pixel_shifts": (I, [P, I, I, I, I, F, P, P]),
+    "tmc_warp_dense_shifts": (I, [P, I, I, I, P, P, P]),
+    "tmc_pixel_tyx": (I, [I, I, I, I, I, P, P]),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def register(name, restype, argtypes):
+    _SIGNATURES[name] = (restype, argtypes)
+
+
+def load() -> ctypes.CDLL:
+    """Load the library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `python -m torch_motion_correction_b200._build`). torch_motion_correction_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library drift apart
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "torch_motion_correction_b200 needs a CUDA device (sm_100a); there is no CPU fallback. "
+            "Use the reference package (or this repo's oracle/) for CPU execution."
+        )
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def call(name: str, *args):
+    """Call an ``int``-returning entry point; non-zero status raises with ``tmc_last_error()``."""
+    lib = load()
+    status = getattr(lib, name)(*args)
+    if status != 0:
+        msg = lib.tmc_last_error().decode("utf-8", "replace")
+        if status == 1:
+            raise ValueError(f"{name}: {msg}")
+        if status == 3:
+            raise NotImplementedError(f"{name}: {msg}")
+        raise RuntimeError(f"{name} failed (status {status}): {msg}")
+
+
+def query(name: str, *args):
+    """Call a value-returning query entry point."""
+    return getattr(load(), name)(*args)
