@@ -1,0 +1,189 @@
+"""FFT building blocks, tables and the cross-correlation estimators against the oracle / goldens."""
+
+import numpy as np
+import pytest
+import torch
+
+import torch_motion_correction_b200 as tmc
+from oracle import deps
+from oracle import reference_path as rp
+from torch_motion_correction_b200 import _fourier, _ops
+
+pytestmark = pytest.mark.gpu
+
+SHIFT_PX = 0.01  # north-star tolerance on estimated shifts (px)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def as_complex(t):
+    return torch.view_as_complex(t.contiguous())
+
+
+@pytest.mark.parametrize("shape", [(16, 16), (32, 32), (64, 128), (128, 64), (256, 256), (512, 1024), (2048, 2048)])
+def test_full_rfft2_and_irfft2_match_torch(dev, shape):
+    ny, nx = shape
+    g = torch.Generator().manual_seed(ny + nx)
+    t = 3
+    img = torch.randn((t, ny, nx), generator=g).to(dev)
+    plan = _fourier.BandPlan(ny, nx, dev, full=True)
+    spec = plan.forward(img, None, None, 0, ny, _fourier.frame_pair_jobs(t, dev))[:t]
+    want = torch.fft.rfftn(img.double(), dim=(-2, -1))
+    err = (as_complex(spec).to(torch.complex128) - want).abs().max() / want.abs().max()
+    assert float(err) < 2e-6
+    back = torch.empty_like(img)
+    plan.inverse_full(spec, back)
+    assert float((back - img).abs().max()) < 1e-5 * float(img.abs().max()) * np.log2(ny * nx)
+
+
+@pytest.mark.parametrize("p,radius,smooth", [(32, 8.0, 4.0), (128, 32.0, 16.0), (128, 32.0, 32.0), (64, 16.0, 0.0)])
+def test_soft_disc_mask_matches_circle(dev, p, radius, smooth):
+    want = deps.circle(radius, (p, p), smoothing_radius=smooth)
+    got, ylo, yhi = _fourier.soft_disc_mask((p, p), radius, smooth, dev)
+    assert float((got.cpu() - want).abs().max()) < 1e-6
+    rows = (want != 0).any(dim=1).nonzero().flatten()
+    assert ylo <= int(rows[0]) and int(rows[-1]) < yhi
+
+
+def test_soft_disc_mask_non_square(dev):
+    want = deps.circle(20.0, (64, 96), smoothing_radius=10.0)
+    got, _, _ = _fourier.soft_disc_mask((64, 96), 20.0, 10.0, dev)
+    assert float((got.cpu() - want).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("n,px,fr,b", [(128, 1.0, (300, 10), 500), (64, 1.3, (120, 6), 500), (32, 1.3, (120, 6), 1000), (256, 0.83, (300, 10), 500)])
+def test_band_weights_match_reference_filters(dev, n, px, fr, b):
+    band, env = rp.fourier_weight((n, n), px, b, fr)
+    want = band * env  # (n, n//2+1)
+    plan = _fourier.BandPlan(n, n, dev, px, b, fr)
+    got = plan.weight.cpu()
+    ky = (torch.arange(plan.ky) + plan.ky_start) % n
+    box = want[ky][:, : plan.kx]
+    assert float((got - box).abs().max()) < 1e-6
+    # nothing of the pass band lies outside the kept box
+    outside = want.clone()
+    outside[ky[:, None], torch.arange(plan.kx)[None, :]] = 0
+    assert float(outside.abs().max()) == 0.0
+    assert int((got != 0).sum()) == int((want != 0).sum())
+
+
+def test_band_limited_patch_spectra(dev):
+    """rows+cols forward kernels vs torch: rfft2(mask^e * normalised patch) * W on the band box."""
+    movie, _ = rp.synthetic_movie(4, 160, 192, seed=4)
+    p, px, fr = 64, 1.1, (100, 5)
+    m = movie.to(dev)
+    stats = _ops.stack_stats(m)
+    plan = _fourier.BandPlan(p, p, dev, px, 500, fr)
+    mask, ylo, yhi = _fourier.soft_disc_mask((p, p), p / 4, p / 8, dev)
+    jobs = torch.tensor([[0, 1, 0, 2, 10, 20], [2, 1, 3, 3, 96, 128], [1, 2, -1, 1, 50, 7]], dtype=torch.int32).to(dev)
+    spec = as_complex(plan.forward(m, stats, mask, ylo, yhi, jobs)).cpu()
+    norm = rp.normalize_image(movie)
+    mk = deps.circle(p / 4, (p, p), smoothing_radius=p / 8)
+    band, env = rp.fourier_weight((p, p), px, 500, fr)
+    ky = (torch.arange(plan.ky) + plan.ky_start) % p
+    for j, (fa, ea, fb, eb, y0, x0) in enumerate(jobs.cpu().tolist()):
+        for part, (f, e) in enumerate(((fa, ea), (fb, eb))):
+            if f < 0:
+                continue
+            want = torch.fft.rfftn(norm[f, y0 : y0 + p, x0 : x0 + p] * mk**e, dim=(-2, -1)) * band * env
+            want = want[ky][:, : plan.kx]
+            err = (spec[2 * j + part] - want).abs().max() / want.abs().max()
+            assert float(err) < 5e-6, (j, part, float(err))
+
+
+def test_global_motion_golden(dev, golden_small, golden_c1):
+    g = golden_small
+    movie = torch.as_tensor(g["movie"]).to(dev)
+    px, fr = float(g["pixel_spacing"]), tuple(float(v) for v in g["frequency_range"])
+    got = tmc.estimate_global_motion(movie, px, frequency_range=fr)
+    assert got.shape == (2, 6, 1, 1)
+    assert float((got.cpu() - torch.as_tensor(g["global_field"])).abs().max()) <= SHIFT_PX * px
+    got = tmc.estimate_global_motion(movie, px, reference_frame=0, b_factor=1000, frequency_range=fr)
+    assert float((got.cpu() - torch.as_tensor(g["global_field_ref0_b1000"])).abs().max()) <= SHIFT_PX * px
+    # BASELINE config 1: known integer drifts are recovered exactly
+    movie, walk = rp.synthetic_movie(10, 512, 512, seed=0, noise=1.0, drift=6.0, integer_shifts=True, sigma_f=0.08)
+    got = tmc.estimate_global_motion(movie.to(dev), 1.0).cpu()
+    assert torch.equal(got, torch.as_tensor(golden_c1["global_field"]))
+    assert torch.equal(got[:, :, 0, 0].T, walk)
+
+
+@pytest.mark.parametrize("strategy", ["mean_except_current", "middle_frame"])
+def test_xc_patches_golden(dev, golden_small, strategy):
+    g = golden_small
+    movie = torch.as_tensor(g["movie"]).to(dev)
+    px, fr = float(g["pixel_spacing"]), tuple(float(v) for v in g["frequency_range"])
+    f, pos = tmc.estimate_motion_cross_correlation_patches(
+        movie, px, reference_strategy=strategy, patch_sidelength=32, frequency_range=fr,
+        temporal_smoothing=False, outlier_rejection=False,
+    )
+    assert np.array_equal(pos.cpu().numpy(), g["xc_positions"])
+    assert float((f.cpu() - torch.as_tensor(g[f"xc_raw_{strategy}"])).abs().max()) <= SHIFT_PX * px
+    f, _ = tmc.estimate_motion_cross_correlation_patches(
+        movie, px, reference_strategy=strategy, patch_sidelength=32, frequency_range=fr,
+        smoothing_window_size=3, outlier_threshold=1.5,
+    )
+    assert float((f.cpu() - torch.as_tensor(g[f"xc_full_{strategy}"])).abs().max()) <= SHIFT_PX * px
+
+
+def test_xc_patches_integer_and_cumulative_golden(dev, golden_small):
+    g = golden_small
+    movie = torch.as_tensor(g["movie"]).to(dev)
+    px, fr = float(g["pixel_spacing"]), tuple(float(v) for v in g["frequency_range"])
+    f, _ = tmc.estimate_motion_cross_correlation_patches(
+        movie, px, patch_sidelength=32, frequency_range=fr, sub_pixel_refinement=False,
+        temporal_smoothing=False, outlier_rejection=False,
+    )
+    assert float((f.cpu() - torch.as_tensor(g["xc_integer"])).abs().max()) <= 1e-5
+    g0 = torch.as_tensor(g["global_field"]).to(dev)
+    f, _ = tmc.estimate_motion_cross_correlation_patches(movie, px, patch_sidelength=32, frequency_range=fr, deformation_field=g0)
+    assert float((f.cpu() - torch.as_tensor(g["xc_cumulative_global"])).abs().max()) <= SHIFT_PX * px
+    assert torch.equal(g0.cpu(), torch.as_tensor(g["xc_cumulative_global_field_after"]))  # Q2
+    f0 = torch.as_tensor(g["xc_cumulative_full_in"]).to(dev)
+    f, _ = tmc.estimate_motion_cross_correlation_patches(movie, px, patch_sidelength=32, frequency_range=fr, deformation_field=f0)
+    assert float((f.cpu() - torch.as_tensor(g["xc_cumulative_full"])).abs().max()) <= SHIFT_PX * px
+
+
+@pytest.mark.parametrize("strategy", ["mean_except_current", "middle_frame"])
+def test_xc_patches_eviction_regime(dev, golden_eviction, strategy):
+    """T = 60 > 50: the cache-eviction regime of quirk Q1."""
+    g = golden_eviction
+    movie = torch.as_tensor(g["movie"].astype(np.float32)).to(dev)
+    fr = tuple(float(v) for v in g["frequency_range"])
+    f, _ = tmc.estimate_motion_cross_correlation_patches(
+        movie, 1.0, reference_strategy=strategy, patch_sidelength=32, frequency_range=fr,
+        temporal_smoothing=False, outlier_rejection=False,
+    )
+    assert float((f.cpu() - torch.as_tensor(g[f"xc_raw_{strategy}"])).abs().max()) <= SHIFT_PX
+
+
+def test_xc_patches_c1_golden(dev, golden_c1):
+    g = golden_c1
+    movie, _ = rp.synthetic_movie(10, 512, 512, seed=0, noise=1.0, drift=6.0, integer_shifts=True, sigma_f=0.08)
+    f, pos = tmc.estimate_motion_cross_correlation_patches(movie.to(dev), 1.0, patch_sidelength=128)
+    assert np.array_equal(pos.cpu().numpy(), g["xc_positions"])
+    assert float((f.cpu() - torch.as_tensor(g["xc_field"])).abs().max()) <= SHIFT_PX
+    s = tmc.correct_motion_sum(movie.to(dev), f, 1.0, grid_type="bspline").cpu()
+    want = torch.as_tensor(g["corrected_sum_rows"])
+    assert float(torch.linalg.norm(s[::64] - want) / torch.linalg.norm(want)) <= 1e-4
+
+
+def test_correct_motion_fast_golden(dev, golden_small):
+    g = golden_small
+    movie = torch.as_tensor(g["movie"]).to(dev)
+    field = torch.as_tensor(g["field_611"]).to(dev)
+    out = tmc.correct_motion_fast(movie, field)
+    want = torch.as_tensor(g["correct_fast"])
+    assert float(torch.linalg.norm(out.cpu() - want) / torch.linalg.norm(want)) <= 1e-4
+    assert torch.equal(field.cpu(), torch.as_tensor(g["correct_fast_field_after"]))  # Q2: negated in place
+    with pytest.raises(ValueError, match="Expected single patch deformation field"):
+        tmc.correct_motion_fast(movie, torch.zeros((2, 6, 2, 2), device=dev))
+    zero = torch.zeros((2, 6, 1, 1), device=dev)
+    assert torch.allclose(tmc.correct_motion_fast(movie, zero), movie, atol=1e-5)
+
+
+def test_unsupported_length_raises(dev):
+    with pytest.raises(NotImplementedError):
+        tmc.estimate_global_motion(torch.zeros((3, 96, 100), device=dev), 1.0)

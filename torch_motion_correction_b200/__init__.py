@@ -7,6 +7,7 @@ hand-written CUDA for sm_100a behind a C ABI (``include/tmc_b200.h``).  No CPU f
 
 from .correct_motion import (
     correct_motion,
+    correct_motion_fast,
     correct_motion_slow,
     correct_motion_sum,
     correct_motion_two_grids,
@@ -19,13 +20,20 @@ from .deformation_field_utils import (
     resample_deformation_field,
 )
 
+from .estimate_motion_xc import estimate_global_motion, estimate_motion_cross_correlation_patches
+from .patch_grid import patch_grid_centers
+from .utils import normalize_image
+
 __version__ = "0.1.0"
 
 __all__ = [
     "correct_motion",
     "correct_motion_two_grids",
+    "correct_motion_fast",
     "correct_motion_slow",
     "correct_motion_sum",
     "get_pixel_shifts",
     "evaluate_deformation_field",
+    "estimate_global_motion",
+    "estimate_motion_cross_correlation_patches",
 ]

@@ -1,0 +1,191 @@
+"""Host-side plans for the band-limited FFT kernels: cached tables (twiddles, masks, Fourier
+weights), band-box geometry, workspace chunking.  No arithmetic on image data happens here."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, query, stream_ptr
+
+_C64 = 8  # bytes per complex64
+#: intermediates of one chunk are kept below this many bytes so they stay L2-resident (126 MB)
+CHUNK_BYTES = int(os.environ.get("TMC_FFT_CHUNK_BYTES", str(96 << 20)))
+
+_twiddles: dict = {}
+_masks: dict = {}
+_weights: dict = {}
+
+
+def _dev_key(device: torch.device):
+    return (device.type, device.index)
+
+
+def twiddles(n: int, device: torch.device) -> torch.Tensor:
+    key = (_dev_key(device), n)
+    tw = _twiddles.get(key)
+    if tw is None:
+        tw = torch.empty((n, 2), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            call("tmc_fft_twiddles", n, ptr(tw), stream_ptr(device))
+        _twiddles[key] = tw
+    return tw
+
+
+def soft_disc_mask(shape, radius: float, smoothing_radius: float, device: torch.device):
+    """(mask (h, w) f32, ylo, yhi): ``torch_grid_utils.circle`` and a conservative row support."""
+    h, w = shape
+    key = (_dev_key(device), h, w, float(radius), float(smoothing_radius))
+    hit = _masks.get(key)
+    if hit is None:
+        mask = torch.empty((h, w), dtype=torch.float32, device=device)
+        ws = torch.empty((h,), dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            call("tmc_soft_disc_mask", h, w, float(radius), float(smoothing_radius), ptr(mask), ptr(ws), stream_ptr(device))
+        reach = int(radius + smoothing_radius) + 2
+        ylo, yhi = max(0, h // 2 - reach), min(h, h // 2 + reach + 1)
+        hit = (mask, ylo, yhi)
+        _masks[key] = hit
+    return hit
+
+
+def band_edges(frequency_range, pixel_spacing: float):
+    """(low, high) in cycles/px exactly as the reference computes them (utils.py:99-102; fp32)."""
+    cuton, cutoff_max = torch.as_tensor(frequency_range).float()
+    cutoff = torch.lerp(cuton, cutoff_max, 1.0)
+    low = torch.as_tensor(1 / cuton, dtype=torch.float32) * pixel_spacing
+    high = torch.as_tensor(1 / cutoff, dtype=torch.float32) * pixel_spacing
+    return float(low), float(high)
+
+
+def _max_index_within(n: int, high: float) -> int:
+    """Largest k in [0, n//2] with fl32(k * fl32(1/n)) <= high (-1 if none)."""
+    k = np.arange(n // 2 + 1, dtype=np.float32) * np.float32(1.0 / n)
+    ok = np.nonzero(k <= np.float32(high))[0]
+    return int(ok[-1]) if len(ok) else -1
+
+
+class BandPlan:
+    """Geometry + tables of one band-limited 2-D transform size."""
+
+    def __init__(self, ny: int, nx: int, device: torch.device, pixel_spacing: float | None = None,
+                 b_factor: float | None = None, frequency_range=None, full: bool = False):
+        for n in (ny, nx):
+            if not query("tmc_fft_supported_length", n):
+                raise NotImplementedError(
+                    f"transform length {n} is not supported: the sm_100a FFT kernels need power-of-two lengths in "
+                    f"[16, 8192] (patch side lengths / frame sizes)"
+                )
+        self.ny, self.nx, self.device = ny, nx, device
+        self.tw_y, self.tw_x = twiddles(ny, device), twiddles(nx, device)
+        if full:
+            self.kx, self.ky, self.ky_start, self.weight = nx // 2 + 1, ny, 0, None
+            return
+        low, high = band_edges(frequency_range, pixel_spacing)
+        kxm, kym = max(_max_index_within(nx, high), 0), max(_max_index_within(ny, high), 0)
+        self.kx = kxm + 1
+        if 2 * kym + 1 > ny:
+            self.ky, self.ky_start = ny, -(ny // 2)
+        else:
+            self.ky, self.ky_start = 2 * kym + 1, -kym
+        key = (_dev_key(device), ny, nx, float(pixel_spacing), float(b_factor), low, high)
+        wt = _weights.get(key)
+        if wt is None:
+            wt = torch.empty((self.ky, self.kx), dtype=torch.float32, device=device)
+            with torch.cuda.device(device):
+                call("tmc_band_weights", ny, nx, self.ky, self.kx, self.ky_start, low, high, 1, float(b_factor),
+                     float(pixel_spacing), 1, ptr(wt), stream_ptr(device))
+            _weights[key] = wt
+        self.weight = wt
+
+    @property
+    def plane_elems(self) -> int:
+        return self.ky * self.kx
+
+    # -- forward ------------------------------------------------------------------------------
+    def forward(self, image: torch.Tensor, mean_std, mask, ylo: int, yhi: int, jobs: torch.Tensor, out=None):
+        """jobs (njobs, 6) int32 device -> spectra (2*njobs, KY, KX) complex64 (as float pairs)."""
+        t, h, w = image.shape
+        njobs = jobs.shape[0]
+        dev = image.device
+        if out is None:
+            out = torch.empty((2 * njobs, self.ky, self.kx, 2), dtype=torch.float32, device=dev)
+        per_job = 2 * self.ny * self.kx * _C64
+        chunk = max(1, min(njobs, CHUNK_BYTES // per_job))
+        tmp = torch.empty((chunk * per_job // 4,), dtype=torch.float32, device=dev)
+        jobs_base, out_base = jobs.data_ptr(), out.data_ptr()
+        with torch.cuda.device(dev):
+            stream = stream_ptr(dev)
+            for j0 in range(0, njobs, chunk):
+                n = min(chunk, njobs - j0)
+                call("tmc_rfft2_band", ptr(image), t, h, w, ptr(mean_std), ptr(mask), self.ny, self.nx,
+                     jobs_base + j0 * 6 * 4, n, ylo, yhi, self.kx, self.ky, self.ky_start, ptr(self.weight),
+                     ptr(self.tw_x), ptr(self.tw_y), ptr(tmp), out_base + 2 * j0 * self.plane_elems * _C64, stream)
+        return out
+
+    # -- inverse + peak ---------------------------------------------------------------------------
+    def peaks(self, prod: torch.Tensor, sub_pixel: bool, shifts=None):
+        """prod (nitems, KY, KX, 2) -> (nitems, 2) px shifts (dy, dx)."""
+        nitems = prod.shape[0]
+        dev = prod.device
+        if shifts is None:
+            shifts = torch.empty((nitems, 2), dtype=torch.float32, device=dev)
+        per_item = self.ny * self.kx * _C64
+        chunk = max(1, min(nitems, CHUNK_BYTES // per_item))
+        tmp = torch.empty((chunk * per_item // 4,), dtype=torch.float32, device=dev)
+        nparts = query("tmc_xc_peak_partials", self.ny, self.nx)
+        partial = torch.empty((chunk * nparts * 2,), dtype=torch.float32, device=dev)
+        prod_base, shifts_base = prod.data_ptr(), shifts.data_ptr()
+        with torch.cuda.device(dev):
+            stream = stream_ptr(dev)
+            for i0 in range(0, nitems, chunk):
+                n = min(chunk, nitems - i0)
+                call("tmc_xc_peaks", prod_base + i0 * self.plane_elems * _C64, n, self.ny, self.nx, self.kx, self.ky,
+                     self.ky_start, int(sub_pixel), ptr(self.tw_x), ptr(self.tw_y), ptr(tmp), ptr(partial),
+                     shifts_base + i0 * 2 * 4, stream)
+        return shifts
+
+    def inverse_full(self, spec: torch.Tensor, out: torch.Tensor):
+        """spec (n, ny, nx/2+1, 2) -> out (n, ny, nx) real (irfftn, backward normalisation)."""
+        n = spec.shape[0]
+        dev = spec.device
+        per_item = self.ny * self.kx * _C64
+        chunk = max(1, min(n, (4 * CHUNK_BYTES) // per_item))
+        tmp = torch.empty((chunk * per_item // 4,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = stream_ptr(dev)
+            for i0 in range(0, n, chunk):
+                m = min(chunk, n - i0)
+                call("tmc_irfft2_full", spec.data_ptr() + i0 * per_item, m, self.ny, self.nx, ptr(self.tw_x), ptr(self.tw_y),
+                     ptr(tmp), out.data_ptr() + i0 * self.ny * self.nx * 4, stream)
+        return out
+
+
+def frame_pair_jobs(t: int, device: torch.device, frame_offset: int = 0) -> torch.Tensor:
+    """Whole-frame jobs packing frames (2i, 2i+1): plane index == frame index."""
+    rows = []
+    for i in range(0, t, 2):
+        fb = i + 1 if i + 1 < t else -1
+        rows.append([frame_offset + i, 1, (frame_offset + fb) if fb >= 0 else -1, 1, 0, 0])
+    return torch.tensor(rows, dtype=torch.int32).to(device, non_blocking=True)
+
+
+def pair_products(spec: torch.Tensor, ref_plane: torch.Tensor, cur_plane: torch.Tensor, plane_elems: int) -> torch.Tensor:
+    n = ref_plane.shape[0]
+    out = torch.empty((n, plane_elems, 2), dtype=torch.float32, device=spec.device)
+    with torch.cuda.device(spec.device):
+        call("tmc_xc_pair_products", ptr(spec), ptr(ref_plane), ptr(cur_plane), n, plane_elems, ptr(out),
+             stream_ptr(spec.device))
+    return out
+
+
+def leave_one_out_products(spec: torch.Tensor, t: int, g: int, plane_elems: int, delta_offsets, deltas) -> torch.Tensor:
+    out = torch.empty((t * g, plane_elems, 2), dtype=torch.float32, device=spec.device)
+    with torch.cuda.device(spec.device):
+        call("tmc_xc_leave_one_out_products", ptr(spec), t, g, plane_elems, ptr(delta_offsets), ptr(deltas), ptr(out),
+             stream_ptr(spec.device))
+    return out

@@ -39,6 +39,19 @@ _SIGNATURES = {
     "tmc_pixel_shifts": (I, [P, I, I, I, I, F, P, P]),
     "tmc_warp_dense_shifts": (I, [P, I, I, I, P, P, P]),
     "tmc_pixel_tyx": (I, [I, I, I, I, I, P, P]),
+    "tmc_fft_supported_length": (I, [I]),
+    "tmc_fft_twiddles": (I, [I, P, P]),
+    "tmc_rfft2_band": (I, [P, I, I, I, P, P, I, I, P, I, I, I, I, I, I, P, P, P, P, P, P]),
+    "tmc_xc_pair_products": (I, [P, P, P, I, L, P, P]),
+    "tmc_xc_leave_one_out_products": (I, [P, I, I, L, P, P, P, P]),
+    "tmc_xc_peak_partials": (I, [I, I]),
+    "tmc_xc_peaks": (I, [P, I, I, I, I, I, I, I, P, P, P, P, P, P]),
+    "tmc_irfft2_full": (I, [P, I, I, I, P, P, P, P, P]),
+    "tmc_fourier_shift": (I, [P, I, I, I, P, F, P]),
+    "tmc_soft_disc_mask": (I, [I, I, F, F, P, P, P]),
+    "tmc_band_weights": (I, [I, I, I, I, I, F, F, I, F, F, I, P, P]),
+    "tmc_xc_postprocess": (I, [P, I, I, F, I, I, F, I, I, I, P, P, P]),
+    "tmc_global_shifts_to_field": (I, [P, I, F, I, P, P]),
 }
 
 

@@ -31,6 +31,7 @@ def correct_motion(
     grad: bool = False,
     grid_type: str = "catmull_rom",
     device: torch.device = None,
+    _mean_std: torch.Tensor | None = None,
 ) -> torch.Tensor:
     """(t, h, w) movie warped by a (yx, nt, nh, nw) Angstrom field -> (t, h, w).
 
@@ -45,7 +46,42 @@ def correct_motion(
     gh, gw = field.shape[-2:]
     lattice = _ops.spline_lattice(field, grid_kind(grid_type), t, 10 * gh, 10 * gw)
     out = torch.empty_like(movie)
-    _ops.warp_lattice(movie, lattice, pixel_spacing, out_stack=out)
+    # _mean_std (internal): warp the normalised movie (image - mean) / std without materialising it
+    _ops.warp_lattice(movie, lattice, pixel_spacing, mean_std=_mean_std, out_stack=out)
+    return out
+
+
+def correct_motion_fast(
+    image: torch.Tensor,
+    deformation_grid: torch.Tensor,
+    device: torch.device = None,
+    _mean_std: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """Rigid per-frame Fourier phase shift for a (2, t, 1, 1) field.
+
+    Reference: correct_motion.py:430-498, including quirk Q2: the field is NEGATED IN PLACE (the
+    reference's ``shifts`` is a view of the caller's tensor) and its values are used as pixels."""
+    from . import _fourier
+    from ._lib import call, ptr, stream_ptr
+
+    if tuple(deformation_grid.shape[-2:]) != (1, 1):
+        raise ValueError(
+            f"Expected single patch deformation field with shape (2, t, 1, 1), "
+            f"but got shape {tuple(deformation_grid.shape)}. "
+            f"Final two dimensions must be (1, 1) for single patch correction."
+        )
+    dev = resolve_device(image, device)
+    movie = _movie(image, dev)
+    t, h, w = movie.shape
+    moved = deformation_grid.to(dev)
+    moved *= -1  # Q2: visible to the caller whenever .to() did not have to copy
+    field = moved.detach().to(torch.float32).contiguous()
+    plan = _fourier.BandPlan(h, w, dev, full=True)
+    spec = plan.forward(movie, _mean_std, None, 0, h, _fourier.frame_pair_jobs(t, dev))
+    with torch.cuda.device(dev):
+        call("tmc_fourier_shift", ptr(spec), t, h, w, ptr(field), 1.0, stream_ptr(dev))
+    out = torch.empty_like(movie)
+    plan.inverse_full(spec[:t], out)
     return out
 
 

@@ -1,0 +1,629 @@
+// Band-limited 2-D real DFTs of masked image patches / whole frames, cross-correlation
+// products, inverse transforms with fused peak search, Fourier-shift of whole frames.
+//
+// Replaces, for the hot path, what the reference does with torch.fft.rfftn / irfftn and
+// elementwise complex passes at estimate_motion_xc.py:77-123,338-369, correct_motion.py:484-496
+// and estimate_motion_optimizer.py:371-372.  Design notes:
+//  * a 2-D transform is a row pass and a column pass, each a batch of 1-D shared-memory FFTs
+//    (fft_core.cuh); only the kx / ky bins inside the band-pass box are ever written, so the
+//    intermediate is KX/(N/2+1) of a full spectrum and the outputs are band-limited;
+//  * two real rows are packed into one complex transform (the patch under two different mask
+//    powers -- quirk Q1 -- or two frames / two output rows);
+//  * rows outside the mask support are skipped; the inverse row pass feeds a block-wide argmax
+//    instead of storing the correlation surface.
+#include "common.cuh"
+#include "fft_core.cuh"
+
+namespace {
+
+using tmcfft::pad_idx;
+using tmcfft::padded_len;
+
+constexpr int kThreads = 256;
+
+__host__ __device__ constexpr int batch_for(int n) { return n >= 4096 ? 1 : (4096 / n > 16 ? 16 : 4096 / n); }
+
+template <int N>
+constexpr size_t fft_smem_bytes() {
+  return 2ull * batch_for(N) * padded_len(N) * sizeof(float2);
+}
+
+// ---- tables -----------------------------------------------------------------------------
+
+__global__ void twiddle_kernel(int n, float2* __restrict__ tw) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  double s, c;
+  sincospi(-2.0 * (double)m / (double)n, &s, &c);
+  tw[m] = make_float2((float)c, (float)s);
+}
+
+// ---- forward: row pass ---------------------------------------------------------------------
+
+struct RowJob {  // one packed pair of real rows-sets: a -> real part, b -> imaginary part
+  int frame_a, exp_a, frame_b, exp_b, y0, x0;
+};
+
+template <int NX>
+__global__ void __launch_bounds__(kThreads)
+rows_forward_kernel(const float* __restrict__ image, int H, int W, const float* __restrict__ mean_std,
+                    const float* __restrict__ mask, const int* __restrict__ jobs, int ylo, int yhi, int NY, int KX,
+                    const float2* __restrict__ tw, float2* __restrict__ tmp) {
+  constexpr int B = batch_for(NX);
+  constexpr int STRIDE = padded_len(NX);
+  extern __shared__ float2 smem[];
+  float2* a = smem;
+  float2* b = smem + B * STRIDE;
+  const int job = blockIdx.y;
+  const int fa = jobs[job * 6 + 0], ea = jobs[job * 6 + 1], fb = jobs[job * 6 + 2], eb = jobs[job * 6 + 3];
+  const int y0 = jobs[job * 6 + 4], x0 = jobs[job * 6 + 5];
+  const int row0 = ylo + blockIdx.x * B;
+  float mean = 0.f, stdv = 1.f;
+  const bool norm = mean_std != nullptr;
+  if (norm) {
+    mean = __ldg(mean_std);
+    stdv = __ldg(mean_std + 1);
+  }
+  const long fs = (long)H * W;
+  for (int idx = threadIdx.x; idx < B * NX; idx += kThreads) {
+    const int s = idx / NX, x = idx % NX;
+    const int y = row0 + s;
+    float2 z = make_float2(0.f, 0.f);
+    if (y < yhi) {
+      const float m = mask ? __ldg(mask + (long)y * NX + x) : 1.0f;
+      const long off = (long)(y0 + y) * W + x0 + x;
+      float va = __ldg(image + fa * fs + off);
+      if (norm) va = __fdiv_rn(__fsub_rn(va, mean), stdv);
+      for (int e = 0; e < ea; ++e) va = __fmul_rn(va, m);
+      z.x = va;
+      if (fb >= 0) {
+        float vb = (fb == fa) ? __ldg(image + fa * fs + off) : __ldg(image + fb * fs + off);
+        if (norm) vb = __fdiv_rn(__fsub_rn(vb, mean), stdv);
+        for (int e = 0; e < eb; ++e) vb = __fmul_rn(vb, m);
+        z.y = vb;
+      }
+    }
+    a[s * STRIDE + pad_idx(x)] = z;
+  }
+  __syncthreads();
+  const float2* r = tmcfft::fft_forward<NX, B, kThreads>(a, b, tw);
+  for (int idx = threadIdx.x; idx < B * KX; idx += kThreads) {
+    const int s = idx / KX, k = idx % KX;
+    const int y = row0 + s;
+    if (y >= yhi) continue;
+    const float2 zk = r[s * STRIDE + pad_idx(k)];
+    const float2 zn = r[s * STRIDE + pad_idx((NX - k) & (NX - 1))];
+    // Z = A + iB with A, B Hermitian:  A = (Z[k] + conj Z[-k]) / 2,  B = (Z[k] - conj Z[-k]) / 2i
+    tmp[((long)(2 * job) * NY + y) * KX + k] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+    if (fb >= 0) tmp[((long)(2 * job + 1) * NY + y) * KX + k] = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+  }
+}
+
+// ---- forward: column pass --------------------------------------------------------------------
+
+// plane p of tmp [NY][KX] -> out[p][KY][KX], ky = ky_start + kyb (wrapped), times weight[kyb][kx]
+template <int NY>
+__global__ void __launch_bounds__(kThreads)
+cols_forward_kernel(const float2* __restrict__ tmp, int ylo, int yhi, int KX, int KY, int ky_start,
+                    const float* __restrict__ weight, const float2* __restrict__ tw, float2* __restrict__ out) {
+  constexpr int B = batch_for(NY);
+  constexpr int STRIDE = padded_len(NY);
+  extern __shared__ float2 smem[];
+  float2* a = smem;
+  float2* b = smem + B * STRIDE;
+  const long plane = blockIdx.y;
+  const int kx0 = blockIdx.x * B;
+  const float2* src = tmp + plane * NY * KX;
+  for (int idx = threadIdx.x; idx < B * NY; idx += kThreads) {
+    const int s = idx % B, y = idx / B;
+    float2 z = make_float2(0.f, 0.f);
+    if (y >= ylo && y < yhi && kx0 + s < KX) z = src[(long)y * KX + kx0 + s];
+    a[s * STRIDE + pad_idx(y)] = z;
+  }
+  __syncthreads();
+  const float2* r = tmcfft::fft_forward<NY, B, kThreads>(a, b, tw);
+  float2* dst = out + plane * KY * KX;
+  for (int idx = threadIdx.x; idx < B * KY; idx += kThreads) {
+    const int s = idx % B, kyb = idx / B;
+    if (kx0 + s >= KX) continue;
+    const int y = (ky_start + kyb + NY) & (NY - 1);
+    float2 v = r[s * STRIDE + pad_idx(y)];
+    if (weight) {
+      const float wgt = __ldg(weight + (long)kyb * KX + kx0 + s);
+      v.x *= wgt;
+      v.y *= wgt;
+    }
+    dst[(long)kyb * KX + kx0 + s] = v;
+  }
+}
+
+// ---- cross-correlation products ------------------------------------------------------------
+
+// out[i] = conj(spec[ref_plane[i]]) * spec[cur_plane[i]]   (estimate_motion_xc.py:112,349)
+__global__ void xc_pair_product_kernel(const float2* __restrict__ spec, const int* __restrict__ ref_plane,
+                                       const int* __restrict__ cur_plane, long plane_elems, float2* __restrict__ out) {
+  const long i = blockIdx.y;
+  const float2* r = spec + (long)ref_plane[i] * plane_elems;
+  const float2* c = spec + (long)cur_plane[i] * plane_elems;
+  float2* o = out + i * plane_elems;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < plane_elems; e += (long)gridDim.x * blockDim.x)
+    o[e] = cmul_conj(r[e], c[e]);
+}
+
+// Leave-one-out reference with the reference's cache aliasing (quirk Q1).  Planes are laid out
+// [frame j][patch g][part] with part 0 = rfft2(mask P_j) W and part 1 = rfft2(mask^2 P_j) W.
+// Frame k's reference spectrum is  ( sum_{j != k} (c_kj ? part1_j : part0_j) ) / (T - 1)  where
+// c_kj in {0,1} says whether frame j had already been masked in place when frame k was processed.
+// c is given as per-k delta lists relative to k-1 (delta = +-(j+1)); T <= 50 gives c_kj = [j < k].
+__global__ void xc_leave_one_out_kernel(const float2* __restrict__ spec, int T, int G, long plane_elems,
+                                        const int* __restrict__ delta_offsets, const int* __restrict__ deltas,
+                                        float2* __restrict__ out) {
+  const int g = blockIdx.y;
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= plane_elems) return;
+  auto part = [&](int j, int p) { return spec[((long)(j * G + g) * 2 + p) * plane_elems + e]; };
+  float2 total = make_float2(0.f, 0.f);
+  for (int j = 0; j < T; ++j) total = cadd(total, part(j, 0));
+  float2 extra = make_float2(0.f, 0.f);  // sum_j c_kj (part1_j - part0_j)
+  const float cnt = (float)(T - 1);
+  for (int k = 0; k < T; ++k) {
+    for (int d = delta_offsets[k]; d < delta_offsets[k + 1]; ++d) {
+      const int v = deltas[d];
+      const int j = (v > 0 ? v : -v) - 1;
+      const float2 diff = csub(part(j, 1), part(j, 0));
+      extra = v > 0 ? cadd(extra, diff) : csub(extra, diff);
+    }
+    const float2 cur = part(k, 0);
+    float2 ref = cadd(csub(total, cur), extra);
+    ref.x = __fdiv_rn(ref.x, cnt);
+    ref.y = __fdiv_rn(ref.y, cnt);
+    out[((long)k * G + g) * plane_elems + e] = cmul_conj(ref, cur);
+  }
+}
+
+// ---- inverse: column pass --------------------------------------------------------------------
+
+// in[item][KY][KX] (ky = ky_start + kyb) -> tmp[item][NY][KX] = unnormalised inverse DFT along y
+template <int NY>
+__global__ void __launch_bounds__(kThreads)
+cols_inverse_kernel(const float2* __restrict__ in, int KX, int KY, int ky_start, const float2* __restrict__ tw,
+                    float2* __restrict__ tmp) {
+  constexpr int B = batch_for(NY);
+  constexpr int STRIDE = padded_len(NY);
+  extern __shared__ float2 smem[];
+  float2* a = smem;
+  float2* b = smem + B * STRIDE;
+  const long item = blockIdx.y;
+  const int kx0 = blockIdx.x * B;
+  for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
+  __syncthreads();
+  const float2* src = in + item * KY * KX;
+  for (int idx = threadIdx.x; idx < B * KY; idx += kThreads) {
+    const int s = idx % B, kyb = idx / B;
+    if (kx0 + s >= KX) continue;
+    const float2 v = src[(long)kyb * KX + kx0 + s];
+    const int y = (ky_start + kyb + NY) & (NY - 1);
+    a[s * STRIDE + pad_idx(y)] = make_float2(v.y, v.x);  // re/im swap: inverse via forward
+  }
+  __syncthreads();
+  const float2* r = tmcfft::fft_forward<NY, B, kThreads>(a, b, tw);
+  float2* dst = tmp + item * NY * KX;
+  for (int idx = threadIdx.x; idx < B * NY; idx += kThreads) {
+    const int s = idx % B, y = idx / B;
+    if (kx0 + s >= KX) continue;
+    const float2 v = r[s * STRIDE + pad_idx(y)];
+    dst[(long)y * KX + kx0 + s] = make_float2(v.y, v.x);
+  }
+}
+
+// ---- inverse: row pass (complex-to-real, two rows per transform) ------------------------------
+
+// builds the packed spectrum of rows ya (real part) and yb (imaginary part) in `a`, re/im swapped
+template <int NX>
+__device__ __forceinline__ void load_c2r_pair(const float2* __restrict__ rowa, const float2* __restrict__ rowb, int KX,
+                                              float2* __restrict__ a_seq) {
+  for (int k = threadIdx.x; k < KX; k += kThreads) {
+    float2 ca = rowa[k];
+    float2 cb = rowb ? rowb[k] : make_float2(0.f, 0.f);
+    if (k == 0 || 2 * k == NX) {  // c2r ignores the imaginary part of the DC / Nyquist bins
+      a_seq[pad_idx(k)] = make_float2(cb.x, ca.x);
+    } else {
+      // Z[k] = Ca + i Cb ; Z[N-k] = conj(Ca) + i conj(Cb) ; stored swapped (im, re)
+      a_seq[pad_idx(k)] = make_float2(ca.y + cb.x, ca.x - cb.y);
+      a_seq[pad_idx(NX - k)] = make_float2(cb.x - ca.y, ca.x + cb.y);
+    }
+  }
+}
+
+struct PeakCandidate {
+  float val;
+  int idx;
+};
+
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+// tmp[item][NY][KX] -> per-CTA maximum of the real correlation surface: partial[item][blockIdx.x]
+template <int NX>
+__global__ void __launch_bounds__(kThreads)
+rows_inverse_argmax_kernel(const float2* __restrict__ tmp, int NY, int KX, const float2* __restrict__ tw,
+                           PeakCandidate* __restrict__ partial) {
+  constexpr int B = batch_for(NX);
+  constexpr int STRIDE = padded_len(NX);
+  extern __shared__ float2 smem[];
+  float2* a = smem;
+  float2* b = smem + B * STRIDE;
+  const long item = blockIdx.y;
+  const int row0 = blockIdx.x * 2 * B;
+  const float2* src = tmp + item * NY * KX;
+  for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
+  __syncthreads();
+  for (int s = 0; s < B; ++s) {
+    const int ya = row0 + 2 * s, yb = ya + 1;
+    if (ya < NY) load_c2r_pair<NX>(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, a + s * STRIDE);
+  }
+  __syncthreads();
+  const float2* r = tmcfft::fft_forward<NX, B, kThreads>(a, b, tw);
+  float best = -INFINITY;
+  int best_idx = 0x7fffffff;
+  for (int idx = threadIdx.x; idx < B * NX; idx += kThreads) {
+    const int s = idx / NX, x = idx % NX;
+    const int ya = row0 + 2 * s;
+    if (ya >= NY) continue;
+    const float2 v = r[s * STRIDE + pad_idx(x)];  // swapped: v.y = row ya, v.x = row ya+1
+    const int ia = ya * NX + x;
+    if (better(v.y, ia, best, best_idx)) {
+      best = v.y;
+      best_idx = ia;
+    }
+    if (ya + 1 < NY && better(v.x, ia + NX, best, best_idx)) {
+      best = v.x;
+      best_idx = ia + NX;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    if (better(ov, oi, best, best_idx)) {
+      best = ov;
+      best_idx = oi;
+    }
+  }
+  __shared__ float sval[kThreads / 32];
+  __shared__ int sidx[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) {
+    sval[threadIdx.x >> 5] = best;
+    sidx[threadIdx.x >> 5] = best_idx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < kThreads / 32; ++i)
+      if (better(sval[i], sidx[i], best, best_idx)) {
+        best = sval[i];
+        best_idx = sidx[i];
+      }
+    PeakCandidate c;
+    c.val = best;
+    c.idx = best_idx;
+    partial[item * gridDim.x + blockIdx.x] = c;
+  }
+}
+
+// tmp[item][NY][KX] -> out[item][NY][NX] real, scaled (irfftn "backward" normalisation)
+template <int NX>
+__global__ void __launch_bounds__(kThreads)
+rows_inverse_store_kernel(const float2* __restrict__ tmp, int NY, int KX, const float2* __restrict__ tw, float scale,
+                          float* __restrict__ out) {
+  constexpr int B = batch_for(NX);
+  constexpr int STRIDE = padded_len(NX);
+  extern __shared__ float2 smem[];
+  float2* a = smem;
+  float2* b = smem + B * STRIDE;
+  const long item = blockIdx.y;
+  const int row0 = blockIdx.x * 2 * B;
+  const float2* src = tmp + item * NY * KX;
+  for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
+  __syncthreads();
+  for (int s = 0; s < B; ++s) {
+    const int ya = row0 + 2 * s, yb = ya + 1;
+    if (ya < NY) load_c2r_pair<NX>(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, a + s * STRIDE);
+  }
+  __syncthreads();
+  const float2* r = tmcfft::fft_forward<NX, B, kThreads>(a, b, tw);
+  float* dst = out + item * NY * NX;
+  for (int idx = threadIdx.x; idx < B * NX; idx += kThreads) {
+    const int s = idx / NX, x = idx % NX;
+    const int ya = row0 + 2 * s;
+    if (ya >= NY) continue;
+    const float2 v = r[s * STRIDE + pad_idx(x)];
+    dst[(long)ya * NX + x] = v.y * scale;
+    if (ya + 1 < NY) dst[(long)(ya + 1) * NX + x] = v.x * scale;
+  }
+}
+
+// ---- peak finalisation: argmax over CTAs, 3-point parabola, wrap ---------------------------
+
+// value of the real surface at (y, x) from the column-transformed rows (direct KX-term sum)
+__device__ __forceinline__ float direct_value(const float2* __restrict__ row, int KX, int NX, int x) {
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < KX; k += blockDim.x) {
+    const float2 c = row[k];
+    if (k == 0 || 2 * k == NX) {
+      const float sgn = (k != 0 && (x & 1)) ? -1.f : 1.f;
+      acc += sgn * c.x;
+    } else {
+      float s, co;
+      const int m = (int)(((long)k * x) % NX);
+      sincospif(2.0f * (float)m / (float)NX, &s, &co);
+      acc += 2.0f * (c.x * co - c.y * s);
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float block_sum_128(float v, float* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return sh[0] + sh[1] + sh[2] + sh[3];
+}
+
+// shifts[item] = (sy, sx) in px: estimate_motion_xc.py:354-369,414-483 (quirks Q6, Q7)
+__global__ void __launch_bounds__(128)
+peak_finalize_kernel(const float2* __restrict__ tmp, const PeakCandidate* __restrict__ partial, int nparts, int NY, int NX,
+                     int KX, int sub_pixel, float* __restrict__ shifts) {
+  __shared__ float sh[4];
+  __shared__ int s_idx;
+  const long item = blockIdx.x;
+  if (threadIdx.x == 0) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = 0; i < nparts; ++i) {
+      const PeakCandidate c = partial[item * nparts + i];
+      if (better(c.val, c.idx, best, bi)) {
+        best = c.val;
+        bi = c.idx;
+      }
+    }
+    s_idx = bi;
+  }
+  __syncthreads();
+  const int y = s_idx / NX, x = s_idx % NX;
+  float py = (float)y, px = (float)x;
+  if (sub_pixel && y >= 1 && y < NY - 1 && x >= 1 && x < NX - 1) {
+    const float2* rows = tmp + item * NY * KX;
+    const float v0 = block_sum_128(direct_value(rows + (long)y * KX, KX, NX, x), sh);
+    const float vym = block_sum_128(direct_value(rows + (long)(y - 1) * KX, KX, NX, x), sh);
+    const float vyp = block_sum_128(direct_value(rows + (long)(y + 1) * KX, KX, NX, x), sh);
+    const float vxm = block_sum_128(direct_value(rows + (long)y * KX, KX, NX, x - 1), sh);
+    const float vxp = block_sum_128(direct_value(rows + (long)y * KX, KX, NX, x + 1), sh);
+    if (vyp != vym) py += 0.5f * (vym - vyp) / (vym - 2.0f * v0 + vyp);
+    if (vxp != vxm) px += 0.5f * (vxm - vxp) / (vxm - 2.0f * v0 + vxp);
+  }
+  if (threadIdx.x == 0) {
+    shifts[item * 2 + 0] = (py <= (float)(NY / 2)) ? py : py - (float)NY;
+    shifts[item * 2 + 1] = (px <= (float)(NX / 2)) ? px : px - (float)NX;
+  }
+}
+
+// ---- whole-frame Fourier shift (correct_motion_fast) -----------------------------------------
+
+// spec[f][NY][KX] *= exp(-2 pi i (fy sy + fx sx)), shifts = sign * field[(c, f)] (field (2, T, 1, 1))
+__global__ void fourier_shift_kernel(float2* __restrict__ spec, int T, int NY, int NX, int KX, const float* __restrict__ field,
+                                     float sign) {
+  const int f = blockIdx.z, ky = blockIdx.y;
+  const int kx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (kx >= KX) return;
+  const float sy = sign * __ldg(field + f), sx = sign * __ldg(field + T + f);
+  // torch.fft.fftfreq: integer index times fp32(1/n)
+  const float fy = __fmul_rn((float)(ky < (NY + 1) / 2 ? ky : ky - NY), (float)(1.0 / (double)NY));
+  const float fx = __fmul_rn((float)kx, (float)(1.0 / (double)NX));
+  const float c = -6.283185307179586f;  // fp32(-2 pi)
+  const float ang = __fadd_rn(__fmul_rn(__fmul_rn(c, fy), sy), __fmul_rn(__fmul_rn(c, fx), sx));
+  float s, co;
+  sincosf(ang, &s, &co);
+  float2* p = spec + ((long)f * NY + ky) * KX + kx;
+  *p = cmul(*p, make_float2(co, s));
+}
+
+// ---- dispatch helpers ------------------------------------------------------------------------
+
+#define TMC_FOR_EACH_N(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
+
+inline bool supported_n(int n) { return n >= 16 && n <= 8192 && (n & (n - 1)) == 0; }
+
+template <typename K>
+int enable_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      tmc_set_error("cudaFuncSetAttribute(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      return TMC_ERR_CUDA;
+    }
+  }
+  return TMC_OK;
+}
+
+}  // namespace
+
+// ---- C ABI ---------------------------------------------------------------------------------------
+
+TMC_API int tmc_fft_supported_length(int n) { return supported_n(n) ? 1 : 0; }
+
+// tw: n complex64 values exp(-2 pi i m / n)
+TMC_API int tmc_fft_twiddles(int n, void* tw, cudaStream_t stream) {
+  TMC_CHECK_ARG(tw && n >= 2, "fft_twiddles: bad arguments");
+  twiddle_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(n, (float2*)tw);
+  TMC_CHECK_LAUNCH("tmc_fft_twiddles");
+  return TMC_OK;
+}
+
+// Band-limited forward 2-D real DFT of masked image windows.
+//  image (T,H,W) f32; mean_std nullable device float[2]; mask (ny,nx) f32 nullable;
+//  jobs (njobs,6) int32 device = {frame_a, exp_a, frame_b (-1: none), exp_b, y0, x0};
+//  rows [ylo,yhi) are the only non-zero rows of the mask; kx in [0,KX), ky in [ky_start, ky_start+KY);
+//  weight (KY,KX) f32 nullable; tw_x/tw_y twiddles for nx/ny; tmp: 2*njobs*ny*KX complex64;
+//  out: (2*njobs, KY, KX) complex64, plane 2*job+0 = a, 2*job+1 = b.
+TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float* mean_std, const float* mask, int ny, int nx,
+                           const int* jobs, int njobs, int ylo, int yhi, int kx_count, int ky_count, int ky_start,
+                           const float* weight, const void* tw_x, const void* tw_y, void* tmp, void* out,
+                           cudaStream_t stream) {
+  TMC_CHECK_ARG(image && jobs && tw_x && tw_y && tmp && out, "rfft2_band: null pointer");
+  TMC_CHECK_ARG(njobs >= 0 && t >= 1 && h >= ny && w >= nx, "rfft2_band: window (%d,%d) larger than image (%d,%d)", ny, nx, h, w);
+  TMC_CHECK_ARG(0 <= ylo && ylo <= yhi && yhi <= ny, "rfft2_band: bad row support [%d,%d)", ylo, yhi);
+  TMC_CHECK_ARG(kx_count >= 1 && kx_count <= nx / 2 + 1 && ky_count >= 1 && ky_count <= ny, "rfft2_band: bad band box");
+  if (!supported_n(nx) || !supported_n(ny)) {
+    tmc_set_error("rfft2_band: transform lengths must be powers of two in [16, 8192], got (%d, %d)", ny, nx);
+    return TMC_ERR_UNSUPPORTED;
+  }
+  if (njobs == 0) return TMC_OK;
+  bool done = false;
+#define ROWS(N)                                                                                                  \
+  if (nx == N) {                                                                                                 \
+    if (int e = enable_smem(rows_forward_kernel<N>, fft_smem_bytes<N>())) return e;                              \
+    dim3 grid(tmc_div_up(yhi - ylo, batch_for(N)), njobs);                                                       \
+    if (yhi > ylo)                                                                                               \
+      rows_forward_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                                   \
+          image, h, w, mean_std, mask, jobs, ylo, yhi, ny, kx_count, (const float2*)tw_x, (float2*)tmp);         \
+    done = true;                                                                                                 \
+  }
+  TMC_FOR_EACH_N(ROWS)
+#undef ROWS
+  TMC_CHECK_ARG(done, "rfft2_band: unsupported nx %d", nx);
+  TMC_CHECK_LAUNCH("tmc_rfft2_band(rows)");
+  done = false;
+#define COLS(N)                                                                                                       \
+  if (ny == N) {                                                                                                      \
+    if (int e = enable_smem(cols_forward_kernel<N>, fft_smem_bytes<N>())) return e;                                   \
+    dim3 grid(tmc_div_up(kx_count, batch_for(N)), 2 * njobs);                                                         \
+    cols_forward_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>((const float2*)tmp, ylo, yhi, kx_count,  \
+                                                                           ky_count, ky_start, weight,               \
+                                                                           (const float2*)tw_y, (float2*)out);       \
+    done = true;                                                                                                      \
+  }
+  TMC_FOR_EACH_N(COLS)
+#undef COLS
+  TMC_CHECK_ARG(done, "rfft2_band: unsupported ny %d", ny);
+  TMC_CHECK_LAUNCH("tmc_rfft2_band(cols)");
+  return TMC_OK;
+}
+
+// out[i] = conj(spec[ref_plane[i]]) * spec[cur_plane[i]], planes of plane_elems complex64
+TMC_API int tmc_xc_pair_products(const void* spec, const int* ref_plane, const int* cur_plane, int nitems, long plane_elems,
+                                 void* out, cudaStream_t stream) {
+  TMC_CHECK_ARG(spec && ref_plane && cur_plane && out && nitems >= 0 && plane_elems >= 1, "xc_pair_products: bad arguments");
+  if (nitems == 0) return TMC_OK;
+  dim3 grid((unsigned)(tmc_div_up(plane_elems, 256) < 64 ? tmc_div_up(plane_elems, 256) : 64), nitems);
+  xc_pair_product_kernel<<<grid, 256, 0, stream>>>((const float2*)spec, ref_plane, cur_plane, plane_elems, (float2*)out);
+  TMC_CHECK_LAUNCH("tmc_xc_pair_products");
+  return TMC_OK;
+}
+
+// spec planes [T][G][2]; out items [T][G]; delta lists: offsets (T+1) and signed (j+1) entries
+TMC_API int tmc_xc_leave_one_out_products(const void* spec, int t, int g, long plane_elems, const int* delta_offsets,
+                                          const int* deltas, void* out, cudaStream_t stream) {
+  TMC_CHECK_ARG(spec && delta_offsets && deltas && out && t >= 2 && g >= 1 && plane_elems >= 1,
+                "xc_leave_one_out_products: bad arguments (need t >= 2)");
+  dim3 grid(tmc_div_up(plane_elems, 128), g);
+  xc_leave_one_out_kernel<<<grid, 128, 0, stream>>>((const float2*)spec, t, g, plane_elems, delta_offsets, deltas,
+                                                    (float2*)out);
+  TMC_CHECK_LAUNCH("tmc_xc_leave_one_out_products");
+  return TMC_OK;
+}
+
+TMC_API int tmc_xc_peak_partials(int ny, int nx) { return supported_n(nx) ? tmc_div_up(ny, 2 * batch_for(nx)) : -1; }
+
+// Inverse 2-D transform of band-limited products + argmax (+ parabola) + wrap.
+//  prod (nitems, KY, KX) complex64; tmp: nitems*ny*KX complex64; partial: nitems*tmc_xc_peak_partials(ny,nx)*8 bytes;
+//  shifts (nitems, 2) f32 = (dy, dx) px.
+TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_count, int ky_count, int ky_start,
+                         int sub_pixel, const void* tw_x, const void* tw_y, void* tmp, void* partial, float* shifts,
+                         cudaStream_t stream) {
+  TMC_CHECK_ARG(prod && tw_x && tw_y && tmp && partial && shifts, "xc_peaks: null pointer");
+  TMC_CHECK_ARG(kx_count >= 1 && kx_count <= nx / 2 + 1 && ky_count >= 1 && ky_count <= ny, "xc_peaks: bad band box");
+  if (!supported_n(nx) || !supported_n(ny)) {
+    tmc_set_error("xc_peaks: transform lengths must be powers of two in [16, 8192], got (%d, %d)", ny, nx);
+    return TMC_ERR_UNSUPPORTED;
+  }
+  if (nitems == 0) return TMC_OK;
+  bool done = false;
+#define COLS(N)                                                                                                  \
+  if (ny == N) {                                                                                                 \
+    if (int e = enable_smem(cols_inverse_kernel<N>, fft_smem_bytes<N>())) return e;                              \
+    dim3 grid(tmc_div_up(kx_count, batch_for(N)), nitems);                                                       \
+    cols_inverse_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                                     \
+        (const float2*)prod, kx_count, ky_count, ky_start, (const float2*)tw_y, (float2*)tmp);                   \
+    done = true;                                                                                                 \
+  }
+  TMC_FOR_EACH_N(COLS)
+#undef COLS
+  TMC_CHECK_ARG(done, "xc_peaks: unsupported ny %d", ny);
+  TMC_CHECK_LAUNCH("tmc_xc_peaks(cols)");
+  const int nparts = tmc_xc_peak_partials(ny, nx);
+  done = false;
+#define ROWS(N)                                                                                                   \
+  if (nx == N) {                                                                                                  \
+    if (int e = enable_smem(rows_inverse_argmax_kernel<N>, fft_smem_bytes<N>())) return e;                        \
+    dim3 grid(nparts, nitems);                                                                                    \
+    rows_inverse_argmax_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                               \
+        (const float2*)tmp, ny, kx_count, (const float2*)tw_x, (PeakCandidate*)partial);                          \
+    done = true;                                                                                                  \
+  }
+  TMC_FOR_EACH_N(ROWS)
+#undef ROWS
+  TMC_CHECK_ARG(done, "xc_peaks: unsupported nx %d", nx);
+  TMC_CHECK_LAUNCH("tmc_xc_peaks(rows)");
+  peak_finalize_kernel<<<nitems, 128, 0, stream>>>((const float2*)tmp, (const PeakCandidate*)partial, nparts, ny, nx,
+                                                   kx_count, sub_pixel, shifts);
+  TMC_CHECK_LAUNCH("tmc_xc_peaks(finalize)");
+  return TMC_OK;
+}
+
+// Full inverse: spec (nitems, ny, nx/2+1) complex64 -> out (nitems, ny, nx) f32 (irfftn, backward norm)
+TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const void* tw_x, const void* tw_y, void* tmp,
+                            float* out, cudaStream_t stream) {
+  TMC_CHECK_ARG(spec && tw_x && tw_y && tmp && out, "irfft2_full: null pointer");
+  if (!supported_n(nx) || !supported_n(ny)) {
+    tmc_set_error("irfft2_full: transform lengths must be powers of two in [16, 8192], got (%d, %d)", ny, nx);
+    return TMC_ERR_UNSUPPORTED;
+  }
+  if (nitems == 0) return TMC_OK;
+  const int kx = nx / 2 + 1;
+  bool done = false;
+#define COLS(N)                                                                                                  \
+  if (ny == N) {                                                                                                 \
+    if (int e = enable_smem(cols_inverse_kernel<N>, fft_smem_bytes<N>())) return e;                              \
+    dim3 grid(tmc_div_up(kx, batch_for(N)), nitems);                                                             \
+    cols_inverse_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>((const float2*)spec, kx, ny, 0,      \
+                                                                           (const float2*)tw_y, (float2*)tmp);   \
+    done = true;                                                                                                 \
+  }
+  TMC_FOR_EACH_N(COLS)
+#undef COLS
+  TMC_CHECK_ARG(done, "irfft2_full: unsupported ny %d", ny);
+  done = false;
+#define ROWS(N)                                                                                                    \
+  if (nx == N) {                                                                                                   \
+    if (int e = enable_smem(rows_inverse_store_kernel<N>, fft_smem_bytes<N>())) return e;                          \
+    dim3 grid(tmc_div_up(ny, 2 * batch_for(N)), nitems);                                                           \
+    rows_inverse_store_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                                 \
+        (const float2*)tmp, ny, kx, (const float2*)tw_x, 1.0f / ((float)nx * (float)ny), out);                     \
+    done = true;                                                                                                   \
+  }
+  TMC_FOR_EACH_N(ROWS)
+#undef ROWS
+  TMC_CHECK_ARG(done, "irfft2_full: unsupported nx %d", nx);
+  TMC_CHECK_LAUNCH("tmc_irfft2_full");
+  return TMC_OK;
+}
+
+// spec (t, ny, nx/2+1) *= exp(-2 pi i (fy sy + fx sx)); (sy, sx) = sign * field (2, t) (device)
+TMC_API int tmc_fourier_shift(void* spec, int t, int ny, int nx, const float* field, float sign, cudaStream_t stream) {
+  TMC_CHECK_ARG(spec && field && t >= 1 && ny >= 1 && nx >= 2, "fourier_shift: bad arguments");
+  const int kx = nx / 2 + 1;
+  dim3 grid(tmc_div_up(kx, 128), ny, t);
+  fourier_shift_kernel<<<grid, 128, 0, stream>>>((float2*)spec, t, ny, nx, kx, field, sign);
+  TMC_CHECK_LAUNCH("tmc_fourier_shift");
+  return TMC_OK;
+}

@@ -1,0 +1,110 @@
+// One-off tables, built on the device so no estimator call ever touches the host:
+//  * the soft-edged circular real-space mask  (torch_grid_utils.circle)
+//  * the band-limited Fourier weight  bandpass * b_envelope  (torch_fourier_filter; A.5),
+//    evaluated only on the band-pass bounding box that the FFT kernels keep.
+// Reference call sites: estimate_motion_xc.py:69-74,81-95,262-280; estimate_motion_optimizer.py:162-184;
+// utils.py:87-114.
+#include "common.cuh"
+
+namespace {
+
+// half-width of the disc on every row: largest dx with sqrt(dy^2 + dx^2) < radius (fp32, like
+// coordinate_grid(norm=True) < radius), or -1 if the row misses the disc
+__global__ void disc_rows_kernel(int h, int w, int cy, int cx, float radius, int* __restrict__ half_width) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= h) return;
+  const float dy = (float)(y - cy);
+  const float dy2 = __fmul_rn(dy, dy);
+  int r = -1;
+  const int max_dx = max(cx, w - 1 - cx);
+  for (int dx = 0; dx <= max_dx; ++dx) {
+    const float fx = (float)dx;
+    const float d = __fsqrt_rn(__fadd_rn(dy2, __fmul_rn(fx, fx)));
+    if (d < radius)
+      r = dx;
+    else
+      break;
+  }
+  half_width[y] = r;
+}
+
+// exact Euclidean distance transform of the complement of the disc, restricted to the soft edge
+__global__ void soft_disc_kernel(int h, int w, int cy, int cx, float radius, float smoothing, const int* __restrict__ half_width,
+                                 float* __restrict__ mask) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const int adx = abs(x - cx);
+  const int hw = half_width[y];
+  float value = 0.f;
+  if (hw >= 0 && adx <= hw) {
+    value = 1.f;
+  } else if (smoothing > 0.f &&
+             sqrtf((float)(y - cy) * (float)(y - cy) + (float)(x - cx) * (float)(x - cx)) <= radius + smoothing + 2.f) {
+    const int reach = (int)ceilf(smoothing) + 1;
+    long best = -1;
+    for (int yy = max(0, y - reach); yy <= min(h - 1, y + reach); ++yy) {
+      const int r = half_width[yy];
+      if (r < 0) continue;
+      // nearest member of the run [cx - r, cx + r] clipped to the image
+      const int lo = max(0, cx - r), hi = min(w - 1, cx + r);
+      const long gx = x < lo ? lo - x : (x > hi ? x - hi : 0);
+      const long gy = y - yy;
+      const long d2 = gx * gx + gy * gy;
+      if (best < 0 || d2 < best) best = d2;
+    }
+    if (best > 0) {
+      const float edt = (float)sqrt((double)best);  // scipy EDT is float64, then .float()
+      if (edt <= smoothing) value = cosf(__fmul_rn(1.5707963267948966f, __fdiv_rn(edt, smoothing)));
+    }
+  }
+  mask[(long)y * w + x] = value;
+}
+
+// weight[kyb][kx] for ky = ky_start + kyb, kx in [0, KX): (low < f <= high) * exp(-B (f/px)^2 / 4)
+__global__ void band_weight_kernel(int ny, int nx, int KY, int KX, int ky_start, float low, float high, int use_band,
+                                   float b_factor, float pixel_size, int use_envelope, float* __restrict__ weight) {
+  const int kx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int kyb = blockIdx.y;
+  if (kx >= KX) return;
+  int ky = ky_start + kyb;  // signed frequency index
+  ky = ((ky % ny) + ny) % ny;
+  if (ky >= (ny + 1) / 2) ky -= ny;
+  // torch.fft.fftfreq / rfftfreq: integer index times fp32(1/n)
+  const float fy = __fmul_rn((float)ky, (float)(1.0 / (double)ny));
+  const float fx = __fmul_rn((float)kx, (float)(1.0 / (double)nx));
+  const float f = __fsqrt_rn(__fadd_rn(__fmul_rn(fy, fy), __fmul_rn(fx, fx)));
+  float v = 1.f;
+  if (use_band && !(f > low && f <= high)) v = 0.f;
+  if (use_envelope && v != 0.f) {
+    const float fp = __fdiv_rn(f, pixel_size);
+    v *= expf(-__fdiv_rn(__fmul_rn(b_factor, __fmul_rn(fp, fp)), 4.0f));
+  }
+  weight[(long)kyb * KX + kx] = v;
+}
+
+}  // namespace
+
+// mask (h, w) f32; workspace: h ints.  Non-zero rows lie within |y - h/2| <= radius + smoothing_radius.
+TMC_API int tmc_soft_disc_mask(int h, int w, float radius, float smoothing_radius, float* mask, int* workspace,
+                               cudaStream_t stream) {
+  TMC_CHECK_ARG(mask && workspace && h >= 1 && w >= 1 && radius >= 0.f && smoothing_radius >= 0.f,
+                "soft_disc_mask: bad arguments");
+  const int cy = h / 2, cx = w / 2;  // torch_grid_utils: centre = shape // 2
+  disc_rows_kernel<<<tmc_div_up(h, 128), 128, 0, stream>>>(h, w, cy, cx, radius, workspace);
+  dim3 grid(tmc_div_up(w, 128), h);
+  soft_disc_kernel<<<grid, 128, 0, stream>>>(h, w, cy, cx, radius, smoothing_radius, workspace, mask);
+  TMC_CHECK_LAUNCH("tmc_soft_disc_mask");
+  return TMC_OK;
+}
+
+TMC_API int tmc_band_weights(int ny, int nx, int ky_count, int kx_count, int ky_start, float low, float high, int use_band,
+                             float b_factor, float pixel_size, int use_envelope, float* weight, cudaStream_t stream) {
+  TMC_CHECK_ARG(weight && ny >= 1 && nx >= 1 && ky_count >= 1 && kx_count >= 1 && kx_count <= nx / 2 + 1 && pixel_size > 0.f,
+                "band_weights: bad arguments");
+  dim3 grid(tmc_div_up(kx_count, 128), ky_count);
+  band_weight_kernel<<<grid, 128, 0, stream>>>(ny, nx, ky_count, kx_count, ky_start, low, high, use_band, b_factor,
+                                              pixel_size, use_envelope, weight);
+  TMC_CHECK_LAUNCH("tmc_band_weights");
+  return TMC_OK;
+}
