@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""Headline benchmark: movies/s for a 40x4096x4096 fp32 movie through estimate + correct.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one movie through ``motion_correct`` (whole-frame XC -> rigid pre-correction ->
+patch XC -> [spline optimiser] -> fused warp-and-sum).  At N > 1 (torchrun, one rank per GPU) every
+rank aligns its own movie (independent movies, no data-path collective: weak scaling) and the value
+is total movies / max-over-ranks device time.  Prints ONE JSON line (rank 0).
+
+``--impl reference`` times the CPU oracle (restatement of the reference's PyTorch path; the
+reference itself cannot be installed offline) on a bounded sample of the workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: K3-like 40-frame 4096^2 movie, global + (3,5,5) spline local motion
+    "c2": dict(t=40, h=4096, w=4096, pixel_spacing=0.83, patch=1024, resolution=(3, 5, 5)),
+    # reduced shapes for quick functional runs (NOT the headline; selected only with --workload)
+    "c1": dict(t=10, h=512, w=512, pixel_spacing=1.0, patch=128, resolution=(3, 5, 5)),
+    "mid": dict(t=16, h=2048, w=2048, pixel_spacing=0.83, patch=512, resolution=(3, 5, 5)),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--iterations", type=int, default=int(os.environ.get("TMC_BENCH_ITERATIONS", "-1")),
+                    help="spline-optimiser iterations per movie (-1: default of the build)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic data
+# --------------------------------------------------------------------------------------------
+
+
+def synthetic_movie_gpu(t, h, w, seed, device):
+    """Band-limited random specimen, integer global drift (<= +-6 px), unit Gaussian noise."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    pad = 16
+    H, W = h + 2 * pad, w + 2 * pad
+    white = torch.randn((H, W), generator=g, device=device)
+    fy = torch.fft.fftfreq(H, device=device)[:, None]
+    fx = torch.fft.rfftfreq(W, device=device)[None, :]
+    spec = torch.fft.rfftn(white) * torch.exp(-(fy**2 + fx**2) / (2 * 0.08**2))
+    specimen = torch.fft.irfftn(spec, s=(H, W))
+    specimen = specimen / specimen.std()
+    del white, spec
+    cpu_g = torch.Generator().manual_seed(seed)
+    walk = torch.cumsum(torch.randn((t, 2), generator=cpu_g), dim=0)
+    walk = walk - walk[t // 2]
+    walk = torch.round(walk / max(float(walk.abs().max()), 1e-6) * 6.0).long()
+    movie = torch.empty((t, h, w), dtype=torch.float32, device=device)
+    for k in range(t):
+        sy, sx = int(walk[k, 0]), int(walk[k, 1])
+        movie[k] = specimen[pad - sy : pad - sy + h, pad - sx : pad - sx + w]
+        movie[k] += torch.randn((h, w), generator=g, device=device)
+    return movie, walk
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {
+            "sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# --------------------------------------------------------------------------------------------
+# roofline bookkeeping: ALGORITHMIC bytes per C-ABI entry point
+# --------------------------------------------------------------------------------------------
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(cfg, iterations):
+    """Per movie, per entry point: the bytes the ALGORITHM must move (not what a kernel happens to)."""
+    t, h, w, p = cfg["t"], cfg["h"], cfg["w"], cfg["patch"]
+    frame = 4 * h * w
+    return {
+        # read every frame once, write one sum
+        "tmc_warp_lattice": t * frame + frame,
+        # central 50% box of every frame
+        "tmc_stack_stats": t * frame // 4,
+        # whole-frame pass (global XC, rigid pre-correction) + patch pass: one read of every frame each
+        "tmc_rfft2_band": 3 * t * frame,
+        # rigid pre-correction writes the shifted stack once
+        "tmc_irfft2_full": t * frame,
+    }
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm (oracle) on a bounded sample
+# --------------------------------------------------------------------------------------------
+
+
+def cpu_sample_step(movie_cpu, cfg):
+    from oracle import reference_path as rp
+
+    px, p = cfg["pixel_spacing"], cfg["patch"]
+    g = rp.estimate_global_motion(movie_cpu, px)
+    f, _ = rp.estimate_motion_cross_correlation_patches(movie_cpu, px, patch_sidelength=p, deformation_field=g)
+    return rp.correct_motion(movie_cpu, f, px, "bspline").sum(dim=0)
+
+
+def cpu_sample_plan(cfg, n_steps_total):
+    """Pick a sample of the workload so n_steps_total CPU steps end within a few minutes."""
+    t, h, w = cfg["t"], cfg["h"], cfg["w"]
+    if h * w <= 1024 * 1024:
+        return dict(frames=min(t, 10), crop=(h, w))
+    if n_steps_total <= 4:
+        return dict(frames=3, crop=(h, w))
+    if n_steps_total <= 8:
+        return dict(frames=2, crop=(h, w))
+    return dict(frames=2, crop=(h // 2, w // 2))
+
+
+def run_cpu_arm(cfg, movie_cpu_full, steps, warmup, tag):
+    torch.set_num_threads(os.cpu_count() or 1)
+    plan = cpu_sample_plan(cfg, steps + warmup)
+    n, (ch, cw) = plan["frames"], plan["crop"]
+    sample = movie_cpu_full[:n, :ch, :cw].contiguous()
+    for _ in range(warmup):
+        cpu_sample_step(sample, cfg)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_sample_step(sample, cfg)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    frac = (n / cfg["t"]) * (ch * cw) / (cfg["h"] * cfg["w"])
+    return {
+        "value": frac / dt,
+        "unit": "movies/s",
+        "cores": torch.get_num_threads(),
+        "kind": "port",
+        "sample": f"{tag}: oracle estimate(global+patch XC)+correct on {n} of {cfg['t']} frames, crop {ch}x{cw} of "
+                  f"{cfg['h']}x{cfg['w']}, {dt:.2f} s/step, extrapolated linearly in frames and area "
+                  f"(understates the reference's O(T^2) leave-one-out loop)",
+        "seconds_per_step": dt,
+    }
+
+
+# --------------------------------------------------------------------------------------------
+# main
+# --------------------------------------------------------------------------------------------
+
+
+def main():
+    args = parse_args()
+    cfg = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cpu_g = torch.Generator().manual_seed(0)
+        plan = cpu_sample_plan(cfg, args.steps + args.warmup)
+        n, (ch, cw) = plan["frames"], plan["crop"]
+        if torch.cuda.is_available():
+            movie, _ = synthetic_movie_gpu(n, cfg["h"], cfg["w"], 0, torch.device("cuda", local_rank))
+            movie_cpu = movie.cpu()
+            del movie
+        else:
+            movie_cpu = torch.randn((n, cfg["h"], cfg["w"]), generator=cpu_g)
+        base = run_cpu_arm(cfg, movie_cpu, args.steps, max(args.warmup, 0), "reference arm")
+        line = {
+            "impl": "reference", "metric": "movies_per_second_estimate_plus_correct", "value": base["value"], "unit": "movies/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{cfg['t']}x{cfg['h']}x{cfg['w']} fp32 movie, global + patch-XC ({cfg['patch']} px) + warp"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "movies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import torch_motion_correction_b200 as tmc
+    from torch_motion_correction_b200 import _lib
+
+    iterations = args.iterations
+    has_optimizer = hasattr(tmc, "estimate_local_motion")
+    if iterations < 0:
+        iterations = 20 if has_optimizer else 0
+    if not has_optimizer:
+        iterations = 0
+    px, p = cfg["pixel_spacing"], cfg["patch"]
+
+    movie, _ = synthetic_movie_gpu(cfg["t"], cfg["h"], cfg["w"], 1000 + rank, dev)
+
+    def step(m):
+        return tmc.motion_correct(
+            m, px, patch_sidelength=p, deformation_field_resolution=cfg["resolution"], n_iterations=iterations
+        )
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(movie)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.TIMING = {}
+    calls_before = dict(_lib.CALLS)
+    launches_before = _lib.query("tmc_launch_count") if "tmc_launch_count" in _lib.exported_symbols() else None
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        step(movie)
+    end.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(end)
+    timing, _lib.TIMING = _lib.TIMING, None
+    launches = (_lib.query("tmc_launch_count") - launches_before) if launches_before is not None else None
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([elapsed_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    max_ms = float(t_ms)
+
+    # ---- end to end through the public API with HOST buffers ----------------------------------
+    host = torch.empty(movie.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(movie)
+    host_out = torch.empty((cfg["h"], cfg["w"]), dtype=torch.float32, pin_memory=True)
+    dev_in = torch.empty_like(movie)
+
+    def e2e_step():
+        dev_in.copy_(host, non_blocking=True)
+        total, _ = step(dev_in)
+        host_out.copy_(total, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e2.record()
+    barrier()
+    e_ms = torch.tensor([s2.elapsed_time(e2)], device=dev)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e_ms)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant entry point ------------------------------------------------------
+    per_entry = {}
+    for name, pairs in timing.items():
+        per_entry[name] = sum(a.elapsed_time(b) for a, b in pairs) / args.steps  # ms per movie
+    dominant = max(per_entry, key=per_entry.get)
+    bytes_tbl = algorithmic_bytes(cfg, iterations)
+    peak, peak_src = measured_peak_gbs()
+    roof = {"bound": "hbm", "kernel": dominant, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
+            "ms_per_movie": per_entry[dominant]}
+    if dominant in bytes_tbl:
+        achieved = bytes_tbl[dominant] / (per_entry[dominant] * 1e-3) / 1e9
+        roof.update(achieved=achieved, frac=achieved / peak, algorithmic_bytes_per_movie=bytes_tbl[dominant])
+    else:
+        roof.update(achieved=None, frac=None)
+    breakdown = {k: round(v, 4) for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1])}
+    entry_rooflines = {
+        k: round(bytes_tbl[k] / (per_entry[k] * 1e-3) / 1e9 / peak, 4) for k in per_entry if k in bytes_tbl and per_entry[k] > 0
+    }
+
+    cpu_base = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu_base = run_cpu_arm(cfg, movie[:3].cpu(), 1, 0, "cpu_baseline")
+        cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    movies = args.steps * world
+    calls = {k: _lib.CALLS[k] - calls_before.get(k, 0) for k in _lib.CALLS}
+    line = {
+        "metric": "movies_per_second_estimate_plus_correct",
+        "value": movies / (max_ms * 1e-3),
+        "unit": "movies/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(args.warmup, 3),
+        "ms_per_step": max_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: {cfg['t']}x{cfg['h']}x{cfg['w']} fp32 movie, whole-frame XC + rigid pre-correction + "
+                        f"patch XC ({p} px, 50% overlap) + {iterations}-iteration {cfg['resolution']} spline optimiser + "
+                        f"fused warp-and-sum",
+            "pixel_spacing": px, "movies_per_rank_per_step": 1, "sharding": "independent movies per rank, no collective",
+            "l2_policy": "inputs (2.7 GB/movie) exceed L2 (126 MB); no explicit flush",
+        },
+        "e2e": {
+            "value": movies / (e2e_ms * 1e-3), "unit": "movies/s", "ms_per_step": e2e_ms / args.steps,
+            "h2d_bytes_per_step": movie.numel() * 4, "d2h_bytes_per_step": cfg["h"] * cfg["w"] * 4,
+        },
+        "gpu_launches": launches if launches is not None else sum(calls.values()),
+        "c_abi_calls": calls,
+        "roofline": roof,
+        "entry_point_ms_per_movie": breakdown,
+        "entry_point_hbm_frac": entry_rooflines,
+        "cpu_baseline": cpu_base,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -22,6 +22,7 @@ from .deformation_field_utils import (
 
 from .estimate_motion_xc import estimate_global_motion, estimate_motion_cross_correlation_patches
 from .patch_grid import patch_grid_centers
+from .pipeline import estimate_motion, motion_correct
 from .utils import normalize_image
 
 __version__ = "0.1.0"
@@ -36,4 +37,6 @@ __all__ = [
     "evaluate_deformation_field",
     "estimate_global_motion",
     "estimate_motion_cross_correlation_patches",
+    "estimate_motion",
+    "motion_correct",
 ]

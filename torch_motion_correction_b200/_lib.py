@@ -28,6 +28,7 @@ _SIGNATURES = {
     "tmc_version": (I, []),
     "tmc_last_error": (c_char_p, []),
     "tmc_sm_count": (I, []),
+    "tmc_launch_count": (L, []),
     "tmc_stack_stats_workspace_doubles": (I, []),
     "tmc_stack_stats": (I, [P, I, I, I, I, I, I, I, P, P, P]),
     "tmc_spline_workspace_floats": (L, [I, I, I, I]),
@@ -101,10 +102,24 @@ def ptr(t):
     return t.data_ptr()
 
 
+#: optional per-entry-point device timing (bench.py): name -> list of (start_event, end_event)
+TIMING: dict | None = None
+#: number of C-ABI compute calls issued (bench.py reports kernels launched through them)
+CALLS: dict = {}
+
+
 def call(name: str, *args):
     """Call an ``int``-returning entry point; non-zero status raises with ``tmc_last_error()``."""
     lib = load()
-    status = getattr(lib, name)(*args)
+    CALLS[name] = CALLS.get(name, 0) + 1
+    if TIMING is not None:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()  # current stream of the current device == the stream passed to the call
+        status = getattr(lib, name)(*args)
+        end.record()
+        TIMING.setdefault(name, []).append((start, end))
+    else:
+        status = getattr(lib, name)(*args)
     if status != 0:
         msg = lib.tmc_last_error().decode("utf-8", "replace")
         if status == 1:

@@ -13,6 +13,8 @@
 
 // thread-local message for tmc_last_error()
 void tmc_set_error(const char* fmt, ...);
+// bookkeeping for bench.py: every kernel launch of this library is counted
+void tmc_count_launch();
 
 #define TMC_CHECK_ARG(cond, ...)          \
   do {                                    \

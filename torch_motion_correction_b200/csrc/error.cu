@@ -3,6 +3,8 @@
 
 #include <stdarg.h>
 
+#include <atomic>
+
 static thread_local char g_last_error[512] = "";
 
 void tmc_set_error(const char* fmt, ...) {
@@ -11,6 +13,11 @@ void tmc_set_error(const char* fmt, ...) {
   vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long> g_launches{0};
+void tmc_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// kernels launched by this library since load (monotonic)
+TMC_API long tmc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 TMC_API const char* tmc_last_error(void) { return g_last_error; }
 

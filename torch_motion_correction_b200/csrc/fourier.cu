@@ -454,7 +454,7 @@ TMC_API int tmc_fft_supported_length(int n) { return supported_n(n) ? 1 : 0; }
 // tw: n complex64 values exp(-2 pi i m / n)
 TMC_API int tmc_fft_twiddles(int n, void* tw, cudaStream_t stream) {
   TMC_CHECK_ARG(tw && n >= 2, "fft_twiddles: bad arguments");
-  twiddle_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(n, (float2*)tw);
+  twiddle_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(n, (float2*)tw); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_fft_twiddles");
   return TMC_OK;
 }
@@ -485,7 +485,7 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
     dim3 grid(tmc_div_up(yhi - ylo, batch_for(N)), njobs);                                                       \
     if (yhi > ylo)                                                                                               \
       rows_forward_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                                   \
-          image, h, w, mean_std, mask, jobs, ylo, yhi, ny, kx_count, (const float2*)tw_x, (float2*)tmp);         \
+          image, h, w, mean_std, mask, jobs, ylo, yhi, ny, kx_count, (const float2*)tw_x, (float2*)tmp); tmc_count_launch();         \
     done = true;                                                                                                 \
   }
   TMC_FOR_EACH_N(ROWS)
@@ -499,7 +499,7 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
     dim3 grid(tmc_div_up(kx_count, batch_for(N)), 2 * njobs);                                                         \
     cols_forward_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>((const float2*)tmp, ylo, yhi, kx_count,  \
                                                                            ky_count, ky_start, weight,               \
-                                                                           (const float2*)tw_y, (float2*)out);       \
+                                                                           (const float2*)tw_y, (float2*)out); tmc_count_launch();       \
     done = true;                                                                                                      \
   }
   TMC_FOR_EACH_N(COLS)
@@ -515,7 +515,7 @@ TMC_API int tmc_xc_pair_products(const void* spec, const int* ref_plane, const i
   TMC_CHECK_ARG(spec && ref_plane && cur_plane && out && nitems >= 0 && plane_elems >= 1, "xc_pair_products: bad arguments");
   if (nitems == 0) return TMC_OK;
   dim3 grid((unsigned)(tmc_div_up(plane_elems, 256) < 64 ? tmc_div_up(plane_elems, 256) : 64), nitems);
-  xc_pair_product_kernel<<<grid, 256, 0, stream>>>((const float2*)spec, ref_plane, cur_plane, plane_elems, (float2*)out);
+  xc_pair_product_kernel<<<grid, 256, 0, stream>>>((const float2*)spec, ref_plane, cur_plane, plane_elems, (float2*)out); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_xc_pair_products");
   return TMC_OK;
 }
@@ -527,7 +527,7 @@ TMC_API int tmc_xc_leave_one_out_products(const void* spec, int t, int g, long p
                 "xc_leave_one_out_products: bad arguments (need t >= 2)");
   dim3 grid(tmc_div_up(plane_elems, 128), g);
   xc_leave_one_out_kernel<<<grid, 128, 0, stream>>>((const float2*)spec, t, g, plane_elems, delta_offsets, deltas,
-                                                    (float2*)out);
+                                                    (float2*)out); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_xc_leave_one_out_products");
   return TMC_OK;
 }
@@ -553,7 +553,7 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
     if (int e = enable_smem(cols_inverse_kernel<N>, fft_smem_bytes<N>())) return e;                              \
     dim3 grid(tmc_div_up(kx_count, batch_for(N)), nitems);                                                       \
     cols_inverse_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                                     \
-        (const float2*)prod, kx_count, ky_count, ky_start, (const float2*)tw_y, (float2*)tmp);                   \
+        (const float2*)prod, kx_count, ky_count, ky_start, (const float2*)tw_y, (float2*)tmp); tmc_count_launch();                   \
     done = true;                                                                                                 \
   }
   TMC_FOR_EACH_N(COLS)
@@ -567,7 +567,7 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
     if (int e = enable_smem(rows_inverse_argmax_kernel<N>, fft_smem_bytes<N>())) return e;                        \
     dim3 grid(nparts, nitems);                                                                                    \
     rows_inverse_argmax_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                               \
-        (const float2*)tmp, ny, kx_count, (const float2*)tw_x, (PeakCandidate*)partial);                          \
+        (const float2*)tmp, ny, kx_count, (const float2*)tw_x, (PeakCandidate*)partial); tmc_count_launch();                          \
     done = true;                                                                                                  \
   }
   TMC_FOR_EACH_N(ROWS)
@@ -575,7 +575,7 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
   TMC_CHECK_ARG(done, "xc_peaks: unsupported nx %d", nx);
   TMC_CHECK_LAUNCH("tmc_xc_peaks(rows)");
   peak_finalize_kernel<<<nitems, 128, 0, stream>>>((const float2*)tmp, (const PeakCandidate*)partial, nparts, ny, nx,
-                                                   kx_count, sub_pixel, shifts);
+                                                   kx_count, sub_pixel, shifts); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_xc_peaks(finalize)");
   return TMC_OK;
 }
@@ -596,7 +596,7 @@ TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const 
     if (int e = enable_smem(cols_inverse_kernel<N>, fft_smem_bytes<N>())) return e;                              \
     dim3 grid(tmc_div_up(kx, batch_for(N)), nitems);                                                             \
     cols_inverse_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>((const float2*)spec, kx, ny, 0,      \
-                                                                           (const float2*)tw_y, (float2*)tmp);   \
+                                                                           (const float2*)tw_y, (float2*)tmp); tmc_count_launch();   \
     done = true;                                                                                                 \
   }
   TMC_FOR_EACH_N(COLS)
@@ -608,7 +608,7 @@ TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const 
     if (int e = enable_smem(rows_inverse_store_kernel<N>, fft_smem_bytes<N>())) return e;                          \
     dim3 grid(tmc_div_up(ny, 2 * batch_for(N)), nitems);                                                           \
     rows_inverse_store_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                                 \
-        (const float2*)tmp, ny, kx, (const float2*)tw_x, 1.0f / ((float)nx * (float)ny), out);                     \
+        (const float2*)tmp, ny, kx, (const float2*)tw_x, 1.0f / ((float)nx * (float)ny), out); tmc_count_launch();                     \
     done = true;                                                                                                   \
   }
   TMC_FOR_EACH_N(ROWS)
@@ -623,7 +623,7 @@ TMC_API int tmc_fourier_shift(void* spec, int t, int ny, int nx, const float* fi
   TMC_CHECK_ARG(spec && field && t >= 1 && ny >= 1 && nx >= 2, "fourier_shift: bad arguments");
   const int kx = nx / 2 + 1;
   dim3 grid(tmc_div_up(kx, 128), ny, t);
-  fourier_shift_kernel<<<grid, 128, 0, stream>>>((float2*)spec, t, ny, nx, kx, field, sign);
+  fourier_shift_kernel<<<grid, 128, 0, stream>>>((float2*)spec, t, ny, nx, kx, field, sign); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_fourier_shift");
   return TMC_OK;
 }

@@ -150,7 +150,7 @@ TMC_API int tmc_xc_postprocess(const float* shifts, int t, int g, float pixel_sp
   const size_t smem = (size_t)g * (2 * sizeof(float) + sizeof(int));
   TMC_CHECK_ARG(smem <= 48 * 1024, "xc_postprocess: too many patches per frame (%d)", g);
   reject_and_accumulate_kernel<<<t, 128, smem, stream>>>(shifts, t, g, outlier_rejection, outlier_threshold, pixel_spacing,
-                                                         skip_frame, field);
+                                                         skip_frame, field); tmc_count_launch();
   if (temporal_smoothing) {
     int window = smoothing_window;
     if (window % 2 == 0) window += 1;
@@ -160,10 +160,10 @@ TMC_API int tmc_xc_postprocess(const float* shifts, int t, int g, float pixel_sp
     if (window >= 3) {
       TMC_CHECK_ARG(window % 2 == 1, "xc_postprocess: smoothing window %d (capped at t=%d) must be odd", window, t);
       TMC_CUDA(cudaMemcpyAsync(scratch, field, sizeof(float) * 2 * (size_t)t * g, cudaMemcpyDeviceToDevice, stream));
-      savgol_linear_kernel<<<tmc_div_up(2 * g, 64), 64, 0, stream>>>(scratch, t, g, window, field);
+      savgol_linear_kernel<<<tmc_div_up(2 * g, 64), 64, 0, stream>>>(scratch, t, g, window, field); tmc_count_launch();
     }
   }
-  if (subtract_mean) subtract_mean_kernel<<<1, 256, 0, stream>>>(field, 2l * t * g);
+  if (subtract_mean) subtract_mean_kernel<<<1, 256, 0, stream>>>(field, 2l * t * g); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_xc_postprocess");
   return TMC_OK;
 }
@@ -171,7 +171,7 @@ TMC_API int tmc_xc_postprocess(const float* shifts, int t, int g, float pixel_sp
 TMC_API int tmc_global_shifts_to_field(const float* shifts, int t, float pixel_spacing, int zero_frame, float* field,
                                        cudaStream_t stream) {
   TMC_CHECK_ARG(shifts && field && t >= 1, "global_shifts_to_field: bad arguments");
-  global_field_kernel<<<tmc_div_up(t, 128), 128, 0, stream>>>(shifts, t, pixel_spacing, zero_frame, field);
+  global_field_kernel<<<tmc_div_up(t, 128), 128, 0, stream>>>(shifts, t, pixel_spacing, zero_frame, field); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_global_shifts_to_field");
   return TMC_OK;
 }

@@ -278,8 +278,8 @@ TMC_API int tmc_spline_eval(const float* coeffs, int c, int n0, int n1, int n2, 
   g.data = workspace;
   g.c = c;
   padded_dims(n0, n1, n2, g.p0, g.p1, g.p2);
-  spline_pad_kernel<<<1, 256, 0, stream>>>(coeffs, c, n0, n1, n2, workspace);
-  if (n > 0) spline_eval_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(g, kind, tyx, n, out);
+  spline_pad_kernel<<<1, 256, 0, stream>>>(coeffs, c, n0, n1, n2, workspace); tmc_count_launch();
+  if (n > 0) spline_eval_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(g, kind, tyx, n, out); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_spline_eval");
   return TMC_OK;
 }
@@ -295,8 +295,8 @@ TMC_API int tmc_spline_eval_backward(int c, int n0, int n1, int n2, int kind, co
   padded_dims(n0, n1, n2, p0, p1, p2);
   TMC_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)c * p0 * p1 * p2, stream));
   if (n > 0)
-    spline_eval_backward_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(c, p0, p1, p2, kind, tyx, n, grad_out, workspace);
-  spline_unpad_kernel<<<1, 256, 0, stream>>>(workspace, c, n0, n1, n2, grad_coeffs, scale);
+    spline_eval_backward_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(c, p0, p1, p2, kind, tyx, n, grad_out, workspace); tmc_count_launch();
+  spline_unpad_kernel<<<1, 256, 0, stream>>>(workspace, c, n0, n1, n2, grad_coeffs, scale); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_spline_eval_backward");
   return TMC_OK;
 }
@@ -313,18 +313,18 @@ TMC_API int tmc_spline_lattice(const float* coeffs, int c, int n0, int n1, int n
   g1.data = workspace;
   g1.c = c;
   padded_dims(n0, n1, n2, g1.p0, g1.p1, g1.p2);
-  spline_pad_kernel<<<1, 256, 0, stream>>>(coeffs, c, n0, n1, n2, workspace);
+  spline_pad_kernel<<<1, 256, 0, stream>>>(coeffs, c, n0, n1, n2, workspace); tmc_count_launch();
   g2 = g1;
   if (coeffs2) {
     if (int e = check_grid(coeffs2, c, m0, m1, m2, kind2)) return e;
     float* ws2 = workspace + tmc_spline_workspace_floats(c, n0, n1, n2);
     g2.data = ws2;
     padded_dims(m0, m1, m2, g2.p0, g2.p1, g2.p2);
-    spline_pad_kernel<<<1, 256, 0, stream>>>(coeffs2, c, m0, m1, m2, ws2);
+    spline_pad_kernel<<<1, 256, 0, stream>>>(coeffs2, c, m0, m1, m2, ws2); tmc_count_launch();
   }
   long total = (long)n_frames * lh * lw;
   spline_lattice_kernel<<<tmc_div_up(total, 128), 128, 0, stream>>>(g1, kind, g2, kind2, coeffs2 != nullptr, n_frames,
-                                                                   frame_offset, total_frames, lh, lw, lattice);
+                                                                   frame_offset, total_frames, lh, lw, lattice); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_spline_lattice");
   return TMC_OK;
 }

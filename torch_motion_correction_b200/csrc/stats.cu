@@ -84,8 +84,8 @@ TMC_API int tmc_stack_stats(const float* image, int t, int h, int w, int y0, int
   TMC_CHECK_ARG(0 <= y0 && y0 < y1 && y1 <= h && 0 <= x0 && x0 < x1 && x1 <= w, "stack_stats: empty or out-of-range box");
   const long rows = (long)t * (y1 - y0);
   int nblocks = (int)(rows < 148 * 8 ? rows : 148 * 8);
-  stats_partial_kernel<<<nblocks, kStatsThreads, 0, stream>>>(image, t, h, w, y0, y1, x0, x1, workspace);
-  stats_final_kernel<<<1, 32, 0, stream>>>(workspace, nblocks, (double)rows * (x1 - x0), mean_std);
+  stats_partial_kernel<<<nblocks, kStatsThreads, 0, stream>>>(image, t, h, w, y0, y1, x0, x1, workspace); tmc_count_launch();
+  stats_final_kernel<<<1, 32, 0, stream>>>(workspace, nblocks, (double)rows * (x1 - x0), mean_std); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_stack_stats");
   return TMC_OK;
 }

@@ -91,9 +91,9 @@ TMC_API int tmc_soft_disc_mask(int h, int w, float radius, float smoothing_radiu
   TMC_CHECK_ARG(mask && workspace && h >= 1 && w >= 1 && radius >= 0.f && smoothing_radius >= 0.f,
                 "soft_disc_mask: bad arguments");
   const int cy = h / 2, cx = w / 2;  // torch_grid_utils: centre = shape // 2
-  disc_rows_kernel<<<tmc_div_up(h, 128), 128, 0, stream>>>(h, w, cy, cx, radius, workspace);
+  disc_rows_kernel<<<tmc_div_up(h, 128), 128, 0, stream>>>(h, w, cy, cx, radius, workspace); tmc_count_launch();
   dim3 grid(tmc_div_up(w, 128), h);
-  soft_disc_kernel<<<grid, 128, 0, stream>>>(h, w, cy, cx, radius, smoothing_radius, workspace, mask);
+  soft_disc_kernel<<<grid, 128, 0, stream>>>(h, w, cy, cx, radius, smoothing_radius, workspace, mask); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_soft_disc_mask");
   return TMC_OK;
 }
@@ -104,7 +104,7 @@ TMC_API int tmc_band_weights(int ny, int nx, int ky_count, int kx_count, int ky_
                 "band_weights: bad arguments");
   dim3 grid(tmc_div_up(kx_count, 128), ky_count);
   band_weight_kernel<<<grid, 128, 0, stream>>>(ny, nx, ky_count, kx_count, ky_start, low, high, use_band, b_factor,
-                                              pixel_size, use_envelope, weight);
+                                              pixel_size, use_envelope, weight); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_band_weights");
   return TMC_OK;
 }

@@ -259,7 +259,7 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
   {
     long rows = (long)t * 2 * lh;
     dim3 g1(tmc_div_up(w, 128), (unsigned)(rows < 4096 ? rows : 4096));
-    lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, workspace);
+    lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, workspace); tmc_count_launch();
   }
   dim3 block(kTileX, kTileYGroups);
   dim3 grid(tmc_div_up(w, kTileX), tmc_div_up(h, kTileYGroups * kRowsPerThread));
@@ -274,6 +274,7 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
   else if (n) LAUNCH(false, true, true);
   else LAUNCH(false, true, false);
 #undef LAUNCH
+  tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_warp_lattice");
   return TMC_OK;
 }
@@ -282,7 +283,7 @@ TMC_API int tmc_pixel_shifts(const float* lattice, int lh, int lw, int h, int w,
                              cudaStream_t stream) {
   TMC_CHECK_ARG(lattice && out && lh >= 1 && lw >= 1 && h >= 2 && w >= 2 && pixel_spacing > 0.f, "pixel_shifts: bad arguments");
   dim3 grid(tmc_div_up(w, 128), h);
-  pixel_shifts_kernel<<<grid, 128, 0, stream>>>(lattice, lh, lw, h, w, pixel_spacing, out);
+  pixel_shifts_kernel<<<grid, 128, 0, stream>>>(lattice, lh, lw, h, w, pixel_spacing, out); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_pixel_shifts");
   return TMC_OK;
 }
@@ -291,7 +292,7 @@ TMC_API int tmc_warp_dense_shifts(const float* image, int t, int h, int w, const
                                   cudaStream_t stream) {
   TMC_CHECK_ARG(image && shifts && out_stack && t >= 1 && h >= 2 && w >= 2, "warp_dense_shifts: bad arguments");
   dim3 grid(tmc_div_up(w, 128), h, t);
-  warp_dense_shifts_kernel<<<grid, 128, 0, stream>>>(image, t, h, w, shifts, out_stack);
+  warp_dense_shifts_kernel<<<grid, 128, 0, stream>>>(image, t, h, w, shifts, out_stack); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_warp_dense_shifts");
   return TMC_OK;
 }
@@ -299,7 +300,7 @@ TMC_API int tmc_warp_dense_shifts(const float* image, int t, int h, int w, const
 TMC_API int tmc_pixel_tyx(int h, int w, int t, int frame_offset, int total_frames, float* tyx, cudaStream_t stream) {
   TMC_CHECK_ARG(tyx && t >= 1 && h >= 2 && w >= 2 && total_frames >= t + frame_offset, "pixel_tyx: bad arguments");
   dim3 grid(tmc_div_up(w, 128), h, t);
-  pixel_tyx_kernel<<<grid, 128, 0, stream>>>(h, w, t, frame_offset, total_frames, tyx);
+  pixel_tyx_kernel<<<grid, 128, 0, stream>>>(h, w, t, frame_offset, total_frames, tyx); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_pixel_tyx");
   return TMC_OK;
 }
