@@ -23,7 +23,12 @@ def as_complex(t):
     return torch.view_as_complex(t.contiguous())
 
 
-@pytest.mark.parametrize("shape", [(16, 16), (32, 32), (64, 128), (128, 64), (256, 256), (512, 1024), (2048, 2048)])
+@pytest.mark.parametrize(
+    "shape",
+    [(16, 16), (32, 32), (64, 128), (128, 64), (256, 256), (512, 1024), (2048, 2048),
+     # arbitrary lengths run as Bluestein chirp-z transforms on the same FFT core
+     (96, 96), (48, 80), (100, 36), (959, 927), (30, 4092)],
+)
 def test_full_rfft2_and_irfft2_match_torch(dev, shape):
     ny, nx = shape
     g = torch.Generator().manual_seed(ny + nx)
@@ -185,5 +190,15 @@ def test_correct_motion_fast_golden(dev, golden_small):
 
 
 def test_unsupported_length_raises(dev):
+    # non-power-of-two lengths above 4096 would need a 16384-point shared-memory transform
     with pytest.raises(NotImplementedError):
-        tmc.estimate_global_motion(torch.zeros((3, 96, 100), device=dev), 1.0)
+        tmc.estimate_global_motion(torch.zeros((2, 5000, 64), device=dev), 1.0)
+
+
+def test_global_motion_non_power_of_two_frames(dev):
+    """96x80 frames (Bluestein on both axes) recover known integer drifts exactly."""
+    movie, walk = rp.synthetic_movie(6, 96, 80, seed=2, noise=0.3, drift=4.0, integer_shifts=True, sigma_f=0.1)
+    want = rp.estimate_global_motion(movie, 1.0, frequency_range=(60, 4))
+    got = tmc.estimate_global_motion(movie.to(dev), 1.0, frequency_range=(60, 4)).cpu()
+    assert torch.equal(got, want)
+    assert torch.equal(got[:, :, 0, 0].T, walk)

@@ -20,14 +20,21 @@ from .deformation_field_utils import (
     resample_deformation_field,
 )
 
+from .data_io import read_deformation_field_from_csv, write_deformation_field_to_csv
+from .estimate_motion_optimizer import estimate_local_motion
 from .estimate_motion_xc import estimate_global_motion, estimate_motion_cross_correlation_patches
+from .optimization_state import OptimizationState, OptimizationTracker
 from .patch_grid import patch_grid_centers
+from .spline_grids import CubicBSplineGrid3d, CubicCatmullRomGrid3d
 from .pipeline import estimate_motion, motion_correct
 from .utils import normalize_image
 
 __version__ = "0.1.0"
 
 __all__ = [
+    "estimate_local_motion",
+    "write_deformation_field_to_csv",
+    "read_deformation_field_from_csv",
     "correct_motion",
     "correct_motion_two_grids",
     "correct_motion_fast",

@@ -26,12 +26,14 @@ def _dev_key(device: torch.device):
 
 
 def twiddles(n: int, device: torch.device) -> torch.Tensor:
+    """Per-length transform plan (twiddles; plus Bluestein chirp tables for non-power-of-two n)."""
     key = (_dev_key(device), n)
     tw = _twiddles.get(key)
     if tw is None:
-        tw = torch.empty((n, 2), dtype=torch.float32, device=device)
+        elems = query("tmc_fft_plan_elems", n)
+        tw = torch.empty((elems, 2), dtype=torch.float32, device=device)
         with torch.cuda.device(device):
-            call("tmc_fft_twiddles", n, ptr(tw), stream_ptr(device))
+            call("tmc_fft_plan_init", n, ptr(tw), stream_ptr(device))
         _twiddles[key] = tw
     return tw
 
@@ -77,8 +79,8 @@ class BandPlan:
         for n in (ny, nx):
             if not query("tmc_fft_supported_length", n):
                 raise NotImplementedError(
-                    f"transform length {n} is not supported: the sm_100a FFT kernels need power-of-two lengths in "
-                    f"[16, 8192] (patch side lengths / frame sizes)"
+                    f"transform length {n} is not supported: the sm_100a FFT kernels take powers of two in [16, 8192] "
+                    f"and arbitrary lengths up to 4096 (patch side lengths / frame sizes)"
                 )
         self.ny, self.nx, self.device = ny, nx, device
         self.tw_y, self.tw_x = twiddles(ny, device), twiddles(nx, device)

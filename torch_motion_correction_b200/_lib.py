@@ -41,7 +41,9 @@ _SIGNATURES = {
     "tmc_warp_dense_shifts": (I, [P, I, I, I, P, P, P]),
     "tmc_pixel_tyx": (I, [I, I, I, I, I, P, P]),
     "tmc_fft_supported_length": (I, [I]),
-    "tmc_fft_twiddles": (I, [I, P, P]),
+    "tmc_fft_plan_elems": (L, [I]),
+    "tmc_fft_plan_init": (I, [I, P, P]),
+    "tmc_fft_c2c_rows": (I, [P, I, I, P, P, P]),
     "tmc_rfft2_band": (I, [P, I, I, I, P, P, I, I, P, I, I, I, I, I, I, P, P, P, P, P, P]),
     "tmc_xc_pair_products": (I, [P, P, P, I, L, P, P]),
     "tmc_xc_leave_one_out_products": (I, [P, I, I, L, P, P, P, P]),
@@ -53,6 +55,10 @@ _SIGNATURES = {
     "tmc_band_weights": (I, [I, I, I, I, I, F, F, I, F, F, I, P, P]),
     "tmc_xc_postprocess": (I, [P, I, I, F, I, I, F, I, I, I, P, P, P]),
     "tmc_global_shifts_to_field": (I, [P, I, F, I, P, P]),
+    "tmc_subtract_mean": (I, [P, L, P]),
+    "tmc_local_spectra_norms": (I, [P, I, I, I, I, I, I, I, I, P, P]),
+    "tmc_local_loss_workspace_bytes": (L, [I, I, I, I]),
+    "tmc_local_loss_grad": (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, F, I, P, P, P, P]),
 }
 
 

@@ -28,7 +28,36 @@ constexpr size_t fft_smem_bytes() {
   return 2ull * batch_for(N) * padded_len(N) * sizeof(float2);
 }
 
-// ---- tables -----------------------------------------------------------------------------
+// ---- transform plans ----------------------------------------------------------------------
+// A plan buffer (device, complex64) for a length-n DFT is  twiddles W_M^m [M] | chirp [n] | bhat [M]
+// with M == n for supported powers of two (no chirp / bhat) and otherwise M = next_pow2(2n - 1):
+// arbitrary lengths run as Bluestein chirp-z convolutions on the same shared-memory FFT core.
+
+inline bool pow2_n(int n) { return n >= 16 && n <= 8192 && (n & (n - 1)) == 0; }
+inline int fft_size_for(int n) {  // 0: unsupported
+  if (pow2_n(n)) return n;
+  if (n < 2) return 0;
+  int m = 16;
+  while (m < 2 * n - 1) m <<= 1;
+  return m <= 8192 ? m : 0;
+}
+
+struct AxisPlan {
+  const float2* tw;     // W_M^m
+  const float2* chirp;  // exp(-i pi j^2 / n), j < n   (Bluestein only)
+  const float2* bhat;   // FFT_M of the wrapped conjugate chirp (Bluestein only)
+  int n;                // transform length
+};
+
+inline AxisPlan make_axis_plan(const void* buf, int n) {
+  const int m = fft_size_for(n);
+  AxisPlan p;
+  p.tw = (const float2*)buf;
+  p.chirp = p.tw + m;
+  p.bhat = p.chirp + n;
+  p.n = n;
+  return p;
+}
 
 __global__ void twiddle_kernel(int n, float2* __restrict__ tw) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -38,19 +67,105 @@ __global__ void twiddle_kernel(int n, float2* __restrict__ tw) {
   tw[m] = make_float2((float)c, (float)s);
 }
 
+// chirp[j] = exp(-i pi j^2 / n) ; b[j] = conj(chirp[|j|]) wrapped into length m, zero elsewhere
+__global__ void chirp_kernel(int n, int m, float2* __restrict__ chirp, float2* __restrict__ b) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  float2 bv = make_float2(0.f, 0.f);
+  auto w = [&](int q) {  // exp(-i pi q^2 / n), q^2 reduced mod 2n exactly
+    long r = ((long)q * q) % (2l * n);
+    double s, c;
+    sincospi(-(double)r / (double)n, &s, &c);
+    return make_float2((float)c, (float)s);
+  };
+  if (j < n) {
+    float2 v = w(j);
+    chirp[j] = v;
+    bv = make_float2(v.x, -v.y);
+  } else if (m - j < n) {
+    float2 v = w(m - j);
+    bv = make_float2(v.x, -v.y);
+  }
+  b[j] = bv;
+}
+
+// Length-n DFT of B sequences held (padded) in `a` (entries [0, n) valid); `b` is scratch.
+// BLU == false: n == M, plain FFT.  BLU == true: Bluestein with FFT size M >= 2n - 1.
+// The caller syncs after filling `a`; the result (natural order, entries [0, n)) is in the
+// returned buffer and a __syncthreads() has been issued.
+template <int M, bool BLU>
+__device__ __forceinline__ float2* dft_smem(float2* a, float2* b, const AxisPlan& plan) {
+  constexpr int B = batch_for(M);
+  if constexpr (!BLU) {
+    return tmcfft::fft_forward<M, B, kThreads>(a, b, plan.tw);
+  } else {
+    constexpr int STRIDE = padded_len(M);
+    const int n = plan.n;
+    for (int idx = threadIdx.x; idx < B * M; idx += kThreads) {
+      const int s = idx / M, j = idx % M;
+      float2* p = a + s * STRIDE + pad_idx(j);
+      *p = j < n ? cmul(*p, __ldg(plan.chirp + j)) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    float2* r = tmcfft::fft_forward<M, B, kThreads>(a, b, plan.tw);
+    float2* other = (r == a) ? b : a;
+    for (int idx = threadIdx.x; idx < B * M; idx += kThreads) {
+      const int s = idx / M, j = idx % M;
+      float2* p = r + s * STRIDE + pad_idx(j);
+      const float2 v = cmul(*p, __ldg(plan.bhat + j));
+      *p = make_float2(v.y, v.x);  // swapped: the next forward FFT acts as the inverse
+    }
+    __syncthreads();
+    float2* c = tmcfft::fft_forward<M, B, kThreads>(r, other, plan.tw);
+    const float inv_m = 1.0f / (float)M;
+    for (int idx = threadIdx.x; idx < B * n; idx += kThreads) {
+      const int s = idx / n, k = idx % n;
+      float2* p = c + s * STRIDE + pad_idx(k);
+      const float2 v = make_float2(p->y * inv_m, p->x * inv_m);
+      *p = cmul(v, __ldg(plan.chirp + k));
+    }
+    __syncthreads();
+    return c;
+  }
+}
+
+// plain batched complex rows (plan construction, tests): out[r] = DFT_n(in[r])
+template <int M, bool BLU>
+__global__ void __launch_bounds__(kThreads)
+c2c_rows_kernel(const float2* __restrict__ in, int rows, AxisPlan plan, float2* __restrict__ out) {
+  constexpr int B = batch_for(M);
+  constexpr int STRIDE = padded_len(M);
+  extern __shared__ float2 smem[];
+  float2* a = smem;
+  float2* b = smem + B * STRIDE;
+  const int n = BLU ? plan.n : M;
+  const int row0 = blockIdx.x * B;
+  for (int idx = threadIdx.x; idx < B * n; idx += kThreads) {
+    const int s = idx / n, j = idx % n;
+    a[s * STRIDE + pad_idx(j)] = row0 + s < rows ? in[(long)(row0 + s) * n + j] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const float2* r = dft_smem<M, BLU>(a, b, plan);
+  for (int idx = threadIdx.x; idx < B * n; idx += kThreads) {
+    const int s = idx / n, j = idx % n;
+    if (row0 + s < rows) out[(long)(row0 + s) * n + j] = r[s * STRIDE + pad_idx(j)];
+  }
+}
+
 // ---- forward: row pass ---------------------------------------------------------------------
 
 struct RowJob {  // one packed pair of real rows-sets: a -> real part, b -> imaginary part
   int frame_a, exp_a, frame_b, exp_b, y0, x0;
 };
 
-template <int NX>
+template <int MX, bool BLU>
 __global__ void __launch_bounds__(kThreads)
 rows_forward_kernel(const float* __restrict__ image, int H, int W, const float* __restrict__ mean_std,
                     const float* __restrict__ mask, const int* __restrict__ jobs, int ylo, int yhi, int NY, int KX,
-                    const float2* __restrict__ tw, float2* __restrict__ tmp) {
-  constexpr int B = batch_for(NX);
-  constexpr int STRIDE = padded_len(NX);
+                    AxisPlan plan, float2* __restrict__ tmp) {
+  constexpr int B = batch_for(MX);
+  constexpr int STRIDE = padded_len(MX);
+  const int NX = BLU ? plan.n : MX;
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B * STRIDE;
@@ -86,13 +201,13 @@ rows_forward_kernel(const float* __restrict__ image, int H, int W, const float* 
     a[s * STRIDE + pad_idx(x)] = z;
   }
   __syncthreads();
-  const float2* r = tmcfft::fft_forward<NX, B, kThreads>(a, b, tw);
+  const float2* r = dft_smem<MX, BLU>(a, b, plan);
   for (int idx = threadIdx.x; idx < B * KX; idx += kThreads) {
     const int s = idx / KX, k = idx % KX;
     const int y = row0 + s;
     if (y >= yhi) continue;
     const float2 zk = r[s * STRIDE + pad_idx(k)];
-    const float2 zn = r[s * STRIDE + pad_idx((NX - k) & (NX - 1))];
+    const float2 zn = r[s * STRIDE + pad_idx(k == 0 ? 0 : NX - k)];
     // Z = A + iB with A, B Hermitian:  A = (Z[k] + conj Z[-k]) / 2,  B = (Z[k] - conj Z[-k]) / 2i
     tmp[((long)(2 * job) * NY + y) * KX + k] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
     if (fb >= 0) tmp[((long)(2 * job + 1) * NY + y) * KX + k] = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
@@ -102,12 +217,13 @@ rows_forward_kernel(const float* __restrict__ image, int H, int W, const float* 
 // ---- forward: column pass --------------------------------------------------------------------
 
 // plane p of tmp [NY][KX] -> out[p][KY][KX], ky = ky_start + kyb (wrapped), times weight[kyb][kx]
-template <int NY>
+template <int MY, bool BLU>
 __global__ void __launch_bounds__(kThreads)
 cols_forward_kernel(const float2* __restrict__ tmp, int ylo, int yhi, int KX, int KY, int ky_start,
-                    const float* __restrict__ weight, const float2* __restrict__ tw, float2* __restrict__ out) {
-  constexpr int B = batch_for(NY);
-  constexpr int STRIDE = padded_len(NY);
+                    const float* __restrict__ weight, AxisPlan plan, float2* __restrict__ out) {
+  constexpr int B = batch_for(MY);
+  constexpr int STRIDE = padded_len(MY);
+  const int NY = BLU ? plan.n : MY;
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B * STRIDE;
@@ -121,12 +237,12 @@ cols_forward_kernel(const float2* __restrict__ tmp, int ylo, int yhi, int KX, in
     a[s * STRIDE + pad_idx(y)] = z;
   }
   __syncthreads();
-  const float2* r = tmcfft::fft_forward<NY, B, kThreads>(a, b, tw);
+  const float2* r = dft_smem<MY, BLU>(a, b, plan);
   float2* dst = out + plane * KY * KX;
   for (int idx = threadIdx.x; idx < B * KY; idx += kThreads) {
     const int s = idx % B, kyb = idx / B;
     if (kx0 + s >= KX) continue;
-    const int y = (ky_start + kyb + NY) & (NY - 1);
+    const int y = ((ky_start + kyb) % NY + NY) % NY;
     float2 v = r[s * STRIDE + pad_idx(y)];
     if (weight) {
       const float wgt = __ldg(weight + (long)kyb * KX + kx0 + s);
@@ -184,12 +300,13 @@ __global__ void xc_leave_one_out_kernel(const float2* __restrict__ spec, int T, 
 // ---- inverse: column pass --------------------------------------------------------------------
 
 // in[item][KY][KX] (ky = ky_start + kyb) -> tmp[item][NY][KX] = unnormalised inverse DFT along y
-template <int NY>
+template <int MY, bool BLU>
 __global__ void __launch_bounds__(kThreads)
-cols_inverse_kernel(const float2* __restrict__ in, int KX, int KY, int ky_start, const float2* __restrict__ tw,
+cols_inverse_kernel(const float2* __restrict__ in, int KX, int KY, int ky_start, AxisPlan plan,
                     float2* __restrict__ tmp) {
-  constexpr int B = batch_for(NY);
-  constexpr int STRIDE = padded_len(NY);
+  constexpr int B = batch_for(MY);
+  constexpr int STRIDE = padded_len(MY);
+  const int NY = BLU ? plan.n : MY;
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B * STRIDE;
@@ -202,11 +319,11 @@ cols_inverse_kernel(const float2* __restrict__ in, int KX, int KY, int ky_start,
     const int s = idx % B, kyb = idx / B;
     if (kx0 + s >= KX) continue;
     const float2 v = src[(long)kyb * KX + kx0 + s];
-    const int y = (ky_start + kyb + NY) & (NY - 1);
+    const int y = ((ky_start + kyb) % NY + NY) % NY;
     a[s * STRIDE + pad_idx(y)] = make_float2(v.y, v.x);  // re/im swap: inverse via forward
   }
   __syncthreads();
-  const float2* r = tmcfft::fft_forward<NY, B, kThreads>(a, b, tw);
+  const float2* r = dft_smem<MY, BLU>(a, b, plan);
   float2* dst = tmp + item * NY * KX;
   for (int idx = threadIdx.x; idx < B * NY; idx += kThreads) {
     const int s = idx % B, y = idx / B;
@@ -219,9 +336,8 @@ cols_inverse_kernel(const float2* __restrict__ in, int KX, int KY, int ky_start,
 // ---- inverse: row pass (complex-to-real, two rows per transform) ------------------------------
 
 // builds the packed spectrum of rows ya (real part) and yb (imaginary part) in `a`, re/im swapped
-template <int NX>
 __device__ __forceinline__ void load_c2r_pair(const float2* __restrict__ rowa, const float2* __restrict__ rowb, int KX,
-                                              float2* __restrict__ a_seq) {
+                                              int NX, float2* __restrict__ a_seq) {
   for (int k = threadIdx.x; k < KX; k += kThreads) {
     float2 ca = rowa[k];
     float2 cb = rowb ? rowb[k] : make_float2(0.f, 0.f);
@@ -243,12 +359,13 @@ struct PeakCandidate {
 __device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 
 // tmp[item][NY][KX] -> per-CTA maximum of the real correlation surface: partial[item][blockIdx.x]
-template <int NX>
+template <int MX, bool BLU>
 __global__ void __launch_bounds__(kThreads)
-rows_inverse_argmax_kernel(const float2* __restrict__ tmp, int NY, int KX, const float2* __restrict__ tw,
+rows_inverse_argmax_kernel(const float2* __restrict__ tmp, int NY, int KX, AxisPlan plan,
                            PeakCandidate* __restrict__ partial) {
-  constexpr int B = batch_for(NX);
-  constexpr int STRIDE = padded_len(NX);
+  constexpr int B = batch_for(MX);
+  constexpr int STRIDE = padded_len(MX);
+  const int NX = BLU ? plan.n : MX;
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B * STRIDE;
@@ -259,10 +376,10 @@ rows_inverse_argmax_kernel(const float2* __restrict__ tmp, int NY, int KX, const
   __syncthreads();
   for (int s = 0; s < B; ++s) {
     const int ya = row0 + 2 * s, yb = ya + 1;
-    if (ya < NY) load_c2r_pair<NX>(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, a + s * STRIDE);
+    if (ya < NY) load_c2r_pair(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, NX, a + s * STRIDE);
   }
   __syncthreads();
-  const float2* r = tmcfft::fft_forward<NX, B, kThreads>(a, b, tw);
+  const float2* r = dft_smem<MX, BLU>(a, b, plan);
   float best = -INFINITY;
   int best_idx = 0x7fffffff;
   for (int idx = threadIdx.x; idx < B * NX; idx += kThreads) {
@@ -310,12 +427,13 @@ rows_inverse_argmax_kernel(const float2* __restrict__ tmp, int NY, int KX, const
 }
 
 // tmp[item][NY][KX] -> out[item][NY][NX] real, scaled (irfftn "backward" normalisation)
-template <int NX>
+template <int MX, bool BLU>
 __global__ void __launch_bounds__(kThreads)
-rows_inverse_store_kernel(const float2* __restrict__ tmp, int NY, int KX, const float2* __restrict__ tw, float scale,
+rows_inverse_store_kernel(const float2* __restrict__ tmp, int NY, int KX, AxisPlan plan, float scale,
                           float* __restrict__ out) {
-  constexpr int B = batch_for(NX);
-  constexpr int STRIDE = padded_len(NX);
+  constexpr int B = batch_for(MX);
+  constexpr int STRIDE = padded_len(MX);
+  const int NX = BLU ? plan.n : MX;
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B * STRIDE;
@@ -326,10 +444,10 @@ rows_inverse_store_kernel(const float2* __restrict__ tmp, int NY, int KX, const 
   __syncthreads();
   for (int s = 0; s < B; ++s) {
     const int ya = row0 + 2 * s, yb = ya + 1;
-    if (ya < NY) load_c2r_pair<NX>(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, a + s * STRIDE);
+    if (ya < NY) load_c2r_pair(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, NX, a + s * STRIDE);
   }
   __syncthreads();
-  const float2* r = tmcfft::fft_forward<NX, B, kThreads>(a, b, tw);
+  const float2* r = dft_smem<MX, BLU>(a, b, plan);
   float* dst = out + item * NY * NX;
   for (int idx = threadIdx.x; idx < B * NX; idx += kThreads) {
     const int s = idx / NX, x = idx % NX;
@@ -429,9 +547,34 @@ __global__ void fourier_shift_kernel(float2* __restrict__ spec, int T, int NY, i
 
 // ---- dispatch helpers ------------------------------------------------------------------------
 
-#define TMC_FOR_EACH_N(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
+#define TMC_FOR_EACH_M(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
 
-inline bool supported_n(int n) { return n >= 16 && n <= 8192 && (n & (n - 1)) == 0; }
+template <int V>
+struct IntC {
+  static constexpr int value = V;
+};
+template <bool V>
+struct BoolC {
+  static constexpr bool value = V;
+};
+
+// calls f(IntC<M>{}, BoolC<BLU>{}) for the FFT size / algorithm that serves a length-n transform
+template <typename F>
+int dispatch_fft(int n, const char* who, F&& f) {
+  const int m = fft_size_for(n);
+  const bool blu = m != n;
+  switch (m) {
+#define CASE(MM) \
+  case MM:       \
+    return blu ? f(IntC<MM>{}, BoolC<true>{}) : f(IntC<MM>{}, BoolC<false>{});
+    TMC_FOR_EACH_M(CASE)
+#undef CASE
+    default:
+      break;
+  }
+  tmc_set_error("%s: transform length %d is not supported (powers of two up to 8192, any length up to 4096)", who, n);
+  return TMC_ERR_UNSUPPORTED;
+}
 
 template <typename K>
 int enable_smem(K kernel, size_t bytes) {
@@ -449,13 +592,61 @@ int enable_smem(K kernel, size_t bytes) {
 
 // ---- C ABI ---------------------------------------------------------------------------------------
 
-TMC_API int tmc_fft_supported_length(int n) { return supported_n(n) ? 1 : 0; }
+TMC_API int tmc_fft_supported_length(int n) { return fft_size_for(n) > 0 ? 1 : 0; }
 
-// tw: n complex64 values exp(-2 pi i m / n)
-TMC_API int tmc_fft_twiddles(int n, void* tw, cudaStream_t stream) {
-  TMC_CHECK_ARG(tw && n >= 2, "fft_twiddles: bad arguments");
-  twiddle_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(n, (float2*)tw); tmc_count_launch();
-  TMC_CHECK_LAUNCH("tmc_fft_twiddles");
+// complex64 elements of the plan buffer for a length-n transform (0: unsupported length)
+TMC_API long tmc_fft_plan_elems(int n) {
+  const int m = fft_size_for(n);
+  if (m == 0) return 0;
+  return m == n ? (long)m : 2l * m + n;
+}
+
+// fills `plan` (tmc_fft_plan_elems(n) complex64): twiddles [+ Bluestein chirp and filter spectrum]
+TMC_API int tmc_fft_plan_init(int n, void* plan, cudaStream_t stream) {
+  TMC_CHECK_ARG(plan, "fft_plan_init: null pointer");
+  const int m = fft_size_for(n);
+  if (m == 0) {
+    tmc_set_error("fft_plan_init: transform length %d is not supported", n);
+    return TMC_ERR_UNSUPPORTED;
+  }
+  float2* tw = (float2*)plan;
+  twiddle_kernel<<<tmc_div_up(m, 128), 128, 0, stream>>>(m, tw); tmc_count_launch();
+  if (m != n) {
+    float2* chirp = tw + m;
+    float2* bhat = chirp + n;
+    chirp_kernel<<<tmc_div_up(m, 128), 128, 0, stream>>>(n, m, chirp, bhat); tmc_count_launch();
+    // bhat <- FFT_m(bhat) in place (one row, plain power-of-two transform)
+    AxisPlan p;
+    p.tw = tw;
+    p.chirp = nullptr;
+    p.bhat = nullptr;
+    p.n = m;
+    int rc = dispatch_fft(m, "fft_plan_init", [&](auto M, auto) {
+      constexpr int MM = decltype(M)::value;
+      if (int e = enable_smem(c2c_rows_kernel<MM, false>, fft_smem_bytes<MM>())) return e;
+      c2c_rows_kernel<MM, false><<<1, kThreads, fft_smem_bytes<MM>(), stream>>>(bhat, 1, p, bhat); tmc_count_launch();
+      return TMC_OK;
+    });
+    if (rc) return rc;
+  }
+  TMC_CHECK_LAUNCH("tmc_fft_plan_init");
+  return TMC_OK;
+}
+
+// out[r] = DFT_n(in[r]) (inverse != 0: unnormalised inverse) for `rows` complex64 rows; in may equal out
+TMC_API int tmc_fft_c2c_rows(const void* in, int rows, int n, const void* plan, void* out, cudaStream_t stream) {
+  TMC_CHECK_ARG(in && out && plan && rows >= 1, "fft_c2c_rows: bad arguments");
+  AxisPlan p = make_axis_plan(plan, n);
+  int rc = dispatch_fft(n, "fft_c2c_rows", [&](auto M, auto BLU) {
+    constexpr int MM = decltype(M)::value;
+    constexpr bool BB = decltype(BLU)::value;
+    if (int e = enable_smem(c2c_rows_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
+    c2c_rows_kernel<MM, BB><<<tmc_div_up(rows, batch_for(MM)), kThreads, fft_smem_bytes<MM>(), stream>>>(
+        (const float2*)in, rows, p, (float2*)out); tmc_count_launch();
+    return TMC_OK;
+  });
+  if (rc) return rc;
+  TMC_CHECK_LAUNCH("tmc_fft_c2c_rows");
   return TMC_OK;
 }
 
@@ -463,48 +654,41 @@ TMC_API int tmc_fft_twiddles(int n, void* tw, cudaStream_t stream) {
 //  image (T,H,W) f32; mean_std nullable device float[2]; mask (ny,nx) f32 nullable;
 //  jobs (njobs,6) int32 device = {frame_a, exp_a, frame_b (-1: none), exp_b, y0, x0};
 //  rows [ylo,yhi) are the only non-zero rows of the mask; kx in [0,KX), ky in [ky_start, ky_start+KY);
-//  weight (KY,KX) f32 nullable; tw_x/tw_y twiddles for nx/ny; tmp: 2*njobs*ny*KX complex64;
-//  out: (2*njobs, KY, KX) complex64, plane 2*job+0 = a, 2*job+1 = b.
+//  weight (KY,KX) f32 nullable; plan_x/plan_y: tmc_fft_plan_init buffers for nx/ny;
+//  tmp: 2*njobs*ny*KX complex64; out: (2*njobs, KY, KX) complex64, plane 2*job+0 = a, 2*job+1 = b.
 TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float* mean_std, const float* mask, int ny, int nx,
                            const int* jobs, int njobs, int ylo, int yhi, int kx_count, int ky_count, int ky_start,
-                           const float* weight, const void* tw_x, const void* tw_y, void* tmp, void* out,
+                           const float* weight, const void* plan_x, const void* plan_y, void* tmp, void* out,
                            cudaStream_t stream) {
-  TMC_CHECK_ARG(image && jobs && tw_x && tw_y && tmp && out, "rfft2_band: null pointer");
+  TMC_CHECK_ARG(image && jobs && plan_x && plan_y && tmp && out, "rfft2_band: null pointer");
   TMC_CHECK_ARG(njobs >= 0 && t >= 1 && h >= ny && w >= nx, "rfft2_band: window (%d,%d) larger than image (%d,%d)", ny, nx, h, w);
   TMC_CHECK_ARG(0 <= ylo && ylo <= yhi && yhi <= ny, "rfft2_band: bad row support [%d,%d)", ylo, yhi);
   TMC_CHECK_ARG(kx_count >= 1 && kx_count <= nx / 2 + 1 && ky_count >= 1 && ky_count <= ny, "rfft2_band: bad band box");
-  if (!supported_n(nx) || !supported_n(ny)) {
-    tmc_set_error("rfft2_band: transform lengths must be powers of two in [16, 8192], got (%d, %d)", ny, nx);
-    return TMC_ERR_UNSUPPORTED;
-  }
   if (njobs == 0) return TMC_OK;
-  bool done = false;
-#define ROWS(N)                                                                                                  \
-  if (nx == N) {                                                                                                 \
-    if (int e = enable_smem(rows_forward_kernel<N>, fft_smem_bytes<N>())) return e;                              \
-    dim3 grid(tmc_div_up(yhi - ylo, batch_for(N)), njobs);                                                       \
-    if (yhi > ylo)                                                                                               \
-      rows_forward_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                                   \
-          image, h, w, mean_std, mask, jobs, ylo, yhi, ny, kx_count, (const float2*)tw_x, (float2*)tmp); tmc_count_launch();         \
-    done = true;                                                                                                 \
-  }
-  TMC_FOR_EACH_N(ROWS)
-#undef ROWS
-  TMC_CHECK_ARG(done, "rfft2_band: unsupported nx %d", nx);
+  const AxisPlan px = make_axis_plan(plan_x, nx), py = make_axis_plan(plan_y, ny);
+  int rc = dispatch_fft(nx, "rfft2_band", [&](auto M, auto BLU) {
+    constexpr int MM = decltype(M)::value;
+    constexpr bool BB = decltype(BLU)::value;
+    if (int e = enable_smem(rows_forward_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
+    dim3 grid(tmc_div_up(yhi - ylo, batch_for(MM)), njobs);
+    if (yhi > ylo) {
+      rows_forward_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>(image, h, w, mean_std, mask, jobs, ylo, yhi,
+                                                                                   ny, kx_count, px, (float2*)tmp); tmc_count_launch();
+    }
+    return TMC_OK;
+  });
+  if (rc) return rc;
   TMC_CHECK_LAUNCH("tmc_rfft2_band(rows)");
-  done = false;
-#define COLS(N)                                                                                                       \
-  if (ny == N) {                                                                                                      \
-    if (int e = enable_smem(cols_forward_kernel<N>, fft_smem_bytes<N>())) return e;                                   \
-    dim3 grid(tmc_div_up(kx_count, batch_for(N)), 2 * njobs);                                                         \
-    cols_forward_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>((const float2*)tmp, ylo, yhi, kx_count,  \
-                                                                           ky_count, ky_start, weight,               \
-                                                                           (const float2*)tw_y, (float2*)out); tmc_count_launch();       \
-    done = true;                                                                                                      \
-  }
-  TMC_FOR_EACH_N(COLS)
-#undef COLS
-  TMC_CHECK_ARG(done, "rfft2_band: unsupported ny %d", ny);
+  rc = dispatch_fft(ny, "rfft2_band", [&](auto M, auto BLU) {
+    constexpr int MM = decltype(M)::value;
+    constexpr bool BB = decltype(BLU)::value;
+    if (int e = enable_smem(cols_forward_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
+    dim3 grid(tmc_div_up(kx_count, batch_for(MM)), 2 * njobs);
+    cols_forward_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ylo, yhi, kx_count, ky_count,
+                                                                                 ky_start, weight, py, (float2*)out); tmc_count_launch();
+    return TMC_OK;
+  });
+  if (rc) return rc;
   TMC_CHECK_LAUNCH("tmc_rfft2_band(cols)");
   return TMC_OK;
 }
@@ -532,47 +716,43 @@ TMC_API int tmc_xc_leave_one_out_products(const void* spec, int t, int g, long p
   return TMC_OK;
 }
 
-TMC_API int tmc_xc_peak_partials(int ny, int nx) { return supported_n(nx) ? tmc_div_up(ny, 2 * batch_for(nx)) : -1; }
+TMC_API int tmc_xc_peak_partials(int ny, int nx) {
+  const int m = fft_size_for(nx);
+  return m ? tmc_div_up(ny, 2 * batch_for(m)) : -1;
+}
 
 // Inverse 2-D transform of band-limited products + argmax (+ parabola) + wrap.
 //  prod (nitems, KY, KX) complex64; tmp: nitems*ny*KX complex64; partial: nitems*tmc_xc_peak_partials(ny,nx)*8 bytes;
 //  shifts (nitems, 2) f32 = (dy, dx) px.
 TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_count, int ky_count, int ky_start,
-                         int sub_pixel, const void* tw_x, const void* tw_y, void* tmp, void* partial, float* shifts,
+                         int sub_pixel, const void* plan_x, const void* plan_y, void* tmp, void* partial, float* shifts,
                          cudaStream_t stream) {
-  TMC_CHECK_ARG(prod && tw_x && tw_y && tmp && partial && shifts, "xc_peaks: null pointer");
+  TMC_CHECK_ARG(prod && plan_x && plan_y && tmp && partial && shifts, "xc_peaks: null pointer");
   TMC_CHECK_ARG(kx_count >= 1 && kx_count <= nx / 2 + 1 && ky_count >= 1 && ky_count <= ny, "xc_peaks: bad band box");
-  if (!supported_n(nx) || !supported_n(ny)) {
-    tmc_set_error("xc_peaks: transform lengths must be powers of two in [16, 8192], got (%d, %d)", ny, nx);
-    return TMC_ERR_UNSUPPORTED;
-  }
   if (nitems == 0) return TMC_OK;
-  bool done = false;
-#define COLS(N)                                                                                                  \
-  if (ny == N) {                                                                                                 \
-    if (int e = enable_smem(cols_inverse_kernel<N>, fft_smem_bytes<N>())) return e;                              \
-    dim3 grid(tmc_div_up(kx_count, batch_for(N)), nitems);                                                       \
-    cols_inverse_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                                     \
-        (const float2*)prod, kx_count, ky_count, ky_start, (const float2*)tw_y, (float2*)tmp); tmc_count_launch();                   \
-    done = true;                                                                                                 \
-  }
-  TMC_FOR_EACH_N(COLS)
-#undef COLS
-  TMC_CHECK_ARG(done, "xc_peaks: unsupported ny %d", ny);
+  const AxisPlan px = make_axis_plan(plan_x, nx), py = make_axis_plan(plan_y, ny);
+  int rc = dispatch_fft(ny, "xc_peaks", [&](auto M, auto BLU) {
+    constexpr int MM = decltype(M)::value;
+    constexpr bool BB = decltype(BLU)::value;
+    if (int e = enable_smem(cols_inverse_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
+    dim3 grid(tmc_div_up(kx_count, batch_for(MM)), nitems);
+    cols_inverse_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)prod, kx_count, ky_count, ky_start,
+                                                                                 py, (float2*)tmp); tmc_count_launch();
+    return TMC_OK;
+  });
+  if (rc) return rc;
   TMC_CHECK_LAUNCH("tmc_xc_peaks(cols)");
   const int nparts = tmc_xc_peak_partials(ny, nx);
-  done = false;
-#define ROWS(N)                                                                                                   \
-  if (nx == N) {                                                                                                  \
-    if (int e = enable_smem(rows_inverse_argmax_kernel<N>, fft_smem_bytes<N>())) return e;                        \
-    dim3 grid(nparts, nitems);                                                                                    \
-    rows_inverse_argmax_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                               \
-        (const float2*)tmp, ny, kx_count, (const float2*)tw_x, (PeakCandidate*)partial); tmc_count_launch();                          \
-    done = true;                                                                                                  \
-  }
-  TMC_FOR_EACH_N(ROWS)
-#undef ROWS
-  TMC_CHECK_ARG(done, "xc_peaks: unsupported nx %d", nx);
+  rc = dispatch_fft(nx, "xc_peaks", [&](auto M, auto BLU) {
+    constexpr int MM = decltype(M)::value;
+    constexpr bool BB = decltype(BLU)::value;
+    if (int e = enable_smem(rows_inverse_argmax_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
+    dim3 grid(nparts, nitems);
+    rows_inverse_argmax_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ny, kx_count, px,
+                                                                                        (PeakCandidate*)partial); tmc_count_launch();
+    return TMC_OK;
+  });
+  if (rc) return rc;
   TMC_CHECK_LAUNCH("tmc_xc_peaks(rows)");
   peak_finalize_kernel<<<nitems, 128, 0, stream>>>((const float2*)tmp, (const PeakCandidate*)partial, nparts, ny, nx,
                                                    kx_count, sub_pixel, shifts); tmc_count_launch();
@@ -581,39 +761,31 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
 }
 
 // Full inverse: spec (nitems, ny, nx/2+1) complex64 -> out (nitems, ny, nx) f32 (irfftn, backward norm)
-TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const void* tw_x, const void* tw_y, void* tmp,
+TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const void* plan_x, const void* plan_y, void* tmp,
                             float* out, cudaStream_t stream) {
-  TMC_CHECK_ARG(spec && tw_x && tw_y && tmp && out, "irfft2_full: null pointer");
-  if (!supported_n(nx) || !supported_n(ny)) {
-    tmc_set_error("irfft2_full: transform lengths must be powers of two in [16, 8192], got (%d, %d)", ny, nx);
-    return TMC_ERR_UNSUPPORTED;
-  }
+  TMC_CHECK_ARG(spec && plan_x && plan_y && tmp && out, "irfft2_full: null pointer");
   if (nitems == 0) return TMC_OK;
   const int kx = nx / 2 + 1;
-  bool done = false;
-#define COLS(N)                                                                                                  \
-  if (ny == N) {                                                                                                 \
-    if (int e = enable_smem(cols_inverse_kernel<N>, fft_smem_bytes<N>())) return e;                              \
-    dim3 grid(tmc_div_up(kx, batch_for(N)), nitems);                                                             \
-    cols_inverse_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>((const float2*)spec, kx, ny, 0,      \
-                                                                           (const float2*)tw_y, (float2*)tmp); tmc_count_launch();   \
-    done = true;                                                                                                 \
-  }
-  TMC_FOR_EACH_N(COLS)
-#undef COLS
-  TMC_CHECK_ARG(done, "irfft2_full: unsupported ny %d", ny);
-  done = false;
-#define ROWS(N)                                                                                                    \
-  if (nx == N) {                                                                                                   \
-    if (int e = enable_smem(rows_inverse_store_kernel<N>, fft_smem_bytes<N>())) return e;                          \
-    dim3 grid(tmc_div_up(ny, 2 * batch_for(N)), nitems);                                                           \
-    rows_inverse_store_kernel<N><<<grid, kThreads, fft_smem_bytes<N>(), stream>>>(                                 \
-        (const float2*)tmp, ny, kx, (const float2*)tw_x, 1.0f / ((float)nx * (float)ny), out); tmc_count_launch();                     \
-    done = true;                                                                                                   \
-  }
-  TMC_FOR_EACH_N(ROWS)
-#undef ROWS
-  TMC_CHECK_ARG(done, "irfft2_full: unsupported nx %d", nx);
+  const AxisPlan px = make_axis_plan(plan_x, nx), py = make_axis_plan(plan_y, ny);
+  int rc = dispatch_fft(ny, "irfft2_full", [&](auto M, auto BLU) {
+    constexpr int MM = decltype(M)::value;
+    constexpr bool BB = decltype(BLU)::value;
+    if (int e = enable_smem(cols_inverse_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
+    dim3 grid(tmc_div_up(kx, batch_for(MM)), nitems);
+    cols_inverse_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)spec, kx, ny, 0, py, (float2*)tmp); tmc_count_launch();
+    return TMC_OK;
+  });
+  if (rc) return rc;
+  rc = dispatch_fft(nx, "irfft2_full", [&](auto M, auto BLU) {
+    constexpr int MM = decltype(M)::value;
+    constexpr bool BB = decltype(BLU)::value;
+    if (int e = enable_smem(rows_inverse_store_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
+    dim3 grid(tmc_div_up(ny, 2 * batch_for(MM)), nitems);
+    rows_inverse_store_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ny, kx, px,
+                                                                                       1.0f / ((float)nx * (float)ny), out); tmc_count_launch();
+    return TMC_OK;
+  });
+  if (rc) return rc;
   TMC_CHECK_LAUNCH("tmc_irfft2_full");
   return TMC_OK;
 }

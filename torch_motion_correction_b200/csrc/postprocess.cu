@@ -175,3 +175,11 @@ TMC_API int tmc_global_shifts_to_field(const float* shifts, int t, float pixel_s
   TMC_CHECK_LAUNCH("tmc_global_shifts_to_field");
   return TMC_OK;
 }
+
+// data -= mean(data), one joint scalar (quirk Q4: estimate_motion_optimizer.py:148,432-434)
+TMC_API int tmc_subtract_mean(float* data, long n, cudaStream_t stream) {
+  TMC_CHECK_ARG(data && n >= 1, "subtract_mean: bad arguments");
+  subtract_mean_kernel<<<1, 256, 0, stream>>>(data, n); tmc_count_launch();
+  TMC_CHECK_LAUNCH("tmc_subtract_mean");
+  return TMC_OK;
+}

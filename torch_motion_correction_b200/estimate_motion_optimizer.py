@@ -1,0 +1,231 @@
+"""Spline-coefficient optimisation of local motion (mirror of the reference's
+``estimate_motion_optimizer.py``).
+
+The forward model and its gradient are closed-form CUDA kernels (``csrc/optimizer.cu``): the
+masked patch spectra are transformed ONCE (the reference re-does the FFTs every iteration, quirk
+Q19) and only their pass band is kept; each iteration evaluates the two spline grids at the patch
+centres, the loss, dL/d(shifts) and scatters that back onto the coefficients.  ``torch.optim``
+drives the coefficient update exactly as in the reference (same defaults)."""
+
+from __future__ import annotations
+
+import random
+from typing import Any, cast
+
+import torch
+
+from . import _fourier, _ops
+from ._common import as_f32, grid_kind, resolve_device
+from ._lib import call, ptr, query, stream_ptr
+from .deformation_field_utils import resample_deformation_field
+from .optimization_state import OptimizationTracker
+from .patch_grid import patch_grid_centers
+
+LOSS_TYPES = {"mse": 0, "cc": 1, "ncc": 2}
+
+
+def _setup_optimizer(optimizer_type: str, parameters, **kwargs: Any) -> torch.optim.Optimizer:
+    """Same optimisers and defaults as the reference (estimate_motion_optimizer.py:513-608)."""
+    name = optimizer_type.lower()
+    if name == "adam":
+        return torch.optim.Adam(
+            parameters, lr=kwargs.get("lr", 0.01), betas=kwargs.get("betas", (0.9, 0.999)), eps=kwargs.get("eps", 1e-08),
+            weight_decay=kwargs.get("weight_decay", 0), amsgrad=kwargs.get("amsgrad", False),
+        )
+    if name == "sgd":
+        return torch.optim.SGD(
+            parameters, lr=kwargs.get("lr", 0.01), momentum=kwargs.get("momentum", 0.9),
+            weight_decay=kwargs.get("weight_decay", 0), dampening=kwargs.get("dampening", 0), nesterov=kwargs.get("nesterov", True),
+        )
+    if name == "rmsprop":
+        return torch.optim.RMSprop(
+            parameters, lr=kwargs.get("lr", 0.01), alpha=kwargs.get("alpha", 0.99), eps=kwargs.get("eps", 1e-08),
+            weight_decay=kwargs.get("weight_decay", 0), momentum=kwargs.get("momentum", 0), centered=kwargs.get("centered", False),
+        )
+    if name == "lbfgs":
+        max_iter = cast(int, kwargs.get("max_iter", 1))
+        max_eval = kwargs.get("max_eval", None)
+        if max_eval is None:
+            max_eval = max(1, int(max_iter * 1.25))
+        return torch.optim.LBFGS(
+            parameters, lr=kwargs.get("lr", 1), max_iter=max_iter, max_eval=max_eval,
+            tolerance_grad=kwargs.get("tolerance_grad", 1e-11), tolerance_change=kwargs.get("tolerance_change", 1e-11),
+            history_size=kwargs.get("history_size", 5), line_search_fn=kwargs.get("line_search_fn", "strong_wolfe"),
+        )
+    raise ValueError(f"Unsupported optimizer: {optimizer_type}. Choose 'adam', 'sgd', 'rmsprop', or 'lbfgs'.")
+
+
+class LocalMotionProblem:
+    """Device-resident state of one ``estimate_local_motion`` call: band-limited patch spectra,
+    their norms, normalised patch centres and the frozen base grid's values at the centres."""
+
+    def __init__(self, image, pixel_spacing, patch_shape, resolution, initial_field, dev, b_factor, frequency_range,
+                 grid_type, loss_type):
+        if loss_type not in LOSS_TYPES:
+            raise ValueError(f"Invalid loss type: {loss_type}. Must be 'mse', 'cc' or 'ncc'.")
+        self.kind = grid_kind(grid_type)
+        self.loss_type = LOSS_TYPES[loss_type]
+        self.dev = dev
+        self.px = float(pixel_spacing)
+        movie = as_f32(image, dev)
+        t, h, w = movie.shape
+        ph, pw = patch_shape
+        self.t, self.ph, self.pw = t, ph, pw
+        self.resolution = tuple(int(r) for r in resolution)
+        stats = _ops.stack_stats(movie)
+        centers = patch_grid_centers((t, h, w), (1, ph, pw), (1, ph // 2, pw // 2), distribute_patches=True)
+        self.centers = centers
+        gh, gw = centers.shape[1:3]
+        self.g = gh * gw
+        flat = centers[0].reshape(-1, 3)
+        # patch window = floor(centre) - p // 2, no clipping (patch_utils.py:117-120,173-183; quirk Q20)
+        y0 = (flat[:, 1] - ph // 2).tolist()
+        x0 = (flat[:, 2] - pw // 2).tolist()
+        if min(y0) < 0 or min(x0) < 0 or max(y0) + ph > h or max(x0) + pw > w:
+            raise AssertionError(f"Patch size {tuple(patch_shape)} too large for control points in image of shape {(t, h, w)}")
+
+        # frozen base grid (estimate_motion_optimizer.py:135-158)
+        if initial_field is None:
+            base = torch.zeros((2, *self.resolution), dtype=torch.float32, device=dev)
+        else:
+            base = resample_deformation_field(as_f32(initial_field, dev), self.resolution)
+            with torch.cuda.device(dev):
+                call("tmc_subtract_mean", ptr(base), base.numel(), stream_ptr(dev))
+        self.base = base
+
+        # spectra FW[g][t] = rfft2(mask * patch) * band * envelope on the pass-band box
+        self.plan = _fourier.BandPlan(ph, pw, dev, pixel_spacing, b_factor, frequency_range)
+        mask, ylo, yhi = _fourier.soft_disc_mask((ph, pw), pw / 4, pw / 4, dev)  # quirk Q18: smoothing pw/4
+        self.tp = 2 * ((t + 1) // 2)
+        jobs = []
+        for gi in range(self.g):
+            for i in range(0, t, 2):
+                jobs.append([i, 1, i + 1 if i + 1 < t else -1, 1, y0[gi], x0[gi]])
+        jobs = torch.tensor(jobs, dtype=torch.int32).to(dev)
+        self.spec = self.plan.forward(movie, stats, mask, ylo, yhi, jobs)  # (g * tp, KY, KX, 2)
+        self.norms = torch.empty((self.g, t, 2), dtype=torch.float64, device=dev)
+        p = self.plan
+        with torch.cuda.device(dev):
+            call("tmc_local_spectra_norms", ptr(self.spec), self.g, t, self.tp, ph, pw, p.ky, p.kx, p.ky_start,
+                 ptr(self.norms), stream_ptr(dev))
+
+        # normalised (t, y, x) centres, (T, G, 3) time-major (patch_utils.py:88-93,157-172; quirk Q10)
+        norm = centers.clone().float()
+        norm[..., 0] /= float(t - 1) if t > 1 else float("nan")
+        norm[..., 1] /= float(h - 1)
+        norm[..., 2] /= float(w - 1)
+        self.centres_norm = norm.reshape(t, self.g, 3).contiguous().to(dev)
+        self.eval_base = _ops.spline_eval(base, self.kind, self.centres_norm)  # (T, G, 2)
+        ws_bytes = query("tmc_local_loss_workspace_bytes", self.g, t, p.ky, p.kx)
+        self.workspace = torch.empty(((ws_bytes + 7) // 8,), dtype=torch.float64, device=dev)
+        self.loss = torch.zeros((1,), dtype=torch.float64, device=dev)
+        self.grad_eval = torch.empty((t, self.g, 2), dtype=torch.float32, device=dev)
+
+    def patch_scales(self, batches) -> torch.Tensor:
+        """Per-patch weight reproducing the reference's per-mini-batch ``mean`` (quirk Q11): the
+        gradient is the SUM over mini-batches of each batch's mean-reduced loss."""
+        scale = [0.0] * self.g
+        for batch in batches:
+            b = len(batch)
+            if self.loss_type == 0:
+                s = 1.0 / (b * self.t * self.ph * (self.pw // 2 + 1)) / (self.ph * self.pw)
+            else:
+                s = 1.0 / (b * self.t)
+            for gi in batch:
+                scale[gi] = s
+        return scale
+
+    def loss_and_grad(self, new_data: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+        """Sum over mini-batches of the batch losses (device float64 (1,)) and d/d new_data."""
+        eval_new = _ops.spline_eval(new_data, self.kind, self.centres_norm)
+        p = self.plan
+        with torch.cuda.device(self.dev):
+            call("tmc_local_loss_grad", ptr(self.spec), ptr(self.norms), ptr(eval_new), ptr(self.eval_base), ptr(scale),
+                 self.g, self.t, self.tp, self.ph, self.pw, p.ky, p.kx, p.ky_start, self.px, self.loss_type, ptr(self.loss),
+                 ptr(self.grad_eval), ptr(self.workspace), stream_ptr(self.dev))
+        grad = _ops.spline_eval_backward((2, *self.resolution), self.kind, self.centres_norm, self.grad_eval)
+        return self.loss, grad
+
+
+def _shuffled_batches(n_patches: int, batch_size: int):
+    """``ImagePatchIterator.get_iterator`` order: ``random.shuffle`` of the flat patch indices
+    (patch_utils.py:157-172); seed ``random`` to make runs repeatable, as with the reference."""
+    order = list(range(n_patches))
+    random.shuffle(order)
+    return [order[i : i + batch_size] for i in range(0, n_patches, batch_size)]
+
+
+def estimate_local_motion(
+    image: torch.Tensor,
+    pixel_spacing: float,
+    patch_shape: tuple[int, int],
+    deformation_field_resolution: tuple[int, int, int],
+    initial_deformation_field: torch.Tensor | None,
+    device: torch.device = None,
+    n_iterations: int = 100,
+    b_factor: float = 500,
+    frequency_range: tuple[float, float] = (300, 10),
+    optimizer_type: str = "adam",
+    grid_type: str = "catmull_rom",
+    loss_type: str = "mse",
+    optimizer_kwargs: dict | None = None,
+    return_trajectory: bool = False,
+    trajectory_kwargs: dict | None = None,
+) -> torch.Tensor | tuple[torch.Tensor, OptimizationTracker]:
+    """Optimise a learnable (2, nt, nh, nw) spline grid added to a frozen base grid so that the
+    Fourier-shifted patches of every frame agree with the mean of the other frames.
+
+    Reference: estimate_motion_optimizer.py:28-439.  Returns the (2, nt, nh, nw) Angstrom field
+    (and an ``OptimizationTracker`` when ``return_trajectory``)."""
+    dev = resolve_device(image, device)
+    if return_trajectory:
+        trajectory_kwargs = trajectory_kwargs if trajectory_kwargs is not None else {}
+        trajectory_kwargs.setdefault("sample_every_n_steps", 1)
+        trajectory_kwargs.setdefault("total_steps", n_iterations)
+        trajectory = OptimizationTracker(**trajectory_kwargs)
+    problem = LocalMotionProblem(
+        image, pixel_spacing, patch_shape, deformation_field_resolution, initial_deformation_field, dev, b_factor,
+        frequency_range, grid_type, loss_type,
+    )
+    kwargs = dict(optimizer_kwargs) if optimizer_kwargs is not None else {}
+    new = torch.nn.Parameter(torch.zeros((2, *problem.resolution), dtype=torch.float32, device=dev))
+    optimizer = _setup_optimizer(optimizer_type, [new], **kwargs)
+    is_lbfgs = optimizer_type.lower() == "lbfgs"
+    subsample = kwargs.get("lbfgs_patch_subsample", None) if is_lbfgs else None
+
+    for iter_idx in range(n_iterations):
+        if is_lbfgs:
+            state = {}
+
+            def closure():
+                optimizer.zero_grad()
+                batches = _shuffled_batches(problem.g, 1)
+                if subsample is not None:
+                    batches = batches[:subsample]
+                if not batches:
+                    return torch.tensor(0.0, device=dev, requires_grad=True)
+                scale = [s / len(batches) for s in problem.patch_scales(batches)]
+                loss, grad = problem.loss_and_grad(new.data, torch.tensor(scale, dtype=torch.float32).to(dev))
+                new.grad = grad
+                state["loss"] = loss.to(torch.float32).reshape(())
+                return state["loss"]
+
+            step_loss = optimizer.step(closure)
+            loss_value = float(step_loss) if return_trajectory else None
+        else:
+            batches = _shuffled_batches(problem.g, 8)
+            scale = torch.tensor(problem.patch_scales(batches), dtype=torch.float32).to(dev)
+            loss, grad = problem.loss_and_grad(new.data, scale)
+            new.grad = grad
+            optimizer.step()
+            optimizer.zero_grad()
+            loss_value = float(loss) / len(batches) if return_trajectory else None
+        if return_trajectory and trajectory.sample_this_step(iter_idx):
+            trajectory.add_checkpoint(deformation_field=new.data, loss=loss_value, step=iter_idx)
+
+    final = (new.data + problem.base).contiguous()
+    with torch.cuda.device(dev):
+        call("tmc_subtract_mean", ptr(final), final.numel(), stream_ptr(dev))
+    if return_trajectory:
+        return final, trajectory
+    return final
