@@ -1,0 +1,170 @@
+/* tmc_b200.h -- C ABI of libtmc_b200.so: B200 (sm_100a) kernels for the hot path of
+ * teamtomo/torch-motion-correction (patch-based Fourier cross-correlation motion estimation and
+ * cubic-spline deformation-field warping of cryo-EM movie stacks).
+ *
+ * The reference is a pure-Python/PyTorch package with no FFI of its own; its "operator interface" for
+ * this path are the Python callables re-exported at src/torch_motion_correction/__init__.py:12-44.
+ * Each entry point below replaces the arithmetic of one stage of those callables (cited as
+ * reference `file:line`, relative to /root/reference/src/torch_motion_correction/); the Python shims in
+ * torch_motion_correction_b200/ bind them with ctypes (see INTEGRATION.md for the binding a
+ * maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - no allocation inside: callers pass workspaces sized by the tmc_*_workspace_* queries;
+ *   - every compute call is asynchronous on `stream` (a cudaStream_t) of the CURRENT device;
+ *   - int-returning calls return 0 on success, 1 bad argument, 2 CUDA error, 3 unsupported;
+ *     tmc_last_error() holds a thread-local message for the last non-zero status;
+ *   - thread-safe for concurrent use from different host threads on different streams/devices;
+ *   - images are float32, spectra complex64 (interleaved re,im), indices int32;
+ *   - deformation fields are (2 [y,x], nt, nh, nw) float32 in Angstrom, spline `kind` 0 = Catmull-Rom,
+ *     1 = cubic B-spline on [0,1]^3 (t, y, x).
+ */
+#ifndef TMC_B200_H
+#define TMC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* tmc_stream_t; /* == cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int tmc_version(void);            /* 100 = 0.1.0 */
+const char* tmc_last_error(void); /* thread-local message of the last failing call (host pointer) */
+int tmc_sm_count(void);           /* SM count of the current device, -1 on error */
+long tmc_launch_count(void);      /* kernels launched by this library since load (bench bookkeeping) */
+
+/* ---- normalize_image statistics: utils.py:49-84 ------------------------------------------------ */
+/* mean and unbiased std of image[:, y0:y1, x0:x1] over ALL frames -> mean_std[2] (device).
+ * The affine (x - mean) / std itself is fused into the consumers (mean_std arguments below). */
+int tmc_stack_stats_workspace_doubles(void);
+int tmc_stack_stats(const float* image, int t, int h, int w, int y0, int y1, int x0, int x1, float* mean_std,
+                    double* workspace, tmc_stream_t stream);
+
+/* frame-split movies: raw moments {sum, sum of squares, count} (device double[3]) of the local frames;
+ * ranks all-reduce (SUM) them and convert once. */
+int tmc_stack_moments(const float* image, int t, int h, int w, int y0, int y1, int x0, int x1, double* moments,
+                      double* workspace, tmc_stream_t stream);
+int tmc_moments_to_mean_std(const double* moments, float* mean_std, tmc_stream_t stream);
+
+/* ---- cubic spline grids: torch_cubic_spline_grids.Cubic{CatmullRom,BSpline}Grid3d as used at
+ *      deformation_field_utils.py:9-93, estimate_motion_optimizer.py:487-490, correct_motion.py:288-305 */
+long tmc_spline_workspace_floats(int c, int n0, int n1, int n2);
+/* out (n, c) = grid(tyx (n, 3)) */
+int tmc_spline_eval(const float* coeffs, int c, int n0, int n1, int n2, int kind, const float* tyx, long n, float* out,
+                    float* workspace, tmc_stream_t stream);
+/* grad_coeffs (c, n0, n1, n2) = scale * B^T grad_out (n, c): the autograd transpose of tmc_spline_eval */
+int tmc_spline_eval_backward(int c, int n0, int n1, int n2, int kind, const float* tyx, long n, const float* grad_out,
+                             float scale, float* grad_coeffs, float* workspace, tmc_stream_t stream);
+/* evaluate_deformation_field_at_t for n_frames frames at once: lattice (n_frames, c, lh, lw) at
+ * t = linspace(0,1,total_frames)[frame_offset + f], y = linspace(0,1,lh), x = linspace(0,1,lw);
+ * coeffs2 (nullable, (c, m0, m1, m2), kind2) is added (correct_motion_two_grids).
+ * workspace: tmc_spline_workspace_floats(coeffs) + tmc_spline_workspace_floats(coeffs2) floats. */
+int tmc_spline_lattice(const float* coeffs, int c, int n0, int n1, int n2, int kind, const float* coeffs2, int m0, int m1,
+                       int m2, int kind2, int n_frames, int frame_offset, int total_frames, int lh, int lw, float* lattice,
+                       float* workspace, tmc_stream_t stream);
+
+/* ---- warp: correct_motion.py:81-185 (_correct_frame, get_pixel_shifts) + sample_image_2d -------- */
+long tmc_warp_workspace_floats(int t, int w, int lh);
+/* per pixel: bicubic(reflection) lookup of the frame's (2, lh, lw) Angstrom lattice -> / pixel_spacing ->
+ * bicubic (border-clamped taps, zero outside) gather of the frame.  out_stack (t,h,w) and/or out_sum (h,w)
+ * (fused sum over frames, never materialising the stack); accumulate_sum != 0 adds into out_sum (frame
+ * blocks of one movie).  mean_std nullable: output is (v - mean) / std of the warped value. */
+int tmc_warp_lattice(const float* image, int t, int h, int w, const float* lattice, int lh, int lw, float pixel_spacing,
+                     const float* mean_std, float* out_stack, float* out_sum, int accumulate_sum, float* workspace,
+                     tmc_stream_t stream);
+/* get_pixel_shifts: (2, lh, lw) lattice -> (h, w, 2) px shifts */
+int tmc_pixel_shifts(const float* lattice, int lh, int lw, int h, int w, float pixel_spacing, float* out,
+                     tmc_stream_t stream);
+/* correct_motion_slow (correct_motion.py:371-427): out = bicubic(frame; pixel + shifts (t,h,w,2) px) */
+int tmc_warp_dense_shifts(const float* image, int t, int h, int w, const float* shifts, float* out_stack,
+                          tmc_stream_t stream);
+/* normalised (t, y, x) of every pixel: tyx (t, h, w, 3)  (correct_motion.py:401-409) */
+int tmc_pixel_tyx(int h, int w, int t, int frame_offset, int total_frames, float* tyx, tmc_stream_t stream);
+
+/* ---- tables: torch_grid_utils.circle, torch_fourier_filter.{bandpass_filter,b_envelope} as used at
+ *      estimate_motion_xc.py:69-95,262-280, estimate_motion_optimizer.py:162-184, utils.py:87-114 ---- */
+/* soft-edged disc centred at (h/2, w/2): 1 inside radius, cos roll-off over the exact Euclidean distance
+ * transform up to smoothing_radius.  workspace: h ints. */
+int tmc_soft_disc_mask(int h, int w, float radius, float smoothing_radius, float* mask, int* workspace,
+                       tmc_stream_t stream);
+/* weight[kyb][kx] = (low < f <= high) * exp(-b_factor (f / pixel_size)^2 / 4) on the band box
+ * ky = ky_start + kyb (kyb < ky_count), kx < kx_count; f in cycles/px on the (ny, nx) rfft grid */
+int tmc_band_weights(int ny, int nx, int ky_count, int kx_count, int ky_start, float low, float high, int use_band,
+                     float b_factor, float pixel_size, int use_envelope, float* weight, tmc_stream_t stream);
+
+/* ---- FFT plans ------------------------------------------------------------------------------------ */
+int tmc_fft_supported_length(int n); /* powers of two in [16, 8192]; any other n in [2, 4096] (Bluestein) */
+long tmc_fft_plan_elems(int n);      /* complex64 elements of a plan buffer, 0 if unsupported */
+int tmc_fft_plan_init(int n, void* plan, tmc_stream_t stream);
+/* out[r] = DFT_n(in[r]) for `rows` complex64 rows (utility / tests) */
+int tmc_fft_c2c_rows(const void* in, int rows, int n, const void* plan, void* out, tmc_stream_t stream);
+
+/* ---- band-limited forward transform: torch.fft.rfftn(patch * mask) * bandpass * b_envelope at
+ *      estimate_motion_xc.py:77-98,338-346, estimate_motion_optimizer.py:371-372, correct_motion.py:484 */
+/* jobs (njobs, 6) int32 = {frame_a, mask_power_a, frame_b (-1: none), mask_power_b, y0, x0}: the (ny, nx)
+ * window at (y0, x0) of frame_a / frame_b, normalised with mean_std (nullable), times mask^power, packed as
+ * real / imaginary part of ONE complex transform.  Only rows [ylo, yhi) of the mask are non-zero.
+ * out (2 * njobs, ky_count, kx_count) complex64: plane 2*job = a, 2*job + 1 = b; ky = ky_start + kyb.
+ * tmp: 2 * njobs * ny * kx_count complex64. */
+int tmc_rfft2_band(const float* image, int t, int h, int w, const float* mean_std, const float* mask, int ny, int nx,
+                   const int* jobs, int njobs, int ylo, int yhi, int kx_count, int ky_count, int ky_start,
+                   const float* weight, const void* plan_x, const void* plan_y, void* tmp, void* out, tmc_stream_t stream);
+
+/* ---- cross-correlation products: estimate_motion_xc.py:112,310-349 ---------------------------------- */
+/* out[i] = conj(spec[ref_plane[i]]) * spec[cur_plane[i]] */
+int tmc_xc_pair_products(const void* spec, const int* ref_plane, const int* cur_plane, int nitems, long plane_elems,
+                         void* out, tmc_stream_t stream);
+/* leave-one-out mean reference incl. the reference's cache aliasing.  spec planes
+ * [t][g][2] (mask^1, mask^2) for ALL t frames; out items [k_count][g] for frames k_begin.. (a rank of a
+ * frame-split movie computes only its own frames); delta_offsets (t+1) / deltas: for frame k the signed
+ * (j+1) entries that toggle "frame j is double-masked" relative to frame k-1. */
+int tmc_xc_leave_one_out_products(const void* spec, int t, int g, long plane_elems, const int* delta_offsets,
+                                  const int* deltas, int k_begin, int k_count, void* out, tmc_stream_t stream);
+
+/* ---- inverse transform + peak: irfftn, argmax, parabola, wrap at estimate_motion_xc.py:113-121,350-369,414-483 */
+int tmc_xc_peak_partials(int ny, int nx);
+/* prod (nitems, ky_count, kx_count) -> shifts (nitems, 2) = (dy, dx) px.  tmp: nitems*ny*kx_count complex64;
+ * partial: nitems * tmc_xc_peak_partials(ny, nx) * 8 bytes. */
+int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_count, int ky_count, int ky_start, int sub_pixel,
+                 const void* plan_x, const void* plan_y, void* tmp, void* partial, float* shifts, tmc_stream_t stream);
+
+/* ---- whole-frame Fourier shift: correct_motion.py:484-496 + torch_fourier_shift.fourier_shift_dft_2d */
+/* spec (t, ny, nx/2+1) *= exp(-2 pi i (f_y s_y + f_x s_x)), (s_y, s_x)[f] = sign * field[(0|1) * t + f] */
+int tmc_fourier_shift(void* spec, int t, int ny, int nx, const float* field, float sign, tmc_stream_t stream);
+/* torch.fft.irfftn(spec, s=(ny, nx)): spec (nitems, ny, nx/2+1) -> out (nitems, ny, nx); tmp like spec */
+int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const void* plan_x, const void* plan_y, void* tmp,
+                    float* out, tmc_stream_t stream);
+
+/* ---- tail of the estimators: estimate_motion_xc.py:131-133,376-410,486-627 -------------------------- */
+/* shifts (t, g, 2) px; field (2, t, g) Angstrom = base field in, result out: per-frame outlier rejection,
+ * px -> Angstrom accumulate, Savitzky-Golay (polyorder 1, scipy mode="interp"), one joint mean removed.
+ * skip_frame: frame left untouched (middle_frame reference), -1 none.  scratch: 2*t*g floats. */
+int tmc_xc_postprocess(const float* shifts, int t, int g, float pixel_spacing, int skip_frame, int outlier_rejection,
+                       float outlier_threshold, int temporal_smoothing, int smoothing_window, int subtract_mean,
+                       float* field, float* scratch, tmc_stream_t stream);
+/* (t, 2) px -> (2, t, 1, 1) Angstrom, zero_frame forced to 0 (deformation_field_utils.py:129-162) */
+int tmc_global_shifts_to_field(const float* shifts, int t, float pixel_spacing, int zero_frame, float* field,
+                               tmc_stream_t stream);
+/* data -= mean(data): one joint scalar (estimate_motion_optimizer.py:148,432-434) */
+int tmc_subtract_mean(float* data, long n, tmc_stream_t stream);
+
+/* ---- spline-coefficient optimiser: estimate_motion_optimizer.py:371-407,442-510,611-671 -------------- */
+/* spec (g, tp, ky_count, kx_count): band-limited filtered spectra of every patch and frame (tp >= t planes
+ * per patch).  norms (g, t, 2) float64 = sum_f w |spec|^2 for w = 1 and Hermitian weights. */
+int tmc_local_spectra_norms(const void* spec, int g, int t, int tp, int ny, int nx, int ky_count, int kx_count,
+                            int ky_start, double* norms, tmc_stream_t stream);
+long tmc_local_loss_workspace_bytes(int g, int t, int ky_count, int kx_count);
+/* one loss + gradient evaluation: eval_new / eval_base (t, g, 2) spline values (Angstrom) at the patch
+ * centres; patch_scale (g): weight of each patch's mean-reduced mini-batch loss; loss_type 0 mse, 1 cc,
+ * 2 ncc.  Outputs: loss (device double, sum over mini-batches) and grad_eval (t, g, 2) = dloss/d eval_new. */
+int tmc_local_loss_grad(const void* spec, const double* norms, const float* eval_new, const float* eval_base,
+                        const float* patch_scale, int g, int t, int tp, int ny, int nx, int ky_count, int kx_count,
+                        int ky_start, float pixel_spacing, int loss_type, double* loss, float* grad_eval, void* workspace,
+                        tmc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMC_B200_H */

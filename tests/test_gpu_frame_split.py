@@ -1,0 +1,68 @@
+"""Frame-split (one movie over several ranks) vs the single-GPU pipeline.  Two gloo ranks share
+cuda:0 here (NCCL needs one GPU per rank; the NCCL path is exercised by tools/frame_split_check.py
+under `gpurun --gpus 2`)."""
+
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _movie():
+    from oracle import reference_path as rp
+
+    movie, _ = rp.synthetic_movie(7, 128, 128, seed=9, noise=0.6, drift=3.0, local=0.5, sigma_f=0.08)
+    return movie
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch_motion_correction_b200 as tmc
+        from torch_motion_correction_b200.distributed import frame_range, motion_correct_frame_split
+
+        dev = torch.device("cuda:0")
+        movie = _movie()
+        t = movie.shape[0]
+        f0, f1 = frame_range(t, rank, world)
+        total, field = motion_correct_frame_split(
+            movie[f0:f1].to(dev), 1.1, f0, t, patch_sidelength=64, frequency_range=(80, 5)
+        )
+        want_total, want_field = tmc.motion_correct(movie.to(dev), 1.1, patch_sidelength=64, frequency_range=(80, 5))
+        assert float((field - want_field).abs().max()) <= 1e-4, float((field - want_field).abs().max())
+        rel = float(torch.linalg.norm(total - want_total) / torch.linalg.norm(want_total))
+        assert rel <= 1e-5, rel
+        with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_split_matches_single_gpu_world2(tmp_path):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(2))
+
+
+def test_frame_split_world1_degenerates_to_single_gpu():
+    import torch_motion_correction_b200 as tmc
+    from torch_motion_correction_b200.distributed import motion_correct_frame_split
+
+    dev = torch.device("cuda:0")
+    movie = _movie().to(dev)
+    total, field = motion_correct_frame_split(movie, 1.1, 0, movie.shape[0], patch_sidelength=64, frequency_range=(80, 5))
+    want_total, want_field = tmc.motion_correct(movie, 1.1, patch_sidelength=64, frequency_range=(80, 5))
+    assert float((field - want_field).abs().max()) <= 1e-5
+    assert float(torch.linalg.norm(total - want_total) / torch.linalg.norm(want_total)) <= 1e-6

@@ -185,9 +185,12 @@ def pair_products(spec: torch.Tensor, ref_plane: torch.Tensor, cur_plane: torch.
     return out
 
 
-def leave_one_out_products(spec: torch.Tensor, t: int, g: int, plane_elems: int, delta_offsets, deltas) -> torch.Tensor:
-    out = torch.empty((t * g, plane_elems, 2), dtype=torch.float32, device=spec.device)
+def leave_one_out_products(spec: torch.Tensor, t: int, g: int, plane_elems: int, delta_offsets, deltas,
+                           k_begin: int = 0, k_count: int | None = None) -> torch.Tensor:
+    """Products for frames [k_begin, k_begin + k_count) given the spectra of ALL t frames."""
+    k_count = t - k_begin if k_count is None else k_count
+    out = torch.empty((k_count * g, plane_elems, 2), dtype=torch.float32, device=spec.device)
     with torch.cuda.device(spec.device):
-        call("tmc_xc_leave_one_out_products", ptr(spec), t, g, plane_elems, ptr(delta_offsets), ptr(deltas), ptr(out),
-             stream_ptr(spec.device))
+        call("tmc_xc_leave_one_out_products", ptr(spec), t, g, plane_elems, ptr(delta_offsets), ptr(deltas), k_begin, k_count,
+             ptr(out), stream_ptr(spec.device))
     return out

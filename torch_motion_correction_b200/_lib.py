@@ -31,6 +31,8 @@ _SIGNATURES = {
     "tmc_launch_count": (L, []),
     "tmc_stack_stats_workspace_doubles": (I, []),
     "tmc_stack_stats": (I, [P, I, I, I, I, I, I, I, P, P, P]),
+    "tmc_stack_moments": (I, [P, I, I, I, I, I, I, I, P, P, P]),
+    "tmc_moments_to_mean_std": (I, [P, P, P]),
     "tmc_spline_workspace_floats": (L, [I, I, I, I]),
     "tmc_spline_eval": (I, [P, I, I, I, I, I, P, L, P, P, P]),
     "tmc_spline_eval_backward": (I, [I, I, I, I, I, P, L, P, F, P, P, P]),
@@ -46,7 +48,7 @@ _SIGNATURES = {
     "tmc_fft_c2c_rows": (I, [P, I, I, P, P, P]),
     "tmc_rfft2_band": (I, [P, I, I, I, P, P, I, I, P, I, I, I, I, I, I, P, P, P, P, P, P]),
     "tmc_xc_pair_products": (I, [P, P, P, I, L, P, P]),
-    "tmc_xc_leave_one_out_products": (I, [P, I, I, L, P, P, P, P]),
+    "tmc_xc_leave_one_out_products": (I, [P, I, I, L, P, P, I, I, P, P]),
     "tmc_xc_peak_partials": (I, [I, I]),
     "tmc_xc_peaks": (I, [P, I, I, I, I, I, I, I, P, P, P, P, P, P]),
     "tmc_irfft2_full": (I, [P, I, I, I, P, P, P, P, P]),

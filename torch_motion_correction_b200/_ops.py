@@ -24,6 +24,25 @@ def stack_stats(image: torch.Tensor, frac_low: float = 0.25, frac_high: float = 
     return out
 
 
+def stack_moments(image: torch.Tensor, frac_low: float = 0.25, frac_high: float = 0.75) -> torch.Tensor:
+    """Device double[3] = (sum, sum of squares, count) of the central box of the local frames."""
+    t, h, w = image.shape
+    y0, y1 = int(frac_low * h), int(frac_high * h)
+    x0, x1 = int(frac_low * w), int(frac_high * w)
+    out = torch.empty((3,), dtype=torch.float64, device=image.device)
+    ws = torch.empty(query("tmc_stack_stats_workspace_doubles"), dtype=torch.float64, device=image.device)
+    with torch.cuda.device(image.device):
+        call("tmc_stack_moments", ptr(image), t, h, w, y0, y1, x0, x1, ptr(out), ptr(ws), stream_ptr(image.device))
+    return out
+
+
+def moments_to_mean_std(moments: torch.Tensor) -> torch.Tensor:
+    out = torch.empty((2,), dtype=torch.float32, device=moments.device)
+    with torch.cuda.device(moments.device):
+        call("tmc_moments_to_mean_std", ptr(moments), ptr(out), stream_ptr(moments.device))
+    return out
+
+
 def spline_eval(coeffs: torch.Tensor, kind: int, tyx: torch.Tensor) -> torch.Tensor:
     c, n0, n1, n2 = coeffs.shape
     lead = tyx.shape[:-1]

@@ -273,7 +273,7 @@ __global__ void xc_pair_product_kernel(const float2* __restrict__ spec, const in
 // c is given as per-k delta lists relative to k-1 (delta = +-(j+1)); T <= 50 gives c_kj = [j < k].
 __global__ void xc_leave_one_out_kernel(const float2* __restrict__ spec, int T, int G, long plane_elems,
                                         const int* __restrict__ delta_offsets, const int* __restrict__ deltas,
-                                        float2* __restrict__ out) {
+                                        int k_begin, int k_count, float2* __restrict__ out) {
   const int g = blockIdx.y;
   const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= plane_elems) return;
@@ -289,11 +289,12 @@ __global__ void xc_leave_one_out_kernel(const float2* __restrict__ spec, int T, 
       const float2 diff = csub(part(j, 1), part(j, 0));
       extra = v > 0 ? cadd(extra, diff) : csub(extra, diff);
     }
+    if (k < k_begin || k >= k_begin + k_count) continue;  // frame-split movies: only the local frames
     const float2 cur = part(k, 0);
     float2 ref = cadd(csub(total, cur), extra);
     ref.x = __fdiv_rn(ref.x, cnt);
     ref.y = __fdiv_rn(ref.y, cnt);
-    out[((long)k * G + g) * plane_elems + e] = cmul_conj(ref, cur);
+    out[((long)(k - k_begin) * G + g) * plane_elems + e] = cmul_conj(ref, cur);
   }
 }
 
@@ -704,14 +705,17 @@ TMC_API int tmc_xc_pair_products(const void* spec, const int* ref_plane, const i
   return TMC_OK;
 }
 
-// spec planes [T][G][2]; out items [T][G]; delta lists: offsets (T+1) and signed (j+1) entries
+// spec planes [T][G][2]; out items [k_count][G] for frames k_begin .. k_begin + k_count - 1;
+// delta lists: offsets (T+1) and signed (j+1) entries
 TMC_API int tmc_xc_leave_one_out_products(const void* spec, int t, int g, long plane_elems, const int* delta_offsets,
-                                          const int* deltas, void* out, cudaStream_t stream) {
+                                          const int* deltas, int k_begin, int k_count, void* out, cudaStream_t stream) {
   TMC_CHECK_ARG(spec && delta_offsets && deltas && out && t >= 2 && g >= 1 && plane_elems >= 1,
                 "xc_leave_one_out_products: bad arguments (need t >= 2)");
+  TMC_CHECK_ARG(k_begin >= 0 && k_count >= 0 && k_begin + k_count <= t, "xc_leave_one_out_products: bad frame range");
+  if (k_count == 0) return TMC_OK;
   dim3 grid(tmc_div_up(plane_elems, 128), g);
   xc_leave_one_out_kernel<<<grid, 128, 0, stream>>>((const float2*)spec, t, g, plane_elems, delta_offsets, deltas,
-                                                    (float2*)out); tmc_count_launch();
+                                                    k_begin, k_count, (float2*)out); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_xc_leave_one_out_products");
   return TMC_OK;
 }

@@ -55,6 +55,29 @@ stats_partial_kernel(const float* __restrict__ image, int t, int h, int w, int y
   }
 }
 
+// moments[3] = {sum, sum of squares, count}: the exchange format for frame-split movies
+__global__ void stats_moments_kernel(const double* __restrict__ partial, int nblocks, double count, double* __restrict__ moments) {
+  double s = 0.0, ss = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 32) {
+    s += partial[2 * i];
+    ss += partial[2 * i + 1];
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if (threadIdx.x == 0) {
+    moments[0] = s;
+    moments[1] = ss;
+    moments[2] = count;
+  }
+}
+
+__global__ void moments_to_mean_std_kernel(const double* __restrict__ moments, float* __restrict__ mean_std) {
+  const double s = moments[0], ss = moments[1], n = moments[2];
+  const double mean = s / n;
+  mean_std[0] = (float)mean;
+  mean_std[1] = (float)sqrt((ss - s * mean) / (n - 1.0));
+}
+
 __global__ void stats_final_kernel(const double* __restrict__ partial, int nblocks, double count, float* __restrict__ mean_std) {
   // one warp, fixed order => deterministic
   double s = 0.0, ss = 0.0;
@@ -87,5 +110,27 @@ TMC_API int tmc_stack_stats(const float* image, int t, int h, int w, int y0, int
   stats_partial_kernel<<<nblocks, kStatsThreads, 0, stream>>>(image, t, h, w, y0, y1, x0, x1, workspace); tmc_count_launch();
   stats_final_kernel<<<1, 32, 0, stream>>>(workspace, nblocks, (double)rows * (x1 - x0), mean_std); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_stack_stats");
+  return TMC_OK;
+}
+
+// Raw moments {sum, sum of squares, count} (device double[3]) of the central box of the local frames: ranks
+// holding frame blocks of one movie all-reduce these (SUM) and call tmc_moments_to_mean_std.
+TMC_API int tmc_stack_moments(const float* image, int t, int h, int w, int y0, int y1, int x0, int x1, double* moments,
+                              double* workspace, cudaStream_t stream) {
+  TMC_CHECK_ARG(image && moments && workspace, "stack_moments: null pointer");
+  TMC_CHECK_ARG(t >= 1 && h >= 1 && w >= 1, "stack_moments: bad shape (%d,%d,%d)", t, h, w);
+  TMC_CHECK_ARG(0 <= y0 && y0 < y1 && y1 <= h && 0 <= x0 && x0 < x1 && x1 <= w, "stack_moments: empty or out-of-range box");
+  const long rows = (long)t * (y1 - y0);
+  int nblocks = (int)(rows < 148 * 8 ? rows : 148 * 8);
+  stats_partial_kernel<<<nblocks, kStatsThreads, 0, stream>>>(image, t, h, w, y0, y1, x0, x1, workspace); tmc_count_launch();
+  stats_moments_kernel<<<1, 32, 0, stream>>>(workspace, nblocks, (double)rows * (x1 - x0), moments); tmc_count_launch();
+  TMC_CHECK_LAUNCH("tmc_stack_moments");
+  return TMC_OK;
+}
+
+TMC_API int tmc_moments_to_mean_std(const double* moments, float* mean_std, cudaStream_t stream) {
+  TMC_CHECK_ARG(moments && mean_std, "moments_to_mean_std: null pointer");
+  moments_to_mean_std_kernel<<<1, 1, 0, stream>>>(moments, mean_std); tmc_count_launch();
+  TMC_CHECK_LAUNCH("tmc_moments_to_mean_std");
   return TMC_OK;
 }

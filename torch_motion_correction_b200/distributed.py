@@ -1,0 +1,186 @@
+"""Multi-GPU sharding of the hot path (one process per GPU, ``torch.distributed`` plumbing).
+
+Two levels:
+
+* independent movies -> one movie per rank, no data-path collective (``bench.py --gpus N``);
+* ONE large movie split into contiguous frame blocks (``motion_correct_frame_split``).  The only
+  bandwidth-relevant collective is the all-reduce of the (h, w) frame sum; the estimators exchange
+  three double-precision moments, the band-limited patch spectra (a few % of the movie) and a few
+  KB of shifts.  Every rank ends up with the same field and the full frame sum.
+
+Nothing here reshapes data for the network: spectra are gathered exactly as the kernels produce
+them.  With ``group=None`` and no initialised process group the functions degenerate to the
+single-GPU path (world size 1), which is how the ``-m gpu`` tests exercise the bookkeeping.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _fourier, _ops
+from ._common import as_f32, grid_kind, resolve_device
+from ._lib import call, ptr, stream_ptr
+from .correct_motion import correct_motion_fast
+from .deformation_field_utils import resample_deformation_field
+from .estimate_motion_xc import _aliasing_schedule
+from .patch_grid import patch_grid_centers
+
+
+def frame_range(total_frames: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block [f0, f1) of rank ``rank``: the first ``total % world`` ranks hold one more."""
+    base, extra = divmod(total_frames, world)
+    f0 = rank * base + min(rank, extra)
+    return f0, f0 + base + (1 if rank < extra else 0)
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def all_gather_frames(local: torch.Tensor, total_frames: int, group=None) -> torch.Tensor:
+    """Concatenate per-rank blocks ``local (t_local, ...)`` (rank order == frame order) into
+    ``(total_frames, ...)`` on every rank.  Blocks may differ by one frame: pad, gather, trim."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    t_max = -(-total_frames // world)
+    padded = local
+    if local.shape[0] < t_max:
+        pad = torch.zeros((t_max - local.shape[0], *local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded = torch.cat([local, pad], dim=0)
+    padded = padded.contiguous()
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    out = []
+    for r in range(world):
+        f0, f1 = frame_range(total_frames, r, world)
+        out.append(parts[r][: f1 - f0])
+    return torch.cat(out, dim=0)
+
+
+def stack_stats_frame_split(local_frames: torch.Tensor, group=None) -> torch.Tensor:
+    """normalize_image statistics of the WHOLE movie from per-rank moments (24 bytes all-reduced)."""
+    moments = _ops.stack_moments(local_frames)
+    _, world = _world(group)
+    if world > 1:
+        dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
+    return _ops.moments_to_mean_std(moments)
+
+
+def correct_motion_sum_frame_split(local_frames, deformation_grid, pixel_spacing, frame_offset, total_frames,
+                                   grid_type="catmull_rom", group=None, reduce=True) -> torch.Tensor:
+    """Warp the local frame block, sum it, and all-reduce the (h, w) partial sums (NCCL over NVLink)."""
+    from .correct_motion import correct_motion_sum
+
+    total = correct_motion_sum(
+        local_frames, deformation_grid, pixel_spacing, grid_type=grid_type, frame_offset=frame_offset, total_frames=total_frames
+    )
+    _, world = _world(group)
+    if world > 1 and reduce:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return total
+
+
+def estimate_global_motion_frame_split(local_frames, pixel_spacing, frame_offset, total_frames, mean_std,
+                                       reference_frame=None, b_factor=500, frequency_range=(300, 10), group=None):
+    """``estimate_global_motion`` for a frame-split movie: the owner of the reference frame
+    broadcasts its band-limited spectrum (a few MB); shifts are all-gathered."""
+    rank, world = _world(group)
+    dev = local_frames.device
+    t_local, h, w = local_frames.shape
+    if reference_frame is None:
+        reference_frame = total_frames // 2
+    plan = _fourier.BandPlan(h, w, dev, pixel_spacing, b_factor, frequency_range)
+    mask, ylo, yhi = _fourier.soft_disc_mask((h, w), min(h, w) / 4, min(h, w) / 8, dev)
+    spec = plan.forward(local_frames, mean_std, mask, ylo, yhi, _fourier.frame_pair_jobs(t_local, dev))
+    ref_spec = torch.empty((1, plan.ky, plan.kx, 2), dtype=torch.float32, device=dev)
+    owner = next(r for r in range(world) if frame_range(total_frames, r, world)[0] <= reference_frame < frame_range(total_frames, r, world)[1])
+    if rank == owner:
+        ref_spec.copy_(spec[reference_frame - frame_offset : reference_frame - frame_offset + 1])
+    if world > 1:
+        dist.broadcast(ref_spec, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+    both = torch.cat([spec[:t_local], ref_spec], dim=0)
+    cur = torch.arange(t_local, dtype=torch.int32, device=dev)
+    ref = torch.full((t_local,), t_local, dtype=torch.int32, device=dev)
+    prod = _fourier.pair_products(both, ref, cur, plan.plane_elems)
+    shifts = plan.peaks(prod.view(t_local, plan.ky, plan.kx, 2), sub_pixel=False)
+    shifts = all_gather_frames(shifts, total_frames, group)
+    field = torch.empty((2, total_frames, 1, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("tmc_global_shifts_to_field", ptr(shifts), total_frames, float(pixel_spacing), int(reference_frame), ptr(field),
+             stream_ptr(dev))
+    return field
+
+
+def estimate_patch_motion_frame_split(local_frames, pixel_spacing, frame_offset, total_frames, mean_std,
+                                      deformation_field=None, b_factor=500, frequency_range=(300, 10), patch_sidelength=1024,
+                                      sub_pixel_refinement=True, temporal_smoothing=True, smoothing_window_size=5,
+                                      outlier_rejection=True, outlier_threshold=3.0, group=None):
+    """``estimate_motion_cross_correlation_patches`` (``mean_except_current``) for a frame-split movie.
+
+    Each rank transforms the patches of its own frames; the band-limited spectra (both mask powers,
+    quirk Q1) are all-gathered so every rank can form the leave-one-out references of its frames."""
+    rank, world = _world(group)
+    dev = local_frames.device
+    t_local, h, w = local_frames.shape
+    t = total_frames
+    if t < 2:
+        raise ValueError("mean_except_current needs at least two frames")
+    source, source_stats = local_frames, mean_std
+    if deformation_field is not None:
+        deformation_field = deformation_field.to(dev)
+        if tuple(deformation_field.shape[-2:]) != (1, 1):
+            raise NotImplementedError("frame-split pre-correction supports the rigid (2, t, 1, 1) field")
+        local_field = deformation_field[:, frame_offset : frame_offset + t_local].clone()
+        source = correct_motion_fast(local_frames, local_field, device=dev, _mean_std=mean_std)
+        deformation_field = deformation_field * -1  # the reference negates the caller's field in place (Q2)
+        source_stats = None
+    p = int(patch_sidelength)
+    centers = patch_grid_centers((t, h, w), (1, p, p), (1, p // 2, p // 2), distribute_patches=True)
+    gh, gw = centers.shape[1:3]
+    g = gh * gw
+    origins = (centers[0, :, :, 1:] - p // 2).reshape(-1, 2).tolist()
+    plan = _fourier.BandPlan(p, p, dev, pixel_spacing, b_factor, frequency_range)
+    mask, ylo, yhi = _fourier.soft_disc_mask((p, p), p / 4, p / 8, dev)
+    if deformation_field is None:
+        field = torch.zeros((2, t, gh, gw), dtype=torch.float32, device=dev)
+    else:
+        field = resample_deformation_field(deformation_field, (t, gh, gw))
+    jobs = torch.tensor([[k, 1, k, 2, y0, x0] for k in range(t_local) for (y0, x0) in origins], dtype=torch.int32).to(dev)
+    spec_local = plan.forward(source, source_stats, mask, ylo, yhi, jobs).view(t_local, g * 2 * plan.plane_elems * 2)
+    spec_all = all_gather_frames(spec_local, t, group)
+    offsets, deltas = _aliasing_schedule(t, "mean_except_current", t // 2)
+    d_off = torch.tensor(offsets, dtype=torch.int32).to(dev)
+    d_val = torch.tensor(deltas if deltas else [0], dtype=torch.int32).to(dev)
+    prod = _fourier.leave_one_out_products(spec_all, t, g, plan.plane_elems, d_off, d_val, frame_offset, t_local)
+    shifts = plan.peaks(prod.view(t_local * g, plan.ky, plan.kx, 2), sub_pixel=bool(sub_pixel_refinement))
+    shifts = all_gather_frames(shifts.view(t_local, g * 2), t, group).contiguous()
+    scratch = torch.empty_like(field)
+    with torch.cuda.device(dev):
+        call("tmc_xc_postprocess", ptr(shifts), t, g, float(pixel_spacing), -1, int(bool(outlier_rejection)),
+             float(outlier_threshold), int(bool(temporal_smoothing)), int(smoothing_window_size), 1, ptr(field), ptr(scratch),
+             stream_ptr(dev))
+    return field, centers.to(dev)
+
+
+def motion_correct_frame_split(local_frames: torch.Tensor, pixel_spacing: float, frame_offset: int, total_frames: int,
+                               patch_sidelength: int = 1024, b_factor: float = 500, frequency_range=(300, 10),
+                               grid_type: str = "bspline", group=None, device=None):
+    """Estimate (global + patch XC) and correct ONE movie whose frames are split across the ranks
+    of ``group``.  Returns ``(frame sum (h, w) on every rank, field (2, t, gh, gw))``."""
+    dev = resolve_device(local_frames, device)
+    frames = as_f32(local_frames, dev)
+    grid_kind(grid_type)
+    stats = stack_stats_frame_split(frames, group)
+    global_field = estimate_global_motion_frame_split(
+        frames, pixel_spacing, frame_offset, total_frames, stats, b_factor=b_factor, frequency_range=frequency_range, group=group
+    )
+    field, _ = estimate_patch_motion_frame_split(
+        frames, pixel_spacing, frame_offset, total_frames, stats, deformation_field=global_field, b_factor=b_factor,
+        frequency_range=frequency_range, patch_sidelength=patch_sidelength, group=group,
+    )
+    total = correct_motion_sum_frame_split(frames, field, pixel_spacing, frame_offset, total_frames, grid_type, group)
+    return total, field
