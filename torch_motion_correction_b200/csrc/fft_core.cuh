@@ -57,6 +57,23 @@ __device__ __forceinline__ void fft_reg(float2 (&v)[R]) {
   }
 }
 
+// same, on a pointer into a register array (all indices are compile-time after unrolling)
+template <int R>
+__device__ __forceinline__ void fft_reg_ptr(float2* v) {
+#pragma unroll
+  for (int half = R / 2; half >= 1; half >>= 1) {
+#pragma unroll
+    for (int base = 0; base < R; base += 2 * half) {
+#pragma unroll
+      for (int k = 0; k < half; ++k) {
+        float2 a = v[base + k], b = v[base + k + half];
+        v[base + k] = cadd(a, b);
+        v[base + k + half] = mul_w16(csub(a, b), k * (8 / half));
+      }
+    }
+  }
+}
+
 // One Stockham pass over B sequences of length N (padded stride), radix R, sub-transform NS.
 template <int N, int R, int NS, int B, int THREADS>
 __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out,

@@ -13,6 +13,7 @@
 //    instead of storing the correlation surface.
 #include "common.cuh"
 #include "fft_core.cuh"
+#include "fft_core2.cuh"
 
 namespace {
 
@@ -460,6 +461,13 @@ rows_inverse_store_kernel(const float2* __restrict__ tmp, int NY, int KX, AxisPl
   }
 }
 
+#include "fourier_p2.cuh"
+
+template <int M, bool BLU>
+constexpr bool use_fast_path() {
+  return !BLU && M >= 256;
+}
+
 // ---- peak finalisation: argmax over CTAs, 3-point parabola, wrap ---------------------------
 
 // value of the real surface at (y, x) from the column-transformed rows (direct KX-term sum)
@@ -670,6 +678,19 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
   int rc = dispatch_fft(nx, "rfft2_band", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
+    if constexpr (use_fast_path<MM, BB>()) {
+      if (yhi > ylo) {
+        constexpr int B = fft2::Cfg<MM>::B;
+        // enough CTAs to fill the chip a few times over, each amortising its twiddle-table load
+        int rows_per_cta = B * 4;
+        while (rows_per_cta > B && (long)tmc_div_up(yhi - ylo, rows_per_cta) * njobs < 148 * 8) rows_per_cta -= B;
+        if (int e = enable_smem(rows_forward_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
+        dim3 grid(tmc_div_up(yhi - ylo, rows_per_cta), njobs);
+        rows_forward_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
+            image, h, w, mean_std, mask, jobs, ylo, yhi, ny, kx_count, px.tw, (float2*)tmp, rows_per_cta); tmc_count_launch();
+      }
+      return TMC_OK;
+    }
     if (int e = enable_smem(rows_forward_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(tmc_div_up(yhi - ylo, batch_for(MM)), njobs);
     if (yhi > ylo) {
@@ -683,6 +704,13 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
   rc = dispatch_fft(ny, "rfft2_band", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
+    if constexpr (use_fast_path<MM, BB>()) {
+      if (int e = enable_smem(cols_forward_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
+      dim3 grid(tmc_div_up(kx_count, fft2::Cfg<MM>::B), 2 * njobs);
+      cols_forward_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
+          (const float2*)tmp, ylo, yhi, kx_count, ky_count, ky_start, weight, py.tw, (float2*)out); tmc_count_launch();
+      return TMC_OK;
+    }
     if (int e = enable_smem(cols_forward_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(tmc_div_up(kx_count, batch_for(MM)), 2 * njobs);
     cols_forward_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ylo, yhi, kx_count, ky_count,
@@ -722,7 +750,12 @@ TMC_API int tmc_xc_leave_one_out_products(const void* spec, int t, int g, long p
 
 TMC_API int tmc_xc_peak_partials(int ny, int nx) {
   const int m = fft_size_for(nx);
-  return m ? tmc_div_up(ny, 2 * batch_for(m)) : -1;
+  if (m == 0) return -1;
+  if (m == nx && m >= 256) {  // power-of-two fast path: several row-pair batches per CTA
+    const int b = 256 / (m / 16) > 0 ? 256 / (m / 16) : 1;
+    return tmc_div_up(ny, 2 * b * kRowIters);
+  }
+  return tmc_div_up(ny, 2 * batch_for(m));
 }
 
 // Inverse 2-D transform of band-limited products + argmax (+ parabola) + wrap.
@@ -738,6 +771,13 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
   int rc = dispatch_fft(ny, "xc_peaks", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
+    if constexpr (use_fast_path<MM, BB>()) {
+      if (int e = enable_smem(cols_inverse_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
+      dim3 grid(tmc_div_up(kx_count, fft2::Cfg<MM>::B), nitems);
+      cols_inverse_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
+          (const float2*)prod, kx_count, ky_count, ky_start, py.tw, (float2*)tmp); tmc_count_launch();
+      return TMC_OK;
+    }
     if (int e = enable_smem(cols_inverse_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(tmc_div_up(kx_count, batch_for(MM)), nitems);
     cols_inverse_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)prod, kx_count, ky_count, ky_start,
@@ -750,6 +790,13 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
   rc = dispatch_fft(nx, "xc_peaks", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
+    if constexpr (use_fast_path<MM, BB>()) {
+      if (int e = enable_smem(rows_inverse_argmax_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
+      dim3 grid(nparts, nitems);
+      rows_inverse_argmax_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
+          (const float2*)tmp, ny, kx_count, px.tw, (PeakCandidate*)partial); tmc_count_launch();
+      return TMC_OK;
+    }
     if (int e = enable_smem(rows_inverse_argmax_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(nparts, nitems);
     rows_inverse_argmax_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ny, kx_count, px,
@@ -774,6 +821,13 @@ TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const 
   int rc = dispatch_fft(ny, "irfft2_full", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
+    if constexpr (use_fast_path<MM, BB>()) {
+      if (int e = enable_smem(cols_inverse_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
+      dim3 grid(tmc_div_up(kx, fft2::Cfg<MM>::B), nitems);
+      cols_inverse_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>((const float2*)spec, kx, ny, 0, py.tw,
+                                                                                      (float2*)tmp); tmc_count_launch();
+      return TMC_OK;
+    }
     if (int e = enable_smem(cols_inverse_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(tmc_div_up(kx, batch_for(MM)), nitems);
     cols_inverse_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)spec, kx, ny, 0, py, (float2*)tmp); tmc_count_launch();
@@ -783,6 +837,13 @@ TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const 
   rc = dispatch_fft(nx, "irfft2_full", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
+    if constexpr (use_fast_path<MM, BB>()) {
+      if (int e = enable_smem(rows_inverse_store_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
+      dim3 grid(tmc_div_up(ny, rows_per_cta_inverse<MM>()), nitems);
+      rows_inverse_store_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
+          (const float2*)tmp, ny, kx, px.tw, 1.0f / ((float)nx * (float)ny), out); tmc_count_launch();
+      return TMC_OK;
+    }
     if (int e = enable_smem(rows_inverse_store_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(tmc_div_up(ny, 2 * batch_for(MM)), nitems);
     rows_inverse_store_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ny, kx, px,

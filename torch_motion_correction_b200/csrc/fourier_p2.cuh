@@ -1,0 +1,309 @@
+// Power-of-two fast-path kernels on fft_core2.cuh (included by fourier.cu inside its anonymous
+// namespace).  Same contracts as the generic kernels of the same name without the _p2 suffix.
+#pragma once
+
+// ---- forward rows: image window * mask^e (two real signals packed) -> tmp[plane][y][kx < KX] --------
+template <int N>
+__global__ void __launch_bounds__(fft2::kThreads)
+rows_forward_p2(const float* __restrict__ image, int H, int W, const float* __restrict__ mean_std,
+                const float* __restrict__ mask, const int* __restrict__ jobs, int ylo, int yhi, int NY, int KX,
+                const float2* __restrict__ tw, float2* __restrict__ tmp, int rows_per_cta) {
+  using C = fft2::Cfg<N>;
+  using P = fft2::Plan<N>;
+  extern __shared__ float2 smem[];
+  const fft2::Smem<N> sm(smem);
+  fft2::load_twiddles<N>(sm, tw);
+  const int seq = threadIdx.x / C::TPS, j = threadIdx.x % C::TPS;
+  float2* myseq = sm.data + seq * C::STRIDE;
+  const int job = blockIdx.y;
+  const int fa = jobs[job * 6 + 0], ea = jobs[job * 6 + 1], fb = jobs[job * 6 + 2], eb = jobs[job * 6 + 3];
+  const int y0 = jobs[job * 6 + 4], x0 = jobs[job * 6 + 5];
+  float mean = 0.f, inv_std = 1.f;
+  if (mean_std != nullptr) {
+    mean = __ldg(mean_std);
+    inv_std = 1.0f / __ldg(mean_std + 1);
+  }
+  const long fs = (long)H * W;
+  const float* img_a = image + fa * fs + (long)y0 * W + x0;
+  const float* img_b = fb >= 0 ? image + fb * fs + (long)y0 * W + x0 : nullptr;
+  const bool same = fb == fa;
+  const int row_begin = ylo + blockIdx.x * rows_per_cta;
+  const int row_end = min(yhi, row_begin + rows_per_cta);
+  float2* plane_a = tmp + (long)(2 * job) * NY * KX;
+  float2* plane_b = plane_a + (long)NY * KX;
+  __syncthreads();
+  for (int row0 = row_begin; row0 < row_end; row0 += C::B) {
+    const int y = row0 + seq;
+    const bool active = y < row_end;
+    float2 v[C::VPT];
+#pragma unroll
+    for (int g = 0; g < P::First::G; ++g)
+#pragma unroll
+      for (int r = 0; r < P::First::R; ++r) {
+        float2 z = make_float2(0.f, 0.f);
+        if (active) {
+          const int x = P::First::in_index(j, g, r);
+          const float m = mask ? __ldg(mask + (long)y * N + x) : 1.0f;
+          const float pa = (__ldg(img_a + (long)y * W + x) - mean) * inv_std;
+          float va = pa;
+          for (int e = 0; e < ea; ++e) va *= m;
+          z.x = va;
+          if (img_b) {
+            float vb = same ? pa : (__ldg(img_b + (long)y * W + x) - mean) * inv_std;
+            for (int e = 0; e < eb; ++e) vb *= m;
+            z.y = vb;
+          }
+        }
+        v[g * P::First::R + r] = z;
+      }
+    fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+    __syncthreads();
+    P::Last::store(myseq, j, v);
+    __syncthreads();
+    if (active) {
+      for (int k = j; k < KX; k += C::TPS) {
+        const float2 zk = myseq[fft2::pad_idx(k)];
+        const float2 zn = myseq[fft2::pad_idx(k == 0 ? 0 : N - k)];
+        plane_a[(long)y * KX + k] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        if (img_b) plane_b[(long)y * KX + k] = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- forward columns: tmp[plane][y][kx] -> out[plane][kyb][kx] * weight --------------------------------
+template <int N>
+__global__ void __launch_bounds__(fft2::kThreads)
+cols_forward_p2(const float2* __restrict__ tmp, int ylo, int yhi, int KX, int KY, int ky_start,
+                const float* __restrict__ weight, const float2* __restrict__ tw, float2* __restrict__ out) {
+  using C = fft2::Cfg<N>;
+  using P = fft2::Plan<N>;
+  extern __shared__ float2 smem[];
+  const fft2::Smem<N> sm(smem);
+  fft2::load_twiddles<N>(sm, tw);
+  const int seq = threadIdx.x % C::B, j = threadIdx.x / C::B;  // neighbouring threads -> neighbouring kx
+  float2* myseq = sm.data + seq * C::STRIDE;
+  const long plane = blockIdx.y;
+  const int kx = blockIdx.x * C::B + seq;
+  const bool active = kx < KX;
+  const float2* src = tmp + plane * N * KX + kx;
+  float2 v[C::VPT];
+#pragma unroll
+  for (int g = 0; g < P::First::G; ++g)
+#pragma unroll
+    for (int r = 0; r < P::First::R; ++r) {
+      const int y = P::First::in_index(j, g, r);
+      v[g * P::First::R + r] = (active && y >= ylo && y < yhi) ? src[(long)y * KX] : make_float2(0.f, 0.f);
+    }
+  __syncthreads();
+  fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+  if (!active) return;
+  float2* dst = out + plane * KY * KX + kx;
+#pragma unroll
+  for (int g = 0; g < P::Last::G; ++g)
+#pragma unroll
+    for (int r = 0; r < P::Last::R; ++r) {
+      const int ky = P::Last::out_index(j, g, r);
+      const int kyb = (ky - ky_start) & (N - 1);
+      if (kyb < KY) {
+        float2 val = P::Last::result(v, g, r);
+        if (weight) {
+          const float wgt = __ldg(weight + (long)kyb * KX + kx);
+          val.x *= wgt;
+          val.y *= wgt;
+        }
+        dst[(long)kyb * KX] = val;
+      }
+    }
+}
+
+// ---- inverse columns: in[item][kyb][kx] -> tmp[item][y][kx] (unnormalised inverse along y) ------------
+template <int N>
+__global__ void __launch_bounds__(fft2::kThreads)
+cols_inverse_p2(const float2* __restrict__ in, int KX, int KY, int ky_start, const float2* __restrict__ tw,
+                float2* __restrict__ tmp) {
+  using C = fft2::Cfg<N>;
+  using P = fft2::Plan<N>;
+  extern __shared__ float2 smem[];
+  const fft2::Smem<N> sm(smem);
+  fft2::load_twiddles<N>(sm, tw);
+  const int seq = threadIdx.x % C::B, j = threadIdx.x / C::B;
+  float2* myseq = sm.data + seq * C::STRIDE;
+  const long item = blockIdx.y;
+  const int kx = blockIdx.x * C::B + seq;
+  const bool active = kx < KX;
+  const float2* src = in + item * KY * KX + kx;
+  float2 v[C::VPT];
+#pragma unroll
+  for (int g = 0; g < P::First::G; ++g)
+#pragma unroll
+    for (int r = 0; r < P::First::R; ++r) {
+      const int y = P::First::in_index(j, g, r);
+      const int kyb = (y - ky_start) & (N - 1);
+      float2 z = make_float2(0.f, 0.f);
+      if (active && kyb < KY) {
+        const float2 c = src[(long)kyb * KX];
+        z = make_float2(c.y, c.x);  // re/im swap: inverse via forward
+      }
+      v[g * P::First::R + r] = z;
+    }
+  __syncthreads();
+  fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+  if (!active) return;
+  float2* dst = tmp + item * N * KX + kx;
+#pragma unroll
+  for (int g = 0; g < P::Last::G; ++g)
+#pragma unroll
+    for (int r = 0; r < P::Last::R; ++r) {
+      const float2 val = P::Last::result(v, g, r);
+      dst[(long)P::Last::out_index(j, g, r) * KX] = make_float2(val.y, val.x);
+    }
+}
+
+// packed, re/im-swapped spectrum entry i of the row pair (rowa -> real part, rowb -> imaginary part)
+template <int N>
+__device__ __forceinline__ float2 c2r_pair_entry(const float2* __restrict__ rowa, const float2* __restrict__ rowb, int KX, int i) {
+  if (i < KX) {
+    const float2 ca = rowa[i];
+    const float2 cb = rowb ? rowb[i] : make_float2(0.f, 0.f);
+    if (i == 0 || 2 * i == N) return make_float2(cb.x, ca.x);
+    return make_float2(ca.y + cb.x, ca.x - cb.y);
+  }
+  const int k = N - i;
+  if (k < KX && 2 * k != N) {
+    const float2 ca = rowa[k];
+    const float2 cb = rowb ? rowb[k] : make_float2(0.f, 0.f);
+    return make_float2(cb.x - ca.y, ca.x + cb.y);
+  }
+  return make_float2(0.f, 0.f);
+}
+
+constexpr int kRowIters = 4;  // row-pair batches per CTA in the inverse row kernels
+
+template <int N>
+__host__ __device__ constexpr int rows_per_cta_inverse() {
+  return 2 * fft2::Cfg<N>::B * kRowIters;
+}
+
+// ---- inverse rows + argmax: tmp[item][y][kx] -> partial[item][cta] ------------------------------------
+template <int N>
+__global__ void __launch_bounds__(fft2::kThreads)
+rows_inverse_argmax_p2(const float2* __restrict__ tmp, int NY, int KX, const float2* __restrict__ tw,
+                       PeakCandidate* __restrict__ partial) {
+  using C = fft2::Cfg<N>;
+  using P = fft2::Plan<N>;
+  extern __shared__ float2 smem[];
+  const fft2::Smem<N> sm(smem);
+  fft2::load_twiddles<N>(sm, tw);
+  const int seq = threadIdx.x / C::TPS, j = threadIdx.x % C::TPS;
+  float2* myseq = sm.data + seq * C::STRIDE;
+  const long item = blockIdx.y;
+  const float2* src = tmp + item * NY * KX;
+  float best = -INFINITY;
+  int best_idx = 0x7fffffff;
+  __syncthreads();
+  for (int it = 0; it < kRowIters; ++it) {
+    const int ya = blockIdx.x * rows_per_cta_inverse<N>() + (it * C::B + seq) * 2;
+    const bool active = ya < NY;
+    const float2* rowa = src + (long)ya * KX;
+    const float2* rowb = (ya + 1 < NY) ? rowa + KX : nullptr;
+    float2 v[C::VPT];
+#pragma unroll
+    for (int g = 0; g < P::First::G; ++g)
+#pragma unroll
+      for (int r = 0; r < P::First::R; ++r)
+        v[g * P::First::R + r] =
+            active ? c2r_pair_entry<N>(rowa, rowb, KX, P::First::in_index(j, g, r)) : make_float2(0.f, 0.f);
+    fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+    if (active) {
+#pragma unroll
+      for (int g = 0; g < P::Last::G; ++g)
+#pragma unroll
+        for (int r = 0; r < P::Last::R; ++r) {
+          const float2 val = P::Last::result(v, g, r);  // swapped: .y = row ya, .x = row ya + 1
+          const int ia = ya * N + P::Last::out_index(j, g, r);
+          if (better(val.y, ia, best, best_idx)) {
+            best = val.y;
+            best_idx = ia;
+          }
+          if (rowb && better(val.x, ia + N, best, best_idx)) {
+            best = val.x;
+            best_idx = ia + N;
+          }
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    if (better(ov, oi, best, best_idx)) {
+      best = ov;
+      best_idx = oi;
+    }
+  }
+  __shared__ float sval[fft2::kThreads / 32];
+  __shared__ int sidx[fft2::kThreads / 32];
+  if ((threadIdx.x & 31) == 0) {
+    sval[threadIdx.x >> 5] = best;
+    sidx[threadIdx.x >> 5] = best_idx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < fft2::kThreads / 32; ++i)
+      if (better(sval[i], sidx[i], best, best_idx)) {
+        best = sval[i];
+        best_idx = sidx[i];
+      }
+    PeakCandidate c;
+    c.val = best;
+    c.idx = best_idx;
+    partial[item * gridDim.x + blockIdx.x] = c;
+  }
+}
+
+// ---- inverse rows + store: tmp[item][y][kx] -> out[item][y][x] real ------------------------------------
+template <int N>
+__global__ void __launch_bounds__(fft2::kThreads)
+rows_inverse_store_p2(const float2* __restrict__ tmp, int NY, int KX, const float2* __restrict__ tw, float scale,
+                      float* __restrict__ out) {
+  using C = fft2::Cfg<N>;
+  using P = fft2::Plan<N>;
+  extern __shared__ float2 smem[];
+  const fft2::Smem<N> sm(smem);
+  fft2::load_twiddles<N>(sm, tw);
+  const int seq = threadIdx.x / C::TPS, j = threadIdx.x % C::TPS;
+  float2* myseq = sm.data + seq * C::STRIDE;
+  const long item = blockIdx.y;
+  const float2* src = tmp + item * NY * KX;
+  float* dst = out + item * NY * N;
+  __syncthreads();
+  for (int it = 0; it < kRowIters; ++it) {
+    const int ya = blockIdx.x * rows_per_cta_inverse<N>() + (it * C::B + seq) * 2;
+    const bool active = ya < NY;
+    const float2* rowa = src + (long)ya * KX;
+    const float2* rowb = (ya + 1 < NY) ? rowa + KX : nullptr;
+    float2 v[C::VPT];
+#pragma unroll
+    for (int g = 0; g < P::First::G; ++g)
+#pragma unroll
+      for (int r = 0; r < P::First::R; ++r)
+        v[g * P::First::R + r] =
+            active ? c2r_pair_entry<N>(rowa, rowb, KX, P::First::in_index(j, g, r)) : make_float2(0.f, 0.f);
+    fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+    if (active) {
+#pragma unroll
+      for (int g = 0; g < P::Last::G; ++g)
+#pragma unroll
+        for (int r = 0; r < P::Last::R; ++r) {
+          const float2 val = P::Last::result(v, g, r);
+          const int x = P::Last::out_index(j, g, r);
+          dst[(long)ya * N + x] = val.y * scale;
+          if (rowb) dst[(long)(ya + 1) * N + x] = val.x * scale;
+        }
+    }
+    __syncthreads();
+  }
+}
