@@ -107,9 +107,10 @@ int tmc_fft_c2c_rows(const void* in, int rows, int n, const void* plan, void* ou
  * window at (y0, x0) of frame_a / frame_b, normalised with mean_std (nullable), times mask^power, packed as
  * real / imaginary part of ONE complex transform.  Only rows [ylo, yhi) of the mask are non-zero.
  * out (2 * njobs, ky_count, kx_count) complex64: plane 2*job = a, 2*job + 1 = b; ky = ky_start + kyb.
+ * job_mode: 0 generic; 1 all jobs are {f, 1, f, 2, ..} (one frame, mask powers 1 and 2); 2 all jobs use power 1.
  * tmp: 2 * njobs * ny * kx_count complex64. */
 int tmc_rfft2_band(const float* image, int t, int h, int w, const float* mean_std, const float* mask, int ny, int nx,
-                   const int* jobs, int njobs, int ylo, int yhi, int kx_count, int ky_count, int ky_start,
+                   const int* jobs, int njobs, int job_mode, int ylo, int yhi, int kx_count, int ky_count, int ky_start,
                    const float* weight, const void* plan_x, const void* plan_y, void* tmp, void* out, tmc_stream_t stream);
 
 /* ---- cross-correlation products: estimate_motion_xc.py:112,310-349 ---------------------------------- */

@@ -46,7 +46,7 @@ def test_library_loads_through_the_binding_and_answers_queries():
     assert _lib.query("tmc_spline_workspace_floats", 2, 3, 5, 5) == 2 * 5 * 7 * 7
     assert _lib.query("tmc_spline_workspace_floats", 2, 40, 1, 1) == 2 * 42 * 4 * 4
     assert _lib.query("tmc_warp_workspace_floats", 40, 4096, 50) == 40 * 2 * 50 * 4096
-    assert _lib.query("tmc_xc_peak_partials", 1024, 1024) == 128
+    assert _lib.query("tmc_xc_peak_partials", 1024, 1024) == 32
 
 
 def test_bad_arguments_are_reported_not_crashed():

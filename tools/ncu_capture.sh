@@ -1,0 +1,23 @@
+#!/bin/bash
+# One `ncu --set full` capture per hot kernel (first launch of each) of one C2 motion_correct step.
+# Usage (on the GPU box): bash tools/ncu_capture.sh <tag>
+set -u
+tag=${1:-r01}
+mkdir -p gpurun_out
+python tools/profile_step.py > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
+i=0
+for k in 'rows_forward_p2<.int.1024>' 'cols_forward_p2<.int.1024>' 'rows_inverse_argmax_p2<.int.1024>' 'cols_inverse_p2<.int.1024>' \
+         'rows_forward_p2<.int.4096>' 'cols_forward_p2<.int.4096>' 'cols_inverse_p2<.int.4096>' 'rows_inverse_argmax_p2<.int.4096>' \
+         'rows_inverse_store_p2<.int.4096>'; do
+  i=$((i+1))
+  ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base demangled \
+      -k regex:"$k" -c 1 -o gpurun_out/prof_${tag}_$i python tools/profile_step.py > gpurun_out/ncu_$i.log 2>&1
+  echo "$k -> $(tail -1 gpurun_out/ncu_$i.log)"
+  # keep what travels back small: raw metrics + per-line source counters as csv, drop the .ncu-rep
+  if [ -f gpurun_out/prof_${tag}_$i.ncu-rep ]; then
+    ncu -i gpurun_out/prof_${tag}_$i.ncu-rep --page raw --csv > gpurun_out/prof_${tag}_${i}_raw.csv 2>/dev/null
+    ncu -i gpurun_out/prof_${tag}_$i.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/prof_${tag}_${i}_source.csv.gz
+    rm -f gpurun_out/prof_${tag}_$i.ncu-rep
+  fi
+done
+du -sh gpurun_out

@@ -109,8 +109,11 @@ class BandPlan:
         return self.ky * self.kx
 
     # -- forward ------------------------------------------------------------------------------
-    def forward(self, image: torch.Tensor, mean_std, mask, ylo: int, yhi: int, jobs: torch.Tensor, out=None):
-        """jobs (njobs, 6) int32 device -> spectra (2*njobs, KY, KX) complex64 (as float pairs)."""
+    def forward(self, image: torch.Tensor, mean_std, mask, ylo: int, yhi: int, jobs: torch.Tensor, out=None, job_mode: int = 0):
+        """jobs (njobs, 6) int32 device -> spectra (2*njobs, KY, KX) complex64 (as float pairs).
+
+        ``job_mode`` promises a structure shared by all jobs (lets the row kernel drop its generic
+        loops): 1 = one frame under mask powers (1, 2); 2 = two frames (or one), power 1; 0 = generic."""
         t, h, w = image.shape
         njobs = jobs.shape[0]
         dev = image.device
@@ -125,7 +128,7 @@ class BandPlan:
             for j0 in range(0, njobs, chunk):
                 n = min(chunk, njobs - j0)
                 call("tmc_rfft2_band", ptr(image), t, h, w, ptr(mean_std), ptr(mask), self.ny, self.nx,
-                     jobs_base + j0 * 6 * 4, n, ylo, yhi, self.kx, self.ky, self.ky_start, ptr(self.weight),
+                     jobs_base + j0 * 6 * 4, n, int(job_mode), ylo, yhi, self.kx, self.ky, self.ky_start, ptr(self.weight),
                      ptr(self.tw_x), ptr(self.tw_y), ptr(tmp), out_base + 2 * j0 * self.plane_elems * _C64, stream)
         return out
 

@@ -661,15 +661,17 @@ TMC_API int tmc_fft_c2c_rows(const void* in, int rows, int n, const void* plan, 
 
 // Band-limited forward 2-D real DFT of masked image windows.
 //  image (T,H,W) f32; mean_std nullable device float[2]; mask (ny,nx) f32 nullable;
-//  jobs (njobs,6) int32 device = {frame_a, exp_a, frame_b (-1: none), exp_b, y0, x0};
+//  jobs (njobs,6) int32 device = {frame_a, exp_a, frame_b (-1: none), exp_b, y0, x0}; job_mode promises a
+//  structure shared by ALL jobs (1: frame_b == frame_a, powers (1,2); 2: powers (1,1)) or 0 for generic;
 //  rows [ylo,yhi) are the only non-zero rows of the mask; kx in [0,KX), ky in [ky_start, ky_start+KY);
 //  weight (KY,KX) f32 nullable; plan_x/plan_y: tmc_fft_plan_init buffers for nx/ny;
 //  tmp: 2*njobs*ny*KX complex64; out: (2*njobs, KY, KX) complex64, plane 2*job+0 = a, 2*job+1 = b.
 TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float* mean_std, const float* mask, int ny, int nx,
-                           const int* jobs, int njobs, int ylo, int yhi, int kx_count, int ky_count, int ky_start,
-                           const float* weight, const void* plan_x, const void* plan_y, void* tmp, void* out,
+                           const int* jobs, int njobs, int job_mode, int ylo, int yhi, int kx_count, int ky_count,
+                           int ky_start, const float* weight, const void* plan_x, const void* plan_y, void* tmp, void* out,
                            cudaStream_t stream) {
   TMC_CHECK_ARG(image && jobs && plan_x && plan_y && tmp && out, "rfft2_band: null pointer");
+  TMC_CHECK_ARG(job_mode >= 0 && job_mode <= 2, "rfft2_band: job_mode must be 0 (generic), 1 (mask powers 1,2 of one frame) or 2 (two frames)");
   TMC_CHECK_ARG(njobs >= 0 && t >= 1 && h >= ny && w >= nx, "rfft2_band: window (%d,%d) larger than image (%d,%d)", ny, nx, h, w);
   TMC_CHECK_ARG(0 <= ylo && ylo <= yhi && yhi <= ny, "rfft2_band: bad row support [%d,%d)", ylo, yhi);
   TMC_CHECK_ARG(kx_count >= 1 && kx_count <= nx / 2 + 1 && ky_count >= 1 && ky_count <= ny, "rfft2_band: bad band box");
@@ -684,10 +686,17 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
         // enough CTAs to fill the chip a few times over, each amortising its twiddle-table load
         int rows_per_cta = B * 4;
         while (rows_per_cta > B && (long)tmc_div_up(yhi - ylo, rows_per_cta) * njobs < 148 * 8) rows_per_cta -= B;
-        if (int e = enable_smem(rows_forward_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
         dim3 grid(tmc_div_up(yhi - ylo, rows_per_cta), njobs);
-        rows_forward_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
-            image, h, w, mean_std, mask, jobs, ylo, yhi, ny, kx_count, px.tw, (float2*)tmp, rows_per_cta); tmc_count_launch();
+        constexpr size_t smem = rows_forward_smem_bytes<MM>();
+#define TMC_ROWS_FWD(MODE)                                                                                      \
+  {                                                                                                             \
+    if (int e = enable_smem(rows_forward_p2<MM, MODE>, smem)) return e;                                         \
+    rows_forward_p2<MM, MODE><<<grid, fft2::kThreads, smem, stream>>>(image, h, w, mean_std, mask, jobs, ylo, yhi, \
+                                                                     ny, kx_count, px.tw, (float2*)tmp, rows_per_cta); \
+  }
+        if (job_mode == 1) TMC_ROWS_FWD(1) else if (job_mode == 2) TMC_ROWS_FWD(2) else TMC_ROWS_FWD(0)
+#undef TMC_ROWS_FWD
+        tmc_count_launch();
       }
       return TMC_OK;
     }

@@ -3,7 +3,28 @@
 #pragma once
 
 // ---- forward rows: image window * mask^e (two real signals packed) -> tmp[plane][y][kx < KX] --------
+//
+// MODE 0: generic jobs {frame_a, power_a, frame_b, power_b}; 1: frame_b == frame_a with powers (1, 2)
+// (the leave-one-out pair of quirk Q1); 2: two frames (or one, frame_b < 0), power 1 each.
+// The pixels / mask values of the NEXT batch of rows are prefetched with cp.async into per-thread
+// shared-memory slots while the current batch is being transformed (global-load latency was the
+// dominant stall of the first version: profiles/r01_*).
+
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit_and_wait() {
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
 template <int N>
+constexpr size_t rows_forward_smem_bytes() {
+  return fft2::Cfg<N>::smem_bytes + 3ull * fft2::Cfg<N>::B * N * sizeof(float);
+}
+
+template <int N, int MODE>
 __global__ void __launch_bounds__(fft2::kThreads)
 rows_forward_p2(const float* __restrict__ image, int H, int W, const float* __restrict__ mean_std,
                 const float* __restrict__ mask, const int* __restrict__ jobs, int ylo, int yhi, int NY, int KX,
@@ -15,6 +36,10 @@ rows_forward_p2(const float* __restrict__ image, int H, int W, const float* __re
   fft2::load_twiddles<N>(sm, tw);
   const int seq = threadIdx.x / C::TPS, j = threadIdx.x % C::TPS;
   float2* myseq = sm.data + seq * C::STRIDE;
+  // per-thread staging slots: element e of this thread lives at stage_x[e * kThreads + threadIdx.x]
+  float* stage_a = reinterpret_cast<float*>(smem + C::B * C::STRIDE + 64 + C::TW_HI);
+  float* stage_b = stage_a + C::B * N;
+  float* stage_m = stage_b + C::B * N;
   const int job = blockIdx.y;
   const int fa = jobs[job * 6 + 0], ea = jobs[job * 6 + 1], fb = jobs[job * 6 + 2], eb = jobs[job * 6 + 3];
   const int y0 = jobs[job * 6 + 4], x0 = jobs[job * 6 + 5];
@@ -25,37 +50,61 @@ rows_forward_p2(const float* __restrict__ image, int H, int W, const float* __re
   }
   const long fs = (long)H * W;
   const float* img_a = image + fa * fs + (long)y0 * W + x0;
-  const float* img_b = fb >= 0 ? image + fb * fs + (long)y0 * W + x0 : nullptr;
-  const bool same = fb == fa;
+  const bool has_b = fb >= 0;
+  const bool separate_b = has_b && (MODE == 2 || (MODE == 0 && fb != fa));
+  const float* img_b = has_b ? image + fb * fs + (long)y0 * W + x0 : nullptr;
   const int row_begin = ylo + blockIdx.x * rows_per_cta;
   const int row_end = min(yhi, row_begin + rows_per_cta);
   float2* plane_a = tmp + (long)(2 * job) * NY * KX;
   float2* plane_b = plane_a + (long)NY * KX;
-  __syncthreads();
+
+  auto prefetch = [&](int row0) {
+    const int y = row0 + seq;
+    if (y < row_end) {
+#pragma unroll
+      for (int e = 0; e < C::VPT; ++e) {
+        const int x = P::First::in_index(j, e / P::First::R, e % P::First::R);
+        const int slot = e * fft2::kThreads + threadIdx.x;
+        cp_async_f32(stage_a + slot, img_a + (long)y * W + x);
+        if (separate_b) cp_async_f32(stage_b + slot, img_b + (long)y * W + x);
+        if (mask) cp_async_f32(stage_m + slot, mask + (long)y * N + x);
+      }
+    }
+  };
+  prefetch(row_begin);
+  __syncthreads();  // twiddle tables
   for (int row0 = row_begin; row0 < row_end; row0 += C::B) {
     const int y = row0 + seq;
     const bool active = y < row_end;
+    cp_async_commit_and_wait();
     float2 v[C::VPT];
 #pragma unroll
-    for (int g = 0; g < P::First::G; ++g)
-#pragma unroll
-      for (int r = 0; r < P::First::R; ++r) {
-        float2 z = make_float2(0.f, 0.f);
-        if (active) {
-          const int x = P::First::in_index(j, g, r);
-          const float m = mask ? __ldg(mask + (long)y * N + x) : 1.0f;
-          const float pa = (__ldg(img_a + (long)y * W + x) - mean) * inv_std;
+    for (int e = 0; e < C::VPT; ++e) {
+      float2 z = make_float2(0.f, 0.f);
+      if (active) {
+        const int slot = e * fft2::kThreads + threadIdx.x;
+        const float m = mask ? stage_m[slot] : 1.0f;
+        const float pa = (stage_a[slot] - mean) * inv_std;
+        if (MODE == 1) {
+          z.x = pa * m;
+          z.y = z.x * m;
+        } else if (MODE == 2) {
+          z.x = pa * m;
+          if (has_b) z.y = (stage_b[slot] - mean) * inv_std * m;
+        } else {
           float va = pa;
-          for (int e = 0; e < ea; ++e) va *= m;
+          for (int k = 0; k < ea; ++k) va *= m;
           z.x = va;
-          if (img_b) {
-            float vb = same ? pa : (__ldg(img_b + (long)y * W + x) - mean) * inv_std;
-            for (int e = 0; e < eb; ++e) vb *= m;
+          if (has_b) {
+            float vb = separate_b ? (stage_b[slot] - mean) * inv_std : pa;
+            for (int k = 0; k < eb; ++k) vb *= m;
             z.y = vb;
           }
         }
-        v[g * P::First::R + r] = z;
       }
+      v[e] = z;
+    }
+    if (row0 + C::B < row_end) prefetch(row0 + C::B);  // overlaps with the transform below
     fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
     __syncthreads();
     P::Last::store(myseq, j, v);
@@ -65,7 +114,7 @@ rows_forward_p2(const float* __restrict__ image, int H, int W, const float* __re
         const float2 zk = myseq[fft2::pad_idx(k)];
         const float2 zn = myseq[fft2::pad_idx(k == 0 ? 0 : N - k)];
         plane_a[(long)y * KX + k] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-        if (img_b) plane_b[(long)y * KX + k] = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+        if (has_b) plane_b[(long)y * KX + k] = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
       }
     }
     __syncthreads();

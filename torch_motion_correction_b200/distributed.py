@@ -95,7 +95,7 @@ def estimate_global_motion_frame_split(local_frames, pixel_spacing, frame_offset
         reference_frame = total_frames // 2
     plan = _fourier.BandPlan(h, w, dev, pixel_spacing, b_factor, frequency_range)
     mask, ylo, yhi = _fourier.soft_disc_mask((h, w), min(h, w) / 4, min(h, w) / 8, dev)
-    spec = plan.forward(local_frames, mean_std, mask, ylo, yhi, _fourier.frame_pair_jobs(t_local, dev))
+    spec = plan.forward(local_frames, mean_std, mask, ylo, yhi, _fourier.frame_pair_jobs(t_local, dev), job_mode=2)
     ref_spec = torch.empty((1, plan.ky, plan.kx, 2), dtype=torch.float32, device=dev)
     owner = next(r for r in range(world) if frame_range(total_frames, r, world)[0] <= reference_frame < frame_range(total_frames, r, world)[1])
     if rank == owner:
@@ -150,7 +150,7 @@ def estimate_patch_motion_frame_split(local_frames, pixel_spacing, frame_offset,
     else:
         field = resample_deformation_field(deformation_field, (t, gh, gw))
     jobs = torch.tensor([[k, 1, k, 2, y0, x0] for k in range(t_local) for (y0, x0) in origins], dtype=torch.int32).to(dev)
-    spec_local = plan.forward(source, source_stats, mask, ylo, yhi, jobs).view(t_local, g * 2 * plan.plane_elems * 2)
+    spec_local = plan.forward(source, source_stats, mask, ylo, yhi, jobs, job_mode=1).view(t_local, g * 2 * plan.plane_elems * 2)
     spec_all = all_gather_frames(spec_local, t, group)
     offsets, deltas = _aliasing_schedule(t, "mean_except_current", t // 2)
     d_off = torch.tensor(offsets, dtype=torch.int32).to(dev)

@@ -102,7 +102,7 @@ class LocalMotionProblem:
             for i in range(0, t, 2):
                 jobs.append([i, 1, i + 1 if i + 1 < t else -1, 1, y0[gi], x0[gi]])
         jobs = torch.tensor(jobs, dtype=torch.int32).to(dev)
-        self.spec = self.plan.forward(movie, stats, mask, ylo, yhi, jobs)  # (g * tp, KY, KX, 2)
+        self.spec = self.plan.forward(movie, stats, mask, ylo, yhi, jobs, job_mode=2)  # (g * tp, KY, KX, 2)
         self.norms = torch.empty((self.g, t, 2), dtype=torch.float64, device=dev)
         p = self.plan
         with torch.cuda.device(dev):

@@ -35,7 +35,7 @@ def estimate_global_motion(
     stats = _ops.stack_stats(movie)
     plan = _fourier.BandPlan(h, w, dev, pixel_spacing, b_factor, frequency_range)
     mask, ylo, yhi = _fourier.soft_disc_mask((h, w), min(h, w) / 4, min(h, w) / 8, dev)
-    spec = plan.forward(movie, stats, mask, ylo, yhi, _fourier.frame_pair_jobs(t, dev))
+    spec = plan.forward(movie, stats, mask, ylo, yhi, _fourier.frame_pair_jobs(t, dev), job_mode=2)
     cur = torch.arange(t, dtype=torch.int32, device=dev)
     ref = torch.full((t,), int(reference_frame), dtype=torch.int32, device=dev)
     prod = _fourier.pair_products(spec, ref, cur, plan.plane_elems)
@@ -168,7 +168,7 @@ def estimate_motion_cross_correlation_patches(
         offsets, deltas = _aliasing_schedule(t, reference_strategy, reference_frame)
         jobs = [[k, 1, k, 2, y0, x0] for k in range(t) for (y0, x0) in origins]
         jobs = torch.tensor(jobs, dtype=torch.int32).to(dev)
-        spec = plan.forward(source, source_stats, mask, ylo, yhi, jobs)
+        spec = plan.forward(source, source_stats, mask, ylo, yhi, jobs, job_mode=1)
         d_off = torch.tensor(offsets, dtype=torch.int32).to(dev)
         d_val = torch.tensor(deltas if deltas else [0], dtype=torch.int32).to(dev)
         prod = _fourier.leave_one_out_products(spec, t, n_patches, plan.plane_elems, d_off, d_val)
