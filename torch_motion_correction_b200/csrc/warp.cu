@@ -16,14 +16,48 @@ constexpr float kA = -0.75f;  // Keys cubic convolution parameter used by ATen's
 
 // ATen get_cubic_upsample_coefficients
 __device__ __forceinline__ void cubic_weights(float t, float (&w)[4]) {
+  // ((A x - 5A) x + 8A) x - 4A   and   ((A + 2) x - (A + 3)) x x + 1, three FMAs each
   float x = t + 1.0f;
-  w[0] = ((kA * x - 5.0f * kA) * x + 8.0f * kA) * x - 4.0f * kA;
+  w[0] = fmaf(fmaf(fmaf(kA, x, -5.0f * kA), x, 8.0f * kA), x, -4.0f * kA);
   x = t;
-  w[1] = ((kA + 2.0f) * x - (kA + 3.0f)) * x * x + 1.0f;
+  w[1] = fmaf(fmaf(kA + 2.0f, x, -(kA + 3.0f)) * x, x, 1.0f);
   x = 1.0f - t;
-  w[2] = ((kA + 2.0f) * x - (kA + 3.0f)) * x * x + 1.0f;
+  w[2] = fmaf(fmaf(kA + 2.0f, x, -(kA + 3.0f)) * x, x, 1.0f);
   x = 2.0f - t;
-  w[3] = ((kA * x - 5.0f * kA) * x + 8.0f * kA) * x - 4.0f * kA;
+  w[3] = fmaf(fmaf(fmaf(kA, x, -5.0f * kA), x, 8.0f * kA), x, -4.0f * kA);
+}
+
+// c / d for a divisor known per launch: q0 = c * (1/d), one Newton step on the residual.  Correctly
+// rounded for all but vanishingly rare operands -- a third of the instructions of __fdiv_rn.
+struct Divisor {
+  float d, rcp;
+};
+__device__ __forceinline__ Divisor make_divisor(float d) {
+  Divisor v;
+  v.d = d;
+  v.rcp = __frcp_rn(d);
+  return v;
+}
+__device__ __forceinline__ float div_by(float c, const Divisor& v) {
+  const float q0 = __fmul_rn(c, v.rcp);
+  const float r = fmaf(-q0, v.d, c);
+  return fmaf(r, v.rcp, q0);
+}
+
+// grid_round_trip with the divisor prepared once per thread
+struct RoundTrip {
+  Divisor denom;  // 0.5 n - 0.5
+  float scale;    // n - 1
+};
+__device__ __forceinline__ RoundTrip make_round_trip(int n) {
+  RoundTrip r;
+  r.denom = make_divisor(__fsub_rn(__fmul_rn(0.5f, (float)n), 0.5f));
+  r.scale = (float)(n - 1);
+  return r;
+}
+__device__ __forceinline__ float round_trip(float c, const RoundTrip& r) {
+  const float g = __fsub_rn(div_by(c, r.denom), 1.0f);
+  return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), r.scale);
 }
 
 // array coordinate -> grid_sample [-1,1] -> unnormalised source coordinate, as fp32 ops:
@@ -99,8 +133,8 @@ __device__ __forceinline__ float gather_bicubic(const float* __restrict__ frame,
 }
 
 constexpr int kTileX = 128;  // threads along x
-constexpr int kTileYGroups = 2;
-constexpr int kRowsPerThread = 4;
+constexpr int kTileYGroups = 8;
+constexpr int kRowsPerThread = 1;
 
 // Stage 1: interpolate every lattice row along x once per (frame, channel, lattice row, image
 // column): RX[f][ch][a][x] = sum_b wx_b(x) * L[f][ch][a][jx_b(x)].  Same x-then-y order as ATen.
@@ -118,7 +152,7 @@ __global__ void lattice_xinterp_kernel(const float* __restrict__ lattice, int T,
 
 // Stage 2: one thread = kRowsPerThread vertically adjacent output pixels of one column.
 template <bool WRITE_STACK, bool WRITE_SUM, bool NORMALISE>
-__global__ void __launch_bounds__(kTileX* kTileYGroups)
+__global__ void __launch_bounds__(kTileX* kTileYGroups, 1)
 warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const float* __restrict__ rx, int lh,
                     float pixel_spacing, const float* __restrict__ mean_std, float* __restrict__ out_stack,
                     float* __restrict__ out_sum, int accumulate_sum) {
@@ -137,37 +171,73 @@ warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const 
       wy[r][k] = a.w[k];
     }
   }
-  float mean = 0.f, stdv = 1.f;
+  float mean = 0.f, inv_std = 1.f;
   if (NORMALISE) {
     mean = __ldg(mean_std);
-    stdv = __ldg(mean_std + 1);
+    inv_std = 1.0f / __ldg(mean_std + 1);
   }
   float acc[kRowsPerThread];
 #pragma unroll
   for (int r = 0; r < kRowsPerThread; ++r) acc[r] = 0.f;
 
-  const long rx_plane = (long)lh * W;
-  for (int f = 0; f < T; ++f) {
-    const float* Ry = rx + (long)f * 2 * rx_plane + x;
-    const float* Rx = Ry + rx_plane;
-    const float* frame = image + (long)f * H * W;
+  const RoundTrip rty = make_round_trip(H), rtx = make_round_trip(W);
+  const float inv_px = 1.0f / pixel_spacing;
+  const float hmax = (float)(H - 1), wmax = (float)(W - 1);
+  const unsigned rx_plane = (unsigned)lh * (unsigned)W;
+  const float* rx_frame = rx + x;
+  const float* frame = image;
+  for (int f = 0; f < T; ++f, rx_frame += 2 * (size_t)rx_plane, frame += (size_t)H * W) {
 #pragma unroll
     for (int r = 0; r < kRowsPerThread; ++r) {
       const int y = y_base + r;
       if (y < H) {
-        float sy = wy[r][0] * __ldg(Ry + jy[r][0]) + wy[r][1] * __ldg(Ry + jy[r][1]) + wy[r][2] * __ldg(Ry + jy[r][2]) +
-                   wy[r][3] * __ldg(Ry + jy[r][3]);
-        float sx = wy[r][0] * __ldg(Rx + jy[r][0]) + wy[r][1] * __ldg(Rx + jy[r][1]) + wy[r][2] * __ldg(Rx + jy[r][2]) +
-                   wy[r][3] * __ldg(Rx + jy[r][3]);
-        // Angstrom -> px (true division like the CPU reference), then pixel_grid + pixel_shifts
-        ImageAxis ay = image_axis(__fadd_rn((float)y, __fdiv_rn(sy, pixel_spacing)), H);
-        ImageAxis ax = image_axis(__fadd_rn((float)x, __fdiv_rn(sx, pixel_spacing)), W);
+        const float* Ry = rx_frame;
+        const float* Rx = rx_frame + rx_plane;
+        float sy = wy[r][0] * __ldg(Ry + jy[r][0]);
+        sy = fmaf(wy[r][1], __ldg(Ry + jy[r][1]), sy);
+        sy = fmaf(wy[r][2], __ldg(Ry + jy[r][2]), sy);
+        sy = fmaf(wy[r][3], __ldg(Ry + jy[r][3]), sy);
+        float sx = wy[r][0] * __ldg(Rx + jy[r][0]);
+        sx = fmaf(wy[r][1], __ldg(Rx + jy[r][1]), sx);
+        sx = fmaf(wy[r][2], __ldg(Rx + jy[r][2]), sx);
+        sx = fmaf(wy[r][3], __ldg(Rx + jy[r][3]), sx);
+        // Angstrom -> px, then pixel_grid + pixel_shifts (two roundings, like the reference)
+        const float cy = __fadd_rn((float)y, __fmul_rn(sy, inv_px));
+        const float cx = __fadd_rn((float)x, __fmul_rn(sx, inv_px));
         float v = 0.f;
-        if (ay.inside && ax.inside) {
-          v = gather_bicubic(frame, W, ay, ax);
-          if (NORMALISE) v = __fdiv_rn(__fsub_rn(v, mean), stdv);
+        if (cy >= 0.0f && cy <= hmax && cx >= 0.0f && cx <= wmax) {
+          const float uy = round_trip(cy, rty), ux = round_trip(cx, rtx);
+          const float fy = floorf(uy), fx = floorf(ux);
+          float ay[4], ax[4];
+          cubic_weights(__fsub_rn(uy, fy), ay);
+          cubic_weights(__fsub_rn(ux, fx), ax);
+          const int iy = (int)fy, ix = (int)fx;
+          if (iy >= 1 && iy <= H - 3 && ix >= 1 && ix <= W - 3) {
+            // interior: 4 row pointers, taps at immediate offsets
+            const float* p = frame + (unsigned)((iy - 1) * W + (ix - 1));
+#pragma unroll
+            for (int a = 0; a < 4; ++a, p += W) {
+              float row = ax[0] * __ldg(p);
+              row = fmaf(ax[1], __ldg(p + 1), row);
+              row = fmaf(ax[2], __ldg(p + 2), row);
+              row = fmaf(ax[3], __ldg(p + 3), row);
+              v = fmaf(ay[a], row, v);
+            }
+          } else {
+            // border: every tap index clamped individually (grid_sample padding_mode="border")
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const float* p = frame + (size_t)min(max(iy - 1 + a, 0), H - 1) * W;
+              float row = ax[0] * __ldg(p + min(max(ix - 1, 0), W - 1));
+              row = fmaf(ax[1], __ldg(p + min(max(ix, 0), W - 1)), row);
+              row = fmaf(ax[2], __ldg(p + min(max(ix + 1, 0), W - 1)), row);
+              row = fmaf(ax[3], __ldg(p + min(max(ix + 2, 0), W - 1)), row);
+              v = fmaf(ay[a], row, v);
+            }
+          }
+          if (NORMALISE) v = (v - mean) * inv_std;
         }
-        if (WRITE_STACK) out_stack[((long)f * H + y) * W + x] = v;
+        if (WRITE_STACK) out_stack[((size_t)f * H + y) * W + x] = v;
         if (WRITE_SUM) acc[r] += v;
       }
     }
