@@ -161,9 +161,12 @@ long tmc_local_loss_workspace_bytes(int g, int t, int ky_count, int kx_count);
  * centres; patch_scale (g): weight of each patch's mean-reduced mini-batch loss; loss_type 0 mse, 1 cc,
  * 2 ncc.  Outputs: loss (device double, sum over mini-batches) and grad_eval (t, g, 2) = dloss/d eval_new. */
 int tmc_local_loss_grad(const void* spec, const double* norms, const float* eval_new, const float* eval_base,
-                        const float* patch_scale, int g, int t, int tp, int ny, int nx, int ky_count, int kx_count,
-                        int ky_start, float pixel_spacing, int loss_type, double* loss, float* grad_eval, void* workspace,
-                        tmc_stream_t stream);
+                        const float* patch_scale, const int* iteration, int g, int t, int tp, int ny, int nx, int ky_count,
+                        int kx_count, int ky_start, float pixel_spacing, int loss_type, double* loss, float* grad_eval,
+                        void* workspace, tmc_stream_t stream);
+/* *counter += 1 on the stream: device-side iteration index so a captured optimiser step can be replayed
+ * (patch_scale may then be (n_iterations, g) with `iteration` = counter; mse / cc only) */
+int tmc_advance_counter(int* counter, tmc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -60,7 +60,8 @@ _SIGNATURES = {
     "tmc_subtract_mean": (I, [P, L, P]),
     "tmc_local_spectra_norms": (I, [P, I, I, I, I, I, I, I, I, P, P]),
     "tmc_local_loss_workspace_bytes": (L, [I, I, I, I]),
-    "tmc_local_loss_grad": (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, F, I, P, P, P, P]),
+    "tmc_local_loss_grad": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, I, P, P, P, P]),
+    "tmc_advance_counter": (I, [P, P]),
 }
 
 
@@ -120,7 +121,7 @@ def call(name: str, *args):
     """Call an ``int``-returning entry point; non-zero status raises with ``tmc_last_error()``."""
     lib = load()
     CALLS[name] = CALLS.get(name, 0) + 1
-    if TIMING is not None:
+    if TIMING is not None and not torch.cuda.is_current_stream_capturing():
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()  # current stream of the current device == the stream passed to the call
         status = getattr(lib, name)(*args)

@@ -206,6 +206,142 @@ loss_backward_kernel(const float2* __restrict__ spec, const float* __restrict__ 
   }
 }
 
+// ---- fused fast path for "mse" and "cc": both depend on the shifts only through q = sum_f w |Sigma|^2
+//      (Z_t = 2 b Sigma with b = -scale a^2 / T resp. -scale / (P (T-1))), so one kernel does it all. ----
+
+// E[(g*T + t) * (KY + KX) + i]: i < KY -> exp(i cfy(i) s_y), else exp(i cfx(i - KY) s_x).
+// exp(i theta) = exp(i cfy s_y) exp(i cfx s_x): 2 table reads + one complex multiply per bin and frame
+// instead of a sincosf (differs from the reference's cos/sin of the summed angle by fp32 rounding only).
+__global__ void phase_tables_kernel(const float* __restrict__ shifts, int T, BandGeom geom, float2* __restrict__ E) {
+  const int gt = blockIdx.x;
+  const float sy = shifts[2 * gt], sx = shifts[2 * gt + 1];
+  const float c = -6.283185307179586f;
+  for (int i = threadIdx.x; i < geom.KY + geom.KX; i += blockDim.x) {
+    float ang;
+    if (i < geom.KY) {
+      int ky = geom.ky_start + i;
+      ky = ((ky % geom.ny) + geom.ny) % geom.ny;
+      if (ky >= (geom.ny + 1) / 2) ky -= geom.ny;
+      ang = __fmul_rn(__fmul_rn(c, __fmul_rn((float)ky, (float)(1.0 / (double)geom.ny))), sy);
+    } else {
+      ang = __fmul_rn(__fmul_rn(c, __fmul_rn((float)(i - geom.KY), (float)(1.0 / (double)geom.nx))), sx);
+    }
+    float s, co;
+    sincosf(ang, &s, &co);
+    E[(long)gt * (geom.KY + geom.KX) + i] = make_float2(co, s);
+  }
+}
+
+constexpr int kFusedBins = 4;  // bins per thread (amortises the per-frame warp reductions)
+
+// q[g] += sum_f w |Sigma|^2 ; grad[g][t][:] += -2 b sum_f w (c f) Im(S_t conj Sigma)
+__global__ void __launch_bounds__(kOptThreads)
+loss_fused_kernel(const float2* __restrict__ spec, const float2* __restrict__ E, const float* __restrict__ patch_scale,
+                  const int* __restrict__ iter_ptr, int G, int T, int Tp, BandGeom geom, int loss_type, int ph, int pw,
+                  double* __restrict__ q, float* __restrict__ grad) {
+  extern __shared__ float acc[];  // [T][2]
+  const int g = blockIdx.y;
+  const int bins = geom.KY * geom.KX;
+  for (int i = threadIdx.x; i < 2 * T; i += kOptThreads) acc[i] = 0.f;
+  const float sc = patch_scale[(long)(iter_ptr ? *iter_ptr : 0) * G + g];
+  if (sc == 0.f || T < 2) return;
+  float b;
+  if (loss_type == 0) {
+    const float a = (float)T / (float)(T - 1);
+    b = -sc * a * a / (float)T;
+  } else {
+    b = -sc / ((float)ph * (float)pw * (float)(T - 1));
+  }
+  int bin[kFusedBins], kyb[kFusedBins], kx[kFusedBins];
+  float cfy[kFusedBins], cfx[kFusedBins], w[kFusedBins];
+  float2 sum[kFusedBins];
+#pragma unroll
+  for (int i = 0; i < kFusedBins; ++i) {
+    bin[i] = (blockIdx.x * kFusedBins + i) * kOptThreads + threadIdx.x;
+    const bool live = bin[i] < bins;
+    const int bb = live ? bin[i] : 0;
+    float herm;
+    bin_freqs(geom, bb, cfy[i], cfx[i], herm);
+    w[i] = live ? (loss_type == 0 ? 1.0f : herm) : 0.0f;
+    kyb[i] = bb / geom.KX;
+    kx[i] = bb % geom.KX;
+    bin[i] = bb;
+    sum[i] = make_float2(0.f, 0.f);
+  }
+  const float2* sp = spec + (long)g * Tp * bins;
+  const float2* Eg = E + (long)g * T * (geom.KY + geom.KX);
+  for (int t = 0; t < T; ++t) {
+    const float2* Et = Eg + (long)t * (geom.KY + geom.KX);
+#pragma unroll
+    for (int i = 0; i < kFusedBins; ++i) {
+      const float2 e = cmul(__ldg(Et + kyb[i]), __ldg(Et + geom.KY + kx[i]));
+      sum[i] = cadd(sum[i], cmul(__ldg(sp + (long)t * bins + bin[i]), e));
+    }
+  }
+  {
+    double v = 0.0;
+#pragma unroll
+    for (int i = 0; i < kFusedBins; ++i) v += (double)w[i] * ((double)sum[i].x * sum[i].x + (double)sum[i].y * sum[i].y);
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) atomicAdd(q + g, v);
+  }
+  __syncthreads();  // acc zeroed
+  for (int t = 0; t < T; ++t) {
+    const float2* Et = Eg + (long)t * (geom.KY + geom.KX);
+    float gy = 0.f, gx = 0.f;
+#pragma unroll
+    for (int i = 0; i < kFusedBins; ++i) {
+      const float2 e = cmul(__ldg(Et + kyb[i]), __ldg(Et + geom.KY + kx[i]));
+      const float2 s = cmul(__ldg(sp + (long)t * bins + bin[i]), e);
+      const float im = w[i] * (s.y * sum[i].x - s.x * sum[i].y);  // w Im(S conj Sigma)
+      gy = fmaf(cfy[i], im, gy);
+      gx = fmaf(cfx[i], im, gx);
+    }
+    gy = warp_sum(gy);
+    gx = warp_sum(gx);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(acc + 2 * t, gy);
+      atomicAdd(acc + 2 * t + 1, gx);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * T; i += kOptThreads) {
+    const float v = -2.0f * b * acc[i];
+    if (v != 0.f) atomicAdd(grad + (long)g * T * 2 + i, v);
+  }
+}
+
+// loss = sum_g scale_g * l_g(q_g, sum_t A_t) ; grad_eval[t][g][c] = -(1/px) grad_shifts[g][t][c]
+__global__ void loss_fused_finish_kernel(const double* __restrict__ norms, const double* __restrict__ q,
+                                         const float* __restrict__ patch_scale, const int* __restrict__ iter_ptr, int G, int T,
+                                         int ph, int pw, int loss_type, const float* __restrict__ grad_shifts,
+                                         float pixel_spacing, double* __restrict__ loss, float* __restrict__ grad_eval) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T * G * 2) {
+    const int c = i & 1, r = i >> 1;
+    const int t = r / G, g = r % G;
+    grad_eval[i] = -grad_shifts[((long)g * T + t) * 2 + c] / pixel_spacing;
+  }
+  if (i < G && T >= 2) {
+    const int g = i;
+    const double sc = (double)patch_scale[(long)(iter_ptr ? *iter_ptr : 0) * G + g];
+    if (sc != 0.0) {
+      double sumA = 0.0;
+      for (int t = 0; t < T; ++t) sumA += norms[((long)g * T + t) * 2 + (loss_type == 0 ? 0 : 1)];
+      double l;
+      if (loss_type == 0) {
+        const double a = (double)T / (double)(T - 1);
+        l = sc * a * a * (sumA - q[g] / T);
+      } else {
+        l = -sc * (q[g] - sumA) / ((double)ph * (double)pw * (double)(T - 1));
+      }
+      atomicAdd(loss, l);
+    }
+  }
+}
+
+__global__ void advance_counter_kernel(int* counter) { *counter += 1; }
+
 // shifts[g][t] = -(new[t][g] + base[t][g]) / pixel_spacing   (estimate_motion_optimizer.py:487-492)
 __global__ void predicted_shifts_kernel(const float* __restrict__ eval_new, const float* __restrict__ eval_base, int T, int G,
                                         float pixel_spacing, float* __restrict__ shifts) {
@@ -244,19 +380,23 @@ TMC_API int tmc_local_spectra_norms(const void* spec, int g, int t, int tp, int 
 // One loss + gradient evaluation.
 //  eval_new / eval_base: (T, G, 2) spline values (Angstrom) at the patch centres; patch_scale (G) f32;
 //  loss_type 0 mse / 1 cc / 2 ncc; outputs: loss (device double, zeroed here), grad_eval (T, G, 2) = dL/d eval_new.
-//  workspace layout (floats): sigma 2*G*bins | shifts 2*G*T | grad_shifts 2*G*T | alpha G*T | beta G |
-//                             then doubles q G | p G*T  (see tmc_local_loss_workspace_bytes)
-TMC_API long tmc_local_loss_workspace_bytes(int g, int t, int ky_count, int kx_count) {
+//  patch_scale: (G) f32, or (n_iterations, G) when `iteration` (device int, nullable) selects the row -- this
+//  lets a captured CUDA graph replay the step with a different mini-batch weighting every iteration;
+//  workspace layout (floats): sigma 2*G*bins | phase tables 2*G*T*(KY+KX) | shifts 2*G*T | grad_shifts 2*G*T |
+//                             alpha G*T | beta G | then doubles q G | p G*T
+static long local_loss_workspace_floats(int g, int t, int ky_count, int kx_count) {
   long bins = (long)ky_count * kx_count;
-  long floats = 2 * g * bins + 2l * g * t + 2l * g * t + (long)g * t + g;
-  floats = (floats + 1) & ~1l;
-  return floats * 4 + 8l * (g + (long)g * t);
+  long floats = 2 * g * bins + 2l * g * t * (ky_count + kx_count) + 2l * g * t + 2l * g * t + (long)g * t + g;
+  return (floats + 1) & ~1l;
+}
+TMC_API long tmc_local_loss_workspace_bytes(int g, int t, int ky_count, int kx_count) {
+  return local_loss_workspace_floats(g, t, ky_count, kx_count) * 4 + 8l * (g + (long)g * t);
 }
 
 TMC_API int tmc_local_loss_grad(const void* spec, const double* norms, const float* eval_new, const float* eval_base,
-                                const float* patch_scale, int g, int t, int tp, int ny, int nx, int ky_count, int kx_count,
-                                int ky_start, float pixel_spacing, int loss_type, double* loss, float* grad_eval,
-                                void* workspace, cudaStream_t stream) {
+                                const float* patch_scale, const int* iteration, int g, int t, int tp, int ny, int nx,
+                                int ky_count, int kx_count, int ky_start, float pixel_spacing, int loss_type, double* loss,
+                                float* grad_eval, void* workspace, cudaStream_t stream) {
   TMC_CHECK_ARG(spec && norms && eval_new && eval_base && patch_scale && loss && grad_eval && workspace,
                 "local_loss_grad: null pointer");
   TMC_CHECK_ARG(g >= 1 && t >= 1 && tp >= t && loss_type >= 0 && loss_type <= 2 && pixel_spacing > 0.f,
@@ -265,12 +405,12 @@ TMC_API int tmc_local_loss_grad(const void* spec, const double* norms, const flo
   const long bins = (long)ky_count * kx_count;
   float* wf = (float*)workspace;
   float2* sigma = (float2*)wf;
-  float* shifts = wf + 2 * g * bins;
+  float2* E = (float2*)(wf + 2 * g * bins);
+  float* shifts = wf + 2 * g * bins + 2l * g * t * (ky_count + kx_count);
   float* grad_shifts = shifts + 2l * g * t;
   float* alpha = grad_shifts + 2l * g * t;
   float* beta = alpha + (long)g * t;
-  long floats = 2 * g * bins + 2l * g * t + 2l * g * t + (long)g * t + g;
-  floats = (floats + 1) & ~1l;
+  const long floats = local_loss_workspace_floats(g, t, ky_count, kx_count);
   double* q = (double*)(wf + floats);
   double* p = q + g;
   TMC_CUDA(cudaMemsetAsync(q, 0, sizeof(double) * ((size_t)g + (size_t)g * t), stream));
@@ -278,6 +418,18 @@ TMC_API int tmc_local_loss_grad(const void* spec, const double* norms, const flo
   TMC_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), stream));
   const int n = t * g * 2;
   predicted_shifts_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(eval_new, eval_base, t, g, pixel_spacing, shifts); tmc_count_launch();
+  if (loss_type != 2) {
+    phase_tables_kernel<<<g * t, 128, 0, stream>>>(shifts, t, geom, E); tmc_count_launch();
+    dim3 fgrid(tmc_div_up(bins, kOptThreads * kFusedBins), g);
+    loss_fused_kernel<<<fgrid, kOptThreads, sizeof(float) * 2 * t, stream>>>((const float2*)spec, E, patch_scale, iteration, g, t, tp,
+                                                                           geom, loss_type, ny, nx, q, grad_shifts); tmc_count_launch();
+    loss_fused_finish_kernel<<<tmc_div_up(n > g ? n : g, 128), 128, 0, stream>>>(norms, q, patch_scale, iteration, g, t, ny, nx,
+                                                                                 loss_type, grad_shifts, pixel_spacing, loss,
+                                                                                 grad_eval); tmc_count_launch();
+    TMC_CHECK_LAUNCH("tmc_local_loss_grad(fused)");
+    return TMC_OK;
+  }
+  TMC_CHECK_ARG(iteration == nullptr, "local_loss_grad: the ncc path takes the per-iteration scale row directly");
   const int hermitian = loss_type != 0;
   dim3 grid(tmc_div_up(bins, kOptThreads), g);
   loss_forward_kernel<<<grid, kOptThreads, 0, stream>>>((const float2*)spec, shifts, t, tp, geom, hermitian, sigma, q, p); tmc_count_launch();
@@ -286,5 +438,13 @@ TMC_API int tmc_local_loss_grad(const void* spec, const double* norms, const flo
                                                         loss_type != 0, grad_shifts); tmc_count_launch();
   shifts_grad_to_eval_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(grad_shifts, t, g, pixel_spacing, grad_eval); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_local_loss_grad");
+  return TMC_OK;
+}
+
+// *counter += 1 on the stream (device-side iteration index of a captured optimiser step)
+TMC_API int tmc_advance_counter(int* counter, cudaStream_t stream) {
+  TMC_CHECK_ARG(counter, "advance_counter: null pointer");
+  advance_counter_kernel<<<1, 1, 0, stream>>>(counter); tmc_count_launch();
+  TMC_CHECK_LAUNCH("tmc_advance_counter");
   return TMC_OK;
 }

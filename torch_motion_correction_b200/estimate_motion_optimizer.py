@@ -30,7 +30,7 @@ def _setup_optimizer(optimizer_type: str, parameters, **kwargs: Any) -> torch.op
     if name == "adam":
         return torch.optim.Adam(
             parameters, lr=kwargs.get("lr", 0.01), betas=kwargs.get("betas", (0.9, 0.999)), eps=kwargs.get("eps", 1e-08),
-            weight_decay=kwargs.get("weight_decay", 0), amsgrad=kwargs.get("amsgrad", False),
+            weight_decay=kwargs.get("weight_decay", 0), amsgrad=kwargs.get("amsgrad", False), capturable=True,
         )
     if name == "sgd":
         return torch.optim.SGD(
@@ -41,6 +41,7 @@ def _setup_optimizer(optimizer_type: str, parameters, **kwargs: Any) -> torch.op
         return torch.optim.RMSprop(
             parameters, lr=kwargs.get("lr", 0.01), alpha=kwargs.get("alpha", 0.99), eps=kwargs.get("eps", 1e-08),
             weight_decay=kwargs.get("weight_decay", 0), momentum=kwargs.get("momentum", 0), centered=kwargs.get("centered", False),
+            capturable=True,
         )
     if name == "lbfgs":
         max_iter = cast(int, kwargs.get("max_iter", 1))
@@ -135,16 +136,64 @@ class LocalMotionProblem:
                 scale[gi] = s
         return scale
 
-    def loss_and_grad(self, new_data: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
-        """Sum over mini-batches of the batch losses (device float64 (1,)) and d/d new_data."""
+    def loss_and_grad(self, new_data: torch.Tensor, scale: torch.Tensor, iteration: torch.Tensor | None = None):
+        """Sum over mini-batches of the batch losses (device float64 (1,)) and d/d new_data.
+
+        ``scale`` is (G,) or, with ``iteration`` (device int32 counter; mse / cc only), (n, G)."""
         eval_new = _ops.spline_eval(new_data, self.kind, self.centres_norm)
         p = self.plan
         with torch.cuda.device(self.dev):
             call("tmc_local_loss_grad", ptr(self.spec), ptr(self.norms), ptr(eval_new), ptr(self.eval_base), ptr(scale),
-                 self.g, self.t, self.tp, self.ph, self.pw, p.ky, p.kx, p.ky_start, self.px, self.loss_type, ptr(self.loss),
-                 ptr(self.grad_eval), ptr(self.workspace), stream_ptr(self.dev))
+                 ptr(iteration), self.g, self.t, self.tp, self.ph, self.pw, p.ky, p.kx, p.ky_start, self.px, self.loss_type,
+                 ptr(self.loss), ptr(self.grad_eval), ptr(self.workspace), stream_ptr(self.dev))
         grad = _ops.spline_eval_backward((2, *self.resolution), self.kind, self.centres_norm, self.grad_eval)
         return self.loss, grad
+
+
+def _graph_capable(optimizer: torch.optim.Optimizer) -> bool:
+    """Optimisers whose step can be captured in a CUDA graph (no host-side state in the step)."""
+    if isinstance(optimizer, torch.optim.SGD):
+        return True
+    return bool(optimizer.defaults.get("capturable", False))
+
+
+def _run_captured(one_step, n_iterations: int, dev: torch.device) -> int:
+    """Run ``n_iterations`` optimiser steps as one eager warm-up + CUDA-graph replays (launch-bound
+    inner loop: ~15 tiny kernels per step).  Returns the number of steps performed (0 if capture
+    is not possible here, e.g. when already capturing)."""
+    if torch.cuda.is_current_stream_capturing():
+        return 0
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(main)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        one_step(0)  # lazily creates the optimiser state outside the capture
+        # capture_begin / capture_end directly: the torch.cuda.graph() context manager would
+        # synchronise the device and empty the caching allocator (every later call would then pay
+        # cudaMalloc for its multi-GB workspaces again)
+        try:
+            graph.capture_begin()
+            try:
+                one_step(1)
+            finally:
+                graph.capture_end()
+        except Exception:  # pragma: no cover - capture refused: finish eagerly
+            main.wait_stream(side)
+            return 1
+    main.wait_stream(side)
+    from . import _lib
+
+    timing = _lib.TIMING
+    if timing is not None:  # bench.py: the replayed kernels are invisible to the per-call timers
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+    for _ in range(n_iterations - 1):
+        graph.replay()
+    if timing is not None:
+        end.record()
+        timing.setdefault("graph:optimiser_steps", []).append((start, end))
+    return n_iterations
 
 
 def _shuffled_batches(n_patches: int, batch_size: int):
@@ -193,8 +242,8 @@ def estimate_local_motion(
     is_lbfgs = optimizer_type.lower() == "lbfgs"
     subsample = kwargs.get("lbfgs_patch_subsample", None) if is_lbfgs else None
 
-    for iter_idx in range(n_iterations):
-        if is_lbfgs:
+    if is_lbfgs:
+        for iter_idx in range(n_iterations):
             state = {}
 
             def closure():
@@ -211,17 +260,35 @@ def estimate_local_motion(
                 return state["loss"]
 
             step_loss = optimizer.step(closure)
-            loss_value = float(step_loss) if return_trajectory else None
-        else:
-            batches = _shuffled_batches(problem.g, 8)
-            scale = torch.tensor(problem.patch_scales(batches), dtype=torch.float32).to(dev)
-            loss, grad = problem.loss_and_grad(new.data, scale)
+            if return_trajectory and trajectory.sample_this_step(iter_idx):
+                trajectory.add_checkpoint(deformation_field=new.data, loss=float(step_loss), step=iter_idx)
+    elif n_iterations > 0:
+        # the mini-batch weighting of every iteration, uploaded once (same random.shuffle stream as the reference)
+        all_batches = [_shuffled_batches(problem.g, 8) for _ in range(n_iterations)]
+        scales = torch.tensor([problem.patch_scales(b) for b in all_batches], dtype=torch.float32).to(dev)
+        counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+        fused = problem.loss_type != 2  # mse / cc: the kernel picks the row from the device-side counter
+
+        def one_step(i: int):
+            if fused:
+                loss, grad = problem.loss_and_grad(new.data, scales, counter)
+            else:
+                loss, grad = problem.loss_and_grad(new.data, scales[i])
             new.grad = grad
             optimizer.step()
-            optimizer.zero_grad()
-            loss_value = float(loss) / len(batches) if return_trajectory else None
-        if return_trajectory and trajectory.sample_this_step(iter_idx):
-            trajectory.add_checkpoint(deformation_field=new.data, loss=loss_value, step=iter_idx)
+            with torch.cuda.device(dev):
+                call("tmc_advance_counter", ptr(counter), stream_ptr(dev))
+            return loss
+
+        done = 0
+        if fused and not return_trajectory and n_iterations >= 4 and _graph_capable(optimizer):
+            done = _run_captured(one_step, n_iterations, dev)
+        for iter_idx in range(done, n_iterations):
+            loss = one_step(iter_idx)
+            if return_trajectory and trajectory.sample_this_step(iter_idx):
+                trajectory.add_checkpoint(
+                    deformation_field=new.data, loss=float(loss) / len(all_batches[iter_idx]), step=iter_idx
+                )
 
     final = (new.data + problem.base).contiguous()
     with torch.cuda.device(dev):
