@@ -167,6 +167,10 @@ int tmc_local_loss_grad(const void* spec, const double* norms, const float* eval
 /* *counter += 1 on the stream: device-side iteration index so a captured optimiser step can be replayed
  * (patch_scale may then be (n_iterations, g) with `iteration` = counter; mse / cc only) */
 int tmc_advance_counter(int* counter, tmc_stream_t stream);
+/* one torch.optim.Adam step (amsgrad off; estimate_motion_optimizer.py:535-548 defaults) on n parameters, fused in
+ * one kernel; the step number is *step_counter + 1 (device int, so the call can live in a CUDA graph) */
+int tmc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int n, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, const int* step_counter, tmc_stream_t stream);
 
 #ifdef __cplusplus
 }

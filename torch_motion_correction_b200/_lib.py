@@ -62,6 +62,7 @@ _SIGNATURES = {
     "tmc_local_loss_workspace_bytes": (L, [I, I, I, I]),
     "tmc_local_loss_grad": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, I, P, P, P, P]),
     "tmc_advance_counter": (I, [P, P]),
+    "tmc_adam_step": (I, [P, P, P, P, I, D, D, D, D, D, P, P]),
 }
 
 

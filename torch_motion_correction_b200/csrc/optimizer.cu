@@ -270,6 +270,7 @@ loss_fused_kernel(const float2* __restrict__ spec, const float2* __restrict__ E,
   }
   const float2* sp = spec + (long)g * Tp * bins;
   const float2* Eg = E + (long)g * T * (geom.KY + geom.KX);
+#pragma unroll 4
   for (int t = 0; t < T; ++t) {
     const float2* Et = Eg + (long)t * (geom.KY + geom.KX);
 #pragma unroll
@@ -286,6 +287,7 @@ loss_fused_kernel(const float2* __restrict__ spec, const float2* __restrict__ E,
     if ((threadIdx.x & 31) == 0) atomicAdd(q + g, v);
   }
   __syncthreads();  // acc zeroed
+#pragma unroll 2
   for (int t = 0; t < T; ++t) {
     const float2* Et = Eg + (long)t * (geom.KY + geom.KX);
     float gy = 0.f, gx = 0.f;
@@ -341,6 +343,32 @@ __global__ void loss_fused_finish_kernel(const double* __restrict__ norms, const
 }
 
 __global__ void advance_counter_kernel(int* counter) { *counter += 1; }
+
+// torch.optim.Adam (amsgrad=False, maximize=False), single-tensor formulas, step = *step_counter + 1:
+//   g += wd p ; m = lerp(m, g, 1 - b1) ; v = b2 v + (1 - b2) g^2 ;
+//   p -= (lr / (1 - b1^step)) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)
+__global__ void adam_step_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ exp_avg,
+                                 float* __restrict__ exp_avg_sq, int n, double lr, double beta1, double beta2, double eps,
+                                 double weight_decay, const int* __restrict__ step_counter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // scalars are formed in double on the "host side" of torch.optim and enter the tensor ops as fp32
+  const double step = (double)(*step_counter + 1);
+  const double bc1 = 1.0 - pow(beta1, step);
+  const double bc2 = 1.0 - pow(beta2, step);
+  const float step_size = (float)(lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const float w1 = (float)(1.0 - beta1), w2 = (float)(1.0 - beta2), b2 = (float)beta2, epsf = (float)eps;
+  float g = grad[i];
+  const float p = param[i];
+  if (weight_decay != 0.0) g = __fadd_rn(g, __fmul_rn((float)weight_decay, p));
+  const float m = __fadd_rn(exp_avg[i], __fmul_rn(w1, __fsub_rn(g, exp_avg[i])));   // lerp_(grad, 1 - beta1)
+  const float v = __fadd_rn(__fmul_rn(exp_avg_sq[i], b2), __fmul_rn(w2, __fmul_rn(g, g)));  // mul_(b2).addcmul_(g, g, 1 - b2)
+  exp_avg[i] = m;
+  exp_avg_sq[i] = v;
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), epsf);
+  param[i] = __fadd_rn(p, __fmul_rn(-step_size, __fdiv_rn(m, denom)));               // addcdiv_(m, denom, value=-step_size)
+}
 
 // shifts[g][t] = -(new[t][g] + base[t][g]) / pixel_spacing   (estimate_motion_optimizer.py:487-492)
 __global__ void predicted_shifts_kernel(const float* __restrict__ eval_new, const float* __restrict__ eval_base, int T, int G,
@@ -446,5 +474,15 @@ TMC_API int tmc_advance_counter(int* counter, cudaStream_t stream) {
   TMC_CHECK_ARG(counter, "advance_counter: null pointer");
   advance_counter_kernel<<<1, 1, 0, stream>>>(counter); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_advance_counter");
+  return TMC_OK;
+}
+
+// One torch.optim.Adam step (amsgrad off) on n parameters; step number = *step_counter + 1 (device int)
+TMC_API int tmc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int n, double lr, double beta1,
+                          double beta2, double eps, double weight_decay, const int* step_counter, cudaStream_t stream) {
+  TMC_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step_counter && n >= 1, "adam_step: bad arguments");
+  adam_step_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                          step_counter); tmc_count_launch();
+  TMC_CHECK_LAUNCH("tmc_adam_step");
   return TMC_OK;
 }

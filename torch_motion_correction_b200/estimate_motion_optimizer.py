@@ -269,19 +269,32 @@ def estimate_local_motion(
         counter = torch.zeros((1,), dtype=torch.int32, device=dev)
         fused = problem.loss_type != 2  # mse / cc: the kernel picks the row from the device-side counter
 
+        # default optimiser: the Adam update is one fused kernel reading the device-side step counter
+        # (torch.optim.Adam's foreach path costs ~15 launches for these <= few hundred parameters)
+        fused_adam = optimizer_type.lower() == "adam" and not kwargs.get("amsgrad", False)
+        if fused_adam:
+            exp_avg, exp_avg_sq = torch.zeros_like(new.data), torch.zeros_like(new.data)
+            lr, (b1, b2) = float(kwargs.get("lr", 0.01)), kwargs.get("betas", (0.9, 0.999))
+            eps, wd = float(kwargs.get("eps", 1e-08)), float(kwargs.get("weight_decay", 0))
+
         def one_step(i: int):
             if fused:
                 loss, grad = problem.loss_and_grad(new.data, scales, counter)
             else:
                 loss, grad = problem.loss_and_grad(new.data, scales[i])
-            new.grad = grad
-            optimizer.step()
+            if fused_adam:
+                with torch.cuda.device(dev):
+                    call("tmc_adam_step", ptr(new.data), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), new.numel(), lr, float(b1),
+                         float(b2), eps, wd, ptr(counter), stream_ptr(dev))
+            else:
+                new.grad = grad
+                optimizer.step()
             with torch.cuda.device(dev):
                 call("tmc_advance_counter", ptr(counter), stream_ptr(dev))
             return loss
 
         done = 0
-        if fused and not return_trajectory and n_iterations >= 4 and _graph_capable(optimizer):
+        if fused and not return_trajectory and n_iterations >= 4 and (fused_adam or _graph_capable(optimizer)):
             done = _run_captured(one_step, n_iterations, dev)
         for iter_idx in range(done, n_iterations):
             loss = one_step(iter_idx)
