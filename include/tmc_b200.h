@@ -138,6 +138,14 @@ int tmc_fourier_shift(void* spec, int t, int ny, int nx, const float* field, flo
 int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const void* plan_x, const void* plan_y, void* tmp,
                     float* out, tmc_stream_t stream);
 
+/* fused correct_motion_fast (power-of-two frame sides >= 256): rows r2c -> columns (FFT, phase, inverse FFT in one
+ * kernel) -> rows c2r.  jobs: frame-pair jobs as for tmc_rfft2_band (job_mode 2) covering the t frames in order;
+ * tmp: 2*njobs*ny*(nx/2+1) complex64; phase: t*ny complex64; out (t, ny, nx). */
+int tmc_fourier_shift_frames_supported(int ny, int nx);
+int tmc_fourier_shift_frames(const float* image, int t, int ny, int nx, const float* mean_std, const int* jobs, int njobs,
+                             const float* field, float sign, const void* plan_x, const void* plan_y, void* tmp, void* phase,
+                             float* out, tmc_stream_t stream);
+
 /* ---- tail of the estimators: estimate_motion_xc.py:131-133,376-410,486-627 -------------------------- */
 /* shifts (t, g, 2) px; field (2, t, g) Angstrom = base field in, result out: per-frame outlier rejection,
  * px -> Angstrom accumulate, Savitzky-Golay (polyorder 1, scipy mode="interp"), one joint mean removed.

@@ -154,6 +154,26 @@ class BandPlan:
                      shifts_base + i0 * 2 * 4, stream)
         return shifts
 
+    def shift_frames(self, image: torch.Tensor, mean_std, field: torch.Tensor) -> torch.Tensor:
+        """Fused whole-frame Fourier shift (3 passes); ``field`` (2, t, 1, 1) px, applied as is."""
+        t, h, w = image.shape
+        dev = image.device
+        out = torch.empty_like(image)
+        per_job = 2 * self.ny * self.kx * _C64
+        chunk_jobs = max(1, min((t + 1) // 2, (8 * CHUNK_BYTES) // per_job))
+        tmp = torch.empty((chunk_jobs * per_job // 4,), dtype=torch.float32, device=dev)
+        phase = torch.empty((2 * chunk_jobs * self.ny, 2), dtype=torch.float32, device=dev)
+        flat = field.reshape(2, t)
+        with torch.cuda.device(dev):
+            stream = stream_ptr(dev)
+            for f0 in range(0, t, 2 * chunk_jobs):
+                n = min(2 * chunk_jobs, t - f0)
+                jobs = frame_pair_jobs(n, dev, frame_offset=f0)
+                sub = flat[:, f0 : f0 + n].contiguous()
+                call("tmc_fourier_shift_frames", ptr(image), n, h, w, ptr(mean_std), ptr(jobs), jobs.shape[0], ptr(sub), 1.0,
+                     ptr(self.tw_x), ptr(self.tw_y), ptr(tmp), ptr(phase), out.data_ptr() + f0 * h * w * 4, stream)
+        return out
+
     def inverse_full(self, spec: torch.Tensor, out: torch.Tensor):
         """spec (n, ny, nx/2+1, 2) -> out (n, ny, nx) real (irfftn, backward normalisation)."""
         n = spec.shape[0]

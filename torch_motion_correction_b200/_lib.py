@@ -53,6 +53,8 @@ _SIGNATURES = {
     "tmc_xc_peaks": (I, [P, I, I, I, I, I, I, I, P, P, P, P, P, P]),
     "tmc_irfft2_full": (I, [P, I, I, I, P, P, P, P, P]),
     "tmc_fourier_shift": (I, [P, I, I, I, P, F, P]),
+    "tmc_fourier_shift_frames_supported": (I, [I, I]),
+    "tmc_fourier_shift_frames": (I, [P, I, I, I, P, P, I, P, F, P, P, P, P, P, P]),
     "tmc_soft_disc_mask": (I, [I, I, F, F, P, P, P]),
     "tmc_band_weights": (I, [I, I, I, I, I, F, F, I, F, F, I, P, P]),
     "tmc_xc_postprocess": (I, [P, I, I, F, I, I, F, I, I, I, P, P, P]),

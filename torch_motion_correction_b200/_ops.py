@@ -43,25 +43,30 @@ def moments_to_mean_std(moments: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def spline_eval(coeffs: torch.Tensor, kind: int, tyx: torch.Tensor) -> torch.Tensor:
+def spline_eval(coeffs: torch.Tensor, kind: int, tyx: torch.Tensor, out=None, ws=None) -> torch.Tensor:
+    """``out`` (n, c) / ``ws`` (tmc_spline_workspace_floats) may be preallocated (allocation-free replays)."""
     c, n0, n1, n2 = coeffs.shape
     lead = tyx.shape[:-1]
     pts = tyx.reshape(-1, 3).contiguous()
     n = pts.shape[0]
-    out = _f32((n, c), coeffs)
-    ws = _f32((query("tmc_spline_workspace_floats", c, n0, n1, n2),), coeffs)
+    if out is None:
+        out = _f32((n, c), coeffs)
+    if ws is None:
+        ws = _f32((query("tmc_spline_workspace_floats", c, n0, n1, n2),), coeffs)
     with torch.cuda.device(coeffs.device):
         call("tmc_spline_eval", ptr(coeffs), c, n0, n1, n2, kind, ptr(pts), n, ptr(out), ptr(ws), stream_ptr(coeffs.device))
     return out.reshape(*lead, c)
 
 
-def spline_eval_backward(shape, kind: int, tyx: torch.Tensor, grad_out: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+def spline_eval_backward(shape, kind: int, tyx: torch.Tensor, grad_out: torch.Tensor, scale: float = 1.0, out=None,
+                         ws=None) -> torch.Tensor:
     c, n0, n1, n2 = shape
     pts = tyx.reshape(-1, 3).contiguous()
     go = grad_out.reshape(-1, c).contiguous()
     n = pts.shape[0]
-    grad = _f32((c, n0, n1, n2), pts)
-    ws = _f32((query("tmc_spline_workspace_floats", c, n0, n1, n2),), pts)
+    grad = _f32((c, n0, n1, n2), pts) if out is None else out
+    if ws is None:
+        ws = _f32((query("tmc_spline_workspace_floats", c, n0, n1, n2),), pts)
     with torch.cuda.device(pts.device):
         call("tmc_spline_eval_backward", c, n0, n1, n2, kind, ptr(pts), n, ptr(go), float(scale), ptr(grad), ptr(ws),
              stream_ptr(pts.device))

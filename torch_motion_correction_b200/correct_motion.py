@@ -77,6 +77,8 @@ def correct_motion_fast(
     moved *= -1  # Q2: visible to the caller whenever .to() did not have to copy
     field = moved.detach().to(torch.float32).contiguous()
     plan = _fourier.BandPlan(h, w, dev, full=True)
+    if _fourier.query("tmc_fourier_shift_frames_supported", h, w):
+        return plan.shift_frames(movie, _mean_std, field)
     spec = plan.forward(movie, _mean_std, None, 0, h, _fourier.frame_pair_jobs(t, dev), job_mode=2)
     with torch.cuda.device(dev):
         call("tmc_fourier_shift", ptr(spec), t, h, w, ptr(field), 1.0, stream_ptr(dev))

@@ -873,3 +873,68 @@ TMC_API int tmc_fourier_shift(void* spec, int t, int ny, int nx, const float* fi
   TMC_CHECK_LAUNCH("tmc_fourier_shift");
   return TMC_OK;
 }
+
+// 1 when tmc_fourier_shift_frames has a fused implementation for (ny, nx) (power-of-two fast path)
+TMC_API int tmc_fourier_shift_frames_supported(int ny, int nx) {
+  return (fft_size_for(ny) == ny && ny >= 256 && fft_size_for(nx) == nx && nx >= 256) ? 1 : 0;
+}
+
+// correct_motion_fast in three passes: rows r2c -> columns (FFT, phase, inverse FFT) -> rows c2r.
+//  image (t, ny, nx) f32 (normalised on load with mean_std, nullable); field (2, t) px shifts, applied as
+//  sign * field; jobs: frame-pair jobs (tmc_rfft2_band format, job_mode 2) covering the t frames in order;
+//  tmp: 2 * njobs * ny * (nx/2+1) complex64; phase: t * ny complex64; out (t, ny, nx) f32.
+TMC_API int tmc_fourier_shift_frames(const float* image, int t, int ny, int nx, const float* mean_std, const int* jobs,
+                                     int njobs, const float* field, float sign, const void* plan_x, const void* plan_y,
+                                     void* tmp, void* phase, float* out, cudaStream_t stream) {
+  TMC_CHECK_ARG(image && jobs && field && plan_x && plan_y && tmp && phase && out, "fourier_shift_frames: null pointer");
+  TMC_CHECK_ARG(t >= 1 && 2 * njobs >= t, "fourier_shift_frames: jobs do not cover the frames");
+  if (!tmc_fourier_shift_frames_supported(ny, nx)) {
+    tmc_set_error("fourier_shift_frames: fused path needs power-of-two frame sides >= 256, got (%d, %d)", ny, nx);
+    return TMC_ERR_UNSUPPORTED;
+  }
+  const int kx = nx / 2 + 1;
+  const AxisPlan px = make_axis_plan(plan_x, nx), py = make_axis_plan(plan_y, ny);
+  int rc = dispatch_fft(nx, "fourier_shift_frames", [&](auto M, auto BLU) {
+    constexpr int MM = decltype(M)::value;
+    if constexpr (use_fast_path<MM, decltype(BLU)::value>()) {
+      constexpr int B = fft2::Cfg<MM>::B;
+      int rows_per_cta = B * 4;
+      while (rows_per_cta > B && (long)tmc_div_up(ny, rows_per_cta) * njobs < 148 * 8) rows_per_cta -= B;
+      constexpr size_t smem = rows_forward_smem_bytes<MM>();
+      if (int e = enable_smem(rows_forward_p2<MM, 2>, smem)) return e;
+      dim3 grid(tmc_div_up(ny, rows_per_cta), njobs);
+      rows_forward_p2<MM, 2><<<grid, fft2::kThreads, smem, stream>>>(image, ny, nx, mean_std, nullptr, jobs, 0, ny, ny, kx, px.tw,
+                                                                    (float2*)tmp, rows_per_cta); tmc_count_launch();
+    }
+    return TMC_OK;
+  });
+  if (rc) return rc;
+  {
+    dim3 grid(tmc_div_up(ny, 128), t);
+    shift_phase_y_kernel<<<grid, 128, 0, stream>>>(field, t, ny, sign, (float2*)phase); tmc_count_launch();
+  }
+  rc = dispatch_fft(ny, "fourier_shift_frames", [&](auto M, auto BLU) {
+    constexpr int MM = decltype(M)::value;
+    if constexpr (use_fast_path<MM, decltype(BLU)::value>()) {
+      if (int e = enable_smem(cols_shift_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
+      dim3 grid(tmc_div_up(kx, fft2::Cfg<MM>::B), t);
+      cols_shift_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>((float2*)tmp, kx, nx, (const float2*)phase,
+                                                                                    field, t, sign, py.tw); tmc_count_launch();
+    }
+    return TMC_OK;
+  });
+  if (rc) return rc;
+  rc = dispatch_fft(nx, "fourier_shift_frames", [&](auto M, auto BLU) {
+    constexpr int MM = decltype(M)::value;
+    if constexpr (use_fast_path<MM, decltype(BLU)::value>()) {
+      if (int e = enable_smem(rows_inverse_store_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
+      dim3 grid(tmc_div_up(ny, rows_per_cta_inverse<MM>()), t);
+      rows_inverse_store_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
+          (const float2*)tmp, ny, kx, px.tw, 1.0f / ((float)nx * (float)ny), out); tmc_count_launch();
+    }
+    return TMC_OK;
+  });
+  if (rc) return rc;
+  TMC_CHECK_LAUNCH("tmc_fourier_shift_frames");
+  return TMC_OK;
+}

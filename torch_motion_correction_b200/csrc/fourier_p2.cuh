@@ -356,3 +356,76 @@ rows_inverse_store_p2(const float2* __restrict__ tmp, int NY, int KX, const floa
     __syncthreads();
   }
 }
+
+// ---- whole-frame Fourier shift, column pass: FFT along y, phase multiply, inverse FFT along y ----------
+// tmp[plane = frame][y][kx] in place.  Fuses what would otherwise be three kernels and three round trips
+// of the (t, ny, nx/2+1) spectrum through HBM (correct_motion.py:484-496).
+// phase_y[f][ky] = exp(i * fp32(-2 pi) * fftfreq(ny)[ky] * s_y[f]) is precomputed; the x factor is one sincosf
+// per thread.  exp(i(a+b)) = exp(ia) exp(ib): differs from the reference's cos/sin of the summed angle by
+// fp32 rounding only.
+template <int N>
+__global__ void __launch_bounds__(fft2::kThreads)
+cols_shift_p2(float2* __restrict__ tmp, int KX, int NX, const float2* __restrict__ phase_y, const float* __restrict__ field,
+              int T, float sign, const float2* __restrict__ tw) {
+  using C = fft2::Cfg<N>;
+  using P = fft2::Plan<N>;
+  extern __shared__ float2 smem[];
+  const fft2::Smem<N> sm(smem);
+  fft2::load_twiddles<N>(sm, tw);
+  const int seq = threadIdx.x % C::B, j = threadIdx.x / C::B;
+  float2* myseq = sm.data + seq * C::STRIDE;
+  const int f = blockIdx.y;
+  const int kx = blockIdx.x * C::B + seq;
+  const bool active = kx < KX;
+  float2* col = tmp + (long)f * N * KX + kx;
+  float2 v[C::VPT];
+#pragma unroll
+  for (int g = 0; g < P::First::G; ++g)
+#pragma unroll
+    for (int r = 0; r < P::First::R; ++r)
+      v[g * P::First::R + r] = active ? col[(long)P::First::in_index(j, g, r) * KX] : make_float2(0.f, 0.f);
+  float2 ex;
+  {
+    const float sx = sign * __ldg(field + T + f);
+    const float fx = __fmul_rn((float)kx, (float)(1.0 / (double)NX));
+    float s, c;
+    sincosf(__fmul_rn(__fmul_rn(-6.283185307179586f, fx), sx), &s, &c);
+    ex = make_float2(c, s);
+  }
+  __syncthreads();
+  fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+  __syncthreads();  // every thread has taken its last-pass inputs out of shared memory
+  const float2* py = phase_y + (long)f * N;
+#pragma unroll
+  for (int g = 0; g < P::Last::G; ++g)
+#pragma unroll
+    for (int r = 0; r < P::Last::R; ++r) {
+      const int ky = P::Last::out_index(j, g, r);
+      const float2 val = cmul(P::Last::result(v, g, r), cmul(__ldg(py + ky), ex));
+      myseq[fft2::pad_idx(ky)] = make_float2(val.y, val.x);  // swapped: the next forward FFT is the inverse
+    }
+  __syncthreads();
+  P::First::load(myseq, j, v);
+  __syncthreads();
+  fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+  if (!active) return;
+#pragma unroll
+  for (int g = 0; g < P::Last::G; ++g)
+#pragma unroll
+    for (int r = 0; r < P::Last::R; ++r) {
+      const float2 val = P::Last::result(v, g, r);
+      col[(long)P::Last::out_index(j, g, r) * KX] = make_float2(val.y, val.x);
+    }
+}
+
+// phase_y[f][ky] for all frames (tiny)
+__global__ void shift_phase_y_kernel(const float* __restrict__ field, int T, int NY, float sign, float2* __restrict__ phase_y) {
+  const int ky = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (ky >= NY) return;
+  const float sy = sign * __ldg(field + f);
+  const float fy = __fmul_rn((float)(ky < (NY + 1) / 2 ? ky : ky - NY), (float)(1.0 / (double)NY));
+  float s, c;
+  sincosf(__fmul_rn(__fmul_rn(-6.283185307179586f, fy), sy), &s, &c);
+  phase_y[(long)f * NY + ky] = make_float2(c, s);
+}

@@ -121,6 +121,12 @@ class LocalMotionProblem:
         self.workspace = torch.empty(((ws_bytes + 7) // 8,), dtype=torch.float64, device=dev)
         self.loss = torch.zeros((1,), dtype=torch.float64, device=dev)
         self.grad_eval = torch.empty((t, self.g, 2), dtype=torch.float32, device=dev)
+        # everything an iteration touches is allocated once: a captured step allocates nothing
+        self.eval_new = torch.empty((t, self.g, 2), dtype=torch.float32, device=dev)
+        self.grad = torch.empty((2, *self.resolution), dtype=torch.float32, device=dev)
+        n_ws = query("tmc_spline_workspace_floats", 2, *self.resolution)
+        self.ws_eval = torch.empty((n_ws,), dtype=torch.float32, device=dev)
+        self.ws_back = torch.empty((n_ws,), dtype=torch.float32, device=dev)
 
     def patch_scales(self, batches) -> torch.Tensor:
         """Per-patch weight reproducing the reference's per-mini-batch ``mean`` (quirk Q11): the
@@ -140,13 +146,15 @@ class LocalMotionProblem:
         """Sum over mini-batches of the batch losses (device float64 (1,)) and d/d new_data.
 
         ``scale`` is (G,) or, with ``iteration`` (device int32 counter; mse / cc only), (n, G)."""
-        eval_new = _ops.spline_eval(new_data, self.kind, self.centres_norm)
+        eval_new = _ops.spline_eval(new_data, self.kind, self.centres_norm, out=self.eval_new.view(-1, 2), ws=self.ws_eval)
         p = self.plan
         with torch.cuda.device(self.dev):
             call("tmc_local_loss_grad", ptr(self.spec), ptr(self.norms), ptr(eval_new), ptr(self.eval_base), ptr(scale),
                  ptr(iteration), self.g, self.t, self.tp, self.ph, self.pw, p.ky, p.kx, p.ky_start, self.px, self.loss_type,
                  ptr(self.loss), ptr(self.grad_eval), ptr(self.workspace), stream_ptr(self.dev))
-        grad = _ops.spline_eval_backward((2, *self.resolution), self.kind, self.centres_norm, self.grad_eval)
+        grad = _ops.spline_eval_backward(
+            (2, *self.resolution), self.kind, self.centres_norm, self.grad_eval, out=self.grad, ws=self.ws_back
+        )
         return self.loss, grad
 
 
@@ -155,6 +163,9 @@ def _graph_capable(optimizer: torch.optim.Optimizer) -> bool:
     if isinstance(optimizer, torch.optim.SGD):
         return True
     return bool(optimizer.defaults.get("capturable", False))
+
+
+_GRAPH_POOL = None
 
 
 def _run_captured(one_step, n_iterations: int, dev: torch.device) -> int:
@@ -167,13 +178,16 @@ def _run_captured(one_step, n_iterations: int, dev: torch.device) -> int:
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(main)
     graph = torch.cuda.CUDAGraph()
+    global _GRAPH_POOL
+    if _GRAPH_POOL is None:
+        _GRAPH_POOL = torch.cuda.graph_pool_handle()  # one pool for every capture: no cudaMalloc/cudaFree churn
     with torch.cuda.stream(side):
         one_step(0)  # lazily creates the optimiser state outside the capture
         # capture_begin / capture_end directly: the torch.cuda.graph() context manager would
         # synchronise the device and empty the caching allocator (every later call would then pay
         # cudaMalloc for its multi-GB workspaces again)
         try:
-            graph.capture_begin()
+            graph.capture_begin(pool=_GRAPH_POOL)
             try:
                 one_step(1)
             finally:
