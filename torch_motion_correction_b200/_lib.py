@@ -118,6 +118,8 @@ def ptr(t):
 TIMING: dict | None = None
 #: number of C-ABI compute calls issued (bench.py reports kernels launched through them)
 CALLS: dict = {}
+#: kernels launched by CUDA-graph replays of captured library calls (not visible to tmc_launch_count)
+GRAPH_LAUNCHES = 0
 
 
 def call(name: str, *args):

@@ -165,9 +165,6 @@ def _graph_capable(optimizer: torch.optim.Optimizer) -> bool:
     return bool(optimizer.defaults.get("capturable", False))
 
 
-_GRAPH_POOL = None
-
-
 def _run_captured(one_step, n_iterations: int, dev: torch.device) -> int:
     """Run ``n_iterations`` optimiser steps as one eager warm-up + CUDA-graph replays (launch-bound
     inner loop: ~15 tiny kernels per step).  Returns the number of steps performed (0 if capture
@@ -178,21 +175,26 @@ def _run_captured(one_step, n_iterations: int, dev: torch.device) -> int:
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(main)
     graph = torch.cuda.CUDAGraph()
-    global _GRAPH_POOL
-    if _GRAPH_POOL is None:
-        _GRAPH_POOL = torch.cuda.graph_pool_handle()  # one pool for every capture: no cudaMalloc/cudaFree churn
     with torch.cuda.stream(side):
         one_step(0)  # lazily creates the optimiser state outside the capture
         # capture_begin / capture_end directly: the torch.cuda.graph() context manager would
         # synchronise the device and empty the caching allocator (every later call would then pay
         # cudaMalloc for its multi-GB workspaces again)
         try:
-            graph.capture_begin(pool=_GRAPH_POOL)
+            launches_before = query("tmc_launch_count")
+            graph.capture_begin()  # the step allocates nothing (buffers live in LocalMotionProblem)
             try:
                 one_step(1)
             finally:
                 graph.capture_end()
-        except Exception:  # pragma: no cover - capture refused: finish eagerly
+            kernels_per_step = query("tmc_launch_count") - launches_before
+        except Exception as exc:  # pragma: no cover - capture refused: finish eagerly
+            import os
+            import warnings
+
+            if os.environ.get("TMC_DEBUG"):
+                raise
+            warnings.warn(f"CUDA-graph capture of the optimiser step failed ({exc}); running eagerly", stacklevel=2)
             main.wait_stream(side)
             return 1
     main.wait_stream(side)
@@ -204,6 +206,7 @@ def _run_captured(one_step, n_iterations: int, dev: torch.device) -> int:
         start.record()
     for _ in range(n_iterations - 1):
         graph.replay()
+    _lib.GRAPH_LAUNCHES += kernels_per_step * (n_iterations - 2)  # the capture pass itself was already counted
     if timing is not None:
         end.record()
         timing.setdefault("graph:optimiser_steps", []).append((start, end))
