@@ -47,4 +47,5 @@ for _name in (
 ):
     _mod = __import__(f"torch_motion_correction_b200.{_name}", fromlist=["_"])
     _sys.modules[f"{__name__}.{_name}"] = _mod
-    globals()[_name] = _mod
+    # like the reference: the FUNCTION correct_motion shadows the submodule of the same name
+    globals().setdefault(_name, _mod)

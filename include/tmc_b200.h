@@ -74,6 +74,13 @@ long tmc_warp_workspace_floats(int t, int w, int lh);
 int tmc_warp_lattice(const float* image, int t, int h, int w, const float* lattice, int lh, int lw, float pixel_spacing,
                      const float* mean_std, float* out_stack, float* out_sum, int accumulate_sum, float* workspace,
                      tmc_stream_t stream);
+/* backward of tmc_warp_lattice w.r.t. the lattice (correct_motion_two_grids, grad=True; correct_motion.py:256-317):
+ * grad_out (t,h,w) -> grad_lattice (t,2,lh,lw).  workspace: 2 * tmc_warp_workspace_floats(t, w, lh) floats. */
+int tmc_warp_lattice_backward(const float* image, int t, int h, int w, const float* lattice, int lh, int lw,
+                              float pixel_spacing, const float* grad_out, float* grad_lattice, float* workspace,
+                              tmc_stream_t stream);
+/* (t, y, x) in [0,1]^3 of every lattice node, (t, lh, lw, 3): the points tmc_spline_lattice evaluates */
+int tmc_lattice_tyx(int t, int frame_offset, int total_frames, int lh, int lw, float* tyx, tmc_stream_t stream);
 /* get_pixel_shifts: (2, lh, lw) lattice -> (h, w, 2) px shifts */
 int tmc_pixel_shifts(const float* lattice, int lh, int lw, int h, int w, float pixel_spacing, float* out,
                      tmc_stream_t stream);

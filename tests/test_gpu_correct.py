@@ -149,3 +149,25 @@ def test_frame_split_sum_matches_whole(dev):
     assert rel_l2(part, whole) <= 1e-6
     want = rp.correct_motion(movie, field.cpu(), 1.1, "bspline").sum(dim=0)
     assert rel_l2(whole, want) <= REL_L2
+
+
+@pytest.mark.parametrize("grid_type", ["catmull_rom", "bspline"])
+def test_two_grids_gradient_matches_autograd(dev, grid_type):
+    """d(sum w * corrected) / d(new grid coefficients): CUDA backward kernels vs autograd through the oracle."""
+    from torch_motion_correction_b200.spline_grids import CubicBSplineGrid3d, CubicCatmullRomGrid3d
+
+    movie, _ = rp.synthetic_movie(4, 96, 80, seed=6, noise=0.2, sigma_f=0.05)
+    g = torch.Generator().manual_seed(12)
+    new = (torch.randn((2, 3, 3, 2), generator=g) * 1.5).requires_grad_(True)
+    base = torch.randn((2, 3, 3, 2), generator=g) * 1.5
+    weights = torch.randn(movie.shape, generator=g)
+    out = rp.correct_motion_two_grids(movie, new, base, 1.2, grid_type)
+    (out * weights).sum().backward()
+    cls = CubicBSplineGrid3d if grid_type == "bspline" else CubicCatmullRomGrid3d
+    new_mod = cls.from_grid_data(new.detach()).to(dev)
+    base_mod = cls.from_grid_data(base).to(dev)
+    got = tmc.correct_motion_two_grids(movie.to(dev), new_mod, base_mod, 1.2, grad=True)
+    assert got.requires_grad and rel_l2(got.detach(), out.detach()) <= REL_L2
+    (got * weights.to(dev)).sum().backward()
+    grad = new_mod.data.grad.cpu()
+    assert float((grad - new.grad).abs().max()) <= 2e-3 * float(new.grad.abs().max())

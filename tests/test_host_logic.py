@@ -128,3 +128,30 @@ def test_no_cpu_fallback():
         tmc.correct_motion(torch.zeros((2, 8, 8)), torch.zeros((2, 2, 1, 1)), 1.0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         tmc.estimate_global_motion(torch.zeros((2, 16, 16)), 1.0)
+
+
+def test_compat_alias_exposes_the_reference_names():
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "compat"))
+    for name in [n for n in sys.modules if n == "torch_motion_correction" or n.startswith("torch_motion_correction.")]:
+        del sys.modules[name]
+    try:
+        import torch_motion_correction as mod
+
+        # reference src/torch_motion_correction/__init__.py:32-44
+        assert sorted(mod.__all__) == sorted([
+            "estimate_local_motion", "correct_motion", "correct_motion_two_grids", "correct_motion_fast", "correct_motion_slow",
+            "get_pixel_shifts", "evaluate_deformation_field", "estimate_global_motion",
+            "estimate_motion_cross_correlation_patches", "write_deformation_field_to_csv", "read_deformation_field_from_csv",
+        ])
+        assert all(callable(getattr(mod, n)) for n in mod.__all__)
+        from torch_motion_correction.correct_motion import correct_motion, correct_motion_fast  # noqa: F401
+        from torch_motion_correction.estimate_motion_optimizer import estimate_local_motion  # noqa: F401
+        from torch_motion_correction.estimate_motion_xc import estimate_global_motion  # noqa: F401
+    finally:
+        sys.path.remove(os.path.join(root, "compat"))
+        for name in [n for n in sys.modules if n == "torch_motion_correction" or n.startswith("torch_motion_correction.")]:
+            del sys.modules[name]

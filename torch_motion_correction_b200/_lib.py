@@ -40,6 +40,8 @@ _SIGNATURES = {
     "tmc_warp_workspace_floats": (L, [I, I, I]),
     "tmc_warp_lattice": (I, [P, I, I, I, P, I, I, F, P, P, P, I, P, P]),
     "tmc_pixel_shifts": (I, [P, I, I, I, I, F, P, P]),
+    "tmc_warp_lattice_backward": (I, [P, I, I, I, P, I, I, F, P, P, P, P]),
+    "tmc_lattice_tyx": (I, [I, I, I, I, I, P, P]),
     "tmc_warp_dense_shifts": (I, [P, I, I, I, P, P, P]),
     "tmc_pixel_tyx": (I, [I, I, I, I, I, P, P]),
     "tmc_fft_supported_length": (I, [I]),

@@ -254,6 +254,109 @@ warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const 
   }
 }
 
+// ---- backward of the warp w.r.t. the shift lattice (correct_motion_two_grids, grad=True) ------------------
+// d out / d shift = (1 / px) * sum_ab w'_a(t_y) w_b(t_x) tap_ab   (ATen grid_sampler_2d_backward, bicubic:
+// gradient flows through the cubic coefficients only; clamped taps and the outside-zero mask carry none)
+
+__device__ __forceinline__ void cubic_weights_grad(float t, float (&w)[4]) {
+  // true derivatives d w_k / d t of cubic_weights (ATen's get_cubic_coefficients_grad stores the negatives
+  // and subtracts them)
+  float x = t + 1.0f;
+  w[0] = (3.0f * kA * x - 10.0f * kA) * x + 8.0f * kA;
+  x = t;
+  w[1] = (3.0f * (kA + 2.0f) * x - 2.0f * (kA + 3.0f)) * x;
+  x = 1.0f - t;
+  w[2] = -(3.0f * (kA + 2.0f) * x - 2.0f * (kA + 3.0f)) * x;
+  x = 2.0f - t;
+  w[3] = -((3.0f * kA * x - 10.0f * kA) * x + 8.0f * kA);
+}
+
+// grad_rx[f][c][a][x] += grad_out[f][y][x] * d out / d s_c * wy_k(y)   for the 4 lattice rows a = jy_k(y)
+__global__ void warp_lattice_backward_kernel(const float* __restrict__ image, int T, int H, int W, const float* __restrict__ rx,
+                                             int lh, float pixel_spacing, const float* __restrict__ grad_out,
+                                             float* __restrict__ grad_rx) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= W) return;
+  const LatticeAxis ly = lattice_axis(y, H, lh);
+  const RoundTrip rty = make_round_trip(H), rtx = make_round_trip(W);
+  const float inv_px = 1.0f / pixel_spacing;
+  const size_t rx_plane = (size_t)lh * W;
+  for (int f = 0; f < T; ++f) {
+    const float go = grad_out[((size_t)f * H + y) * W + x];
+    if (go == 0.f) continue;
+    const float* Ry = rx + (size_t)f * 2 * rx_plane + x;
+    const float* Rx = Ry + rx_plane;
+    float sy = 0.f, sx = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sy = fmaf(ly.w[k], __ldg(Ry + (size_t)ly.j[k] * W), sy);
+      sx = fmaf(ly.w[k], __ldg(Rx + (size_t)ly.j[k] * W), sx);
+    }
+    const float cy = __fadd_rn((float)y, __fmul_rn(sy, inv_px));
+    const float cx = __fadd_rn((float)x, __fmul_rn(sx, inv_px));
+    if (!(cy >= 0.0f && cy <= (float)(H - 1) && cx >= 0.0f && cx <= (float)(W - 1))) continue;
+    const float uy = round_trip(cy, rty), ux = round_trip(cx, rtx);
+    const float fy = floorf(uy), fx = floorf(ux);
+    float ay[4], ax[4], day[4], dax[4];
+    cubic_weights(uy - fy, ay);
+    cubic_weights(ux - fx, ax);
+    cubic_weights_grad(uy - fy, day);
+    cubic_weights_grad(ux - fx, dax);
+    const int iy = (int)fy, ix = (int)fx;
+    const float* frame = image + (size_t)f * H * W;
+    float dvy = 0.f, dvx = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float* p = frame + (size_t)min(max(iy - 1 + a, 0), H - 1) * W;
+      float row = 0.f, drow = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const float tap = __ldg(p + min(max(ix - 1 + b, 0), W - 1));
+        row = fmaf(ax[b], tap, row);
+        drow = fmaf(dax[b], tap, drow);
+      }
+      dvy = fmaf(day[a], row, dvy);
+      dvx = fmaf(ay[a], drow, dvx);
+    }
+    const float gy = go * dvy * inv_px, gx = go * dvx * inv_px;
+    float* Gy = grad_rx + (size_t)f * 2 * rx_plane + x;
+    float* Gx = Gy + rx_plane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(Gy + (size_t)ly.j[k] * W, gy * ly.w[k]);
+      atomicAdd(Gx + (size_t)ly.j[k] * W, gx * ly.w[k]);
+    }
+  }
+}
+
+// grad_lattice[r][jx_b(x)] += wx_b(x) * grad_rx[r][x]   (transpose of lattice_xinterp_kernel)
+__global__ void lattice_xinterp_backward_kernel(const float* __restrict__ grad_rx, long rows, int lw, int W,
+                                                float* __restrict__ grad_lattice) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const LatticeAxis lx = lattice_axis(x, W, lw);
+  for (long r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float g = grad_rx[r * W + x];
+    if (g == 0.f) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) atomicAdd(grad_lattice + r * lw + lx.j[b], g * lx.w[b]);
+  }
+}
+
+// (t, y, x) in [0,1]^3 of every lattice node, (T, lh, lw, 3), matching spline_lattice_kernel
+__global__ void lattice_tyx_kernel(int T, int frame_offset, int total_frames, int lh, int lw, float* __restrict__ tyx) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)T * lh * lw) return;
+  const int ix = i % lw;
+  const long r = i / lw;
+  const int iy = r % lh;
+  const int f = r / lh;
+  tyx[3 * i] = linspace01(f + frame_offset, total_frames);
+  tyx[3 * i + 1] = linspace01(iy, lh);
+  tyx[3 * i + 2] = linspace01(ix, lw);
+}
+
 // get_pixel_shifts (correct_motion.py:132-185): (h, w, 2) px shifts of one lattice (2, lh, lw)
 __global__ void pixel_shifts_kernel(const float* __restrict__ lattice, int lh, int lw, int H, int W, float pixel_spacing,
                                     float* __restrict__ out) {
@@ -372,5 +475,36 @@ TMC_API int tmc_pixel_tyx(int h, int w, int t, int frame_offset, int total_frame
   dim3 grid(tmc_div_up(w, 128), h, t);
   pixel_tyx_kernel<<<grid, 128, 0, stream>>>(h, w, t, frame_offset, total_frames, tyx); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_pixel_tyx");
+  return TMC_OK;
+}
+
+// Backward of tmc_warp_lattice w.r.t. the lattice: grad_out (t,h,w) -> grad_lattice (t,2,lh,lw) (zeroed here).
+// workspace: 2 * tmc_warp_workspace_floats(t, w, lh) floats.
+TMC_API int tmc_warp_lattice_backward(const float* image, int t, int h, int w, const float* lattice, int lh, int lw,
+                                      float pixel_spacing, const float* grad_out, float* grad_lattice, float* workspace,
+                                      cudaStream_t stream) {
+  TMC_CHECK_ARG(image && lattice && grad_out && grad_lattice && workspace, "warp_lattice_backward: null pointer");
+  TMC_CHECK_ARG(t >= 1 && h >= 2 && w >= 2 && lh >= 1 && lw >= 1 && pixel_spacing > 0.f, "warp_lattice_backward: bad arguments");
+  const long rows = (long)t * 2 * lh;
+  float* rx = workspace;
+  float* grad_rx = workspace + rows * w;
+  dim3 g1(tmc_div_up(w, 128), (unsigned)(rows < 4096 ? rows : 4096));
+  lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, rx); tmc_count_launch();
+  TMC_CUDA(cudaMemsetAsync(grad_rx, 0, sizeof(float) * (size_t)rows * w, stream));
+  TMC_CUDA(cudaMemsetAsync(grad_lattice, 0, sizeof(float) * (size_t)rows * lw, stream));
+  dim3 g2(tmc_div_up(w, 128), h);
+  warp_lattice_backward_kernel<<<g2, 128, 0, stream>>>(image, t, h, w, rx, lh, pixel_spacing, grad_out, grad_rx); tmc_count_launch();
+  lattice_xinterp_backward_kernel<<<g1, 128, 0, stream>>>(grad_rx, rows, lw, w, grad_lattice); tmc_count_launch();
+  TMC_CHECK_LAUNCH("tmc_warp_lattice_backward");
+  return TMC_OK;
+}
+
+// normalised (t, y, x) of every node of the (t, lh, lw) lattice: tyx (t, lh, lw, 3)
+TMC_API int tmc_lattice_tyx(int t, int frame_offset, int total_frames, int lh, int lw, float* tyx, cudaStream_t stream) {
+  TMC_CHECK_ARG(tyx && t >= 1 && lh >= 1 && lw >= 1 && frame_offset >= 0 && frame_offset + t <= total_frames,
+                "lattice_tyx: bad arguments");
+  const long n = (long)t * lh * lw;
+  lattice_tyx_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(t, frame_offset, total_frames, lh, lw, tyx); tmc_count_launch();
+  TMC_CHECK_LAUNCH("tmc_lattice_tyx");
   return TMC_OK;
 }
