@@ -232,10 +232,11 @@ __global__ void phase_tables_kernel(const float* __restrict__ shifts, int T, Ban
   }
 }
 
-constexpr int kFusedBins = 4;  // bins per thread (amortises the per-frame warp reductions)
-
 // q[g] += sum_f w |Sigma|^2 ; grad[g][t][:] += -2 b sum_f w (c f) Im(S_t conj Sigma)
-__global__ void __launch_bounds__(kOptThreads)
+// kFusedBins bins per thread amortise the per-frame warp reductions; UNROLL frames in flight hide load latency;
+// MINB CTAs/SM caps the registers (the first version ran at 168 registers, 17 % occupancy: profiles/r01_final_*)
+template <int kFusedBins, int UNROLL, int MINB>
+__global__ void __launch_bounds__(kOptThreads, MINB)
 loss_fused_kernel(const float2* __restrict__ spec, const float2* __restrict__ E, const float* __restrict__ patch_scale,
                   const int* __restrict__ iter_ptr, int G, int T, int Tp, BandGeom geom, int loss_type, int ph, int pw,
                   double* __restrict__ q, float* __restrict__ grad) {
@@ -270,7 +271,7 @@ loss_fused_kernel(const float2* __restrict__ spec, const float2* __restrict__ E,
   }
   const float2* sp = spec + (long)g * Tp * bins;
   const float2* Eg = E + (long)g * T * (geom.KY + geom.KX);
-#pragma unroll 4
+#pragma unroll UNROLL
   for (int t = 0; t < T; ++t) {
     const float2* Et = Eg + (long)t * (geom.KY + geom.KX);
 #pragma unroll
@@ -287,7 +288,7 @@ loss_fused_kernel(const float2* __restrict__ spec, const float2* __restrict__ E,
     if ((threadIdx.x & 31) == 0) atomicAdd(q + g, v);
   }
   __syncthreads();  // acc zeroed
-#pragma unroll 2
+#pragma unroll UNROLL
   for (int t = 0; t < T; ++t) {
     const float2* Et = Eg + (long)t * (geom.KY + geom.KX);
     float gy = 0.f, gx = 0.f;
@@ -450,9 +451,11 @@ TMC_API int tmc_local_loss_grad(const void* spec, const double* norms, const flo
     phase_tables_kernel<<<g * t, 128, 0, stream>>>(shifts, t, geom, E); tmc_count_launch();
     // (a variant that kept all frames of a bin tile in shared memory was measured 20-75 % slower: occupancy)
     {
-      dim3 fgrid(tmc_div_up(bins, kOptThreads * kFusedBins), g);
-      loss_fused_kernel<<<fgrid, kOptThreads, sizeof(float) * 2 * t, stream>>>((const float2*)spec, E, patch_scale, iteration, g, t,
-                                                                             tp, geom, loss_type, ny, nx, q, grad_shifts);
+      // 4 bins per thread, 4 frames in flight: measured fastest (ILP beats occupancy here; the 64-register
+      // variants with 2-8 CTAs/SM were 10-45 % slower)
+      dim3 fgrid(tmc_div_up(bins, kOptThreads * 4), g);
+      loss_fused_kernel<4, 4, 1><<<fgrid, kOptThreads, sizeof(float) * 2 * t, stream>>>(
+          (const float2*)spec, E, patch_scale, iteration, g, t, tp, geom, loss_type, ny, nx, q, grad_shifts);
     }
     tmc_count_launch();
     loss_fused_finish_kernel<<<tmc_div_up(n > g ? n : g, 128), 128, 0, stream>>>(norms, q, patch_scale, iteration, g, t, ny, nx,
