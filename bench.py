@@ -97,7 +97,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
         except OSError:
@@ -306,12 +306,14 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput ------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step(movie)
-    barrier()
+    # the clock sampler (nvidia-smi) starts before the warm-up: its start-up (NVML init) must not land inside
+    # the timed region; it samples clocks / throttle reasons under load through warm-up and timed steps
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(movie)
+    barrier()
     _lib.TIMING = {}
     calls_before = dict(_lib.CALLS)
     launches_before = _lib.query("tmc_launch_count") + _lib.GRAPH_LAUNCHES

@@ -43,3 +43,27 @@ def grid_kind(grid_type: str) -> int:
         return GRID_KINDS[grid_type]
     except KeyError:
         raise ValueError(f"Invalid grid type: {grid_type}. Must be 'catmull_rom' or 'bspline'.") from None
+
+
+_device_cache: dict = {}
+
+
+def cached_device_tensor(key, build, device: torch.device) -> torch.Tensor:
+    """Small planning tensors (job lists, schedules, patch centres) are pure functions of the call
+    geometry: build them once per device and geometry instead of paying a host-blocking pageable
+    H2D copy in the middle of every call.  The tensors must be treated as read-only."""
+    full_key = (device.type, device.index, key)
+    hit = _device_cache.get(full_key)
+    if hit is None:
+        if len(_device_cache) > 256:
+            _device_cache.clear()
+        hit = build().to(device)
+        _device_cache[full_key] = hit
+    return hit
+
+
+def to_device_async(host_tensor: torch.Tensor, device: torch.device) -> torch.Tensor:
+    """H2D copy through pinned staging memory that does not block the host."""
+    staged = torch.empty(host_tensor.shape, dtype=host_tensor.dtype, pin_memory=True)
+    staged.copy_(host_tensor)
+    return staged.to(device, non_blocking=True)

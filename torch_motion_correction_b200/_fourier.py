@@ -192,11 +192,16 @@ class BandPlan:
 
 def frame_pair_jobs(t: int, device: torch.device, frame_offset: int = 0) -> torch.Tensor:
     """Whole-frame jobs packing frames (2i, 2i+1): plane index == frame index."""
-    rows = []
-    for i in range(0, t, 2):
-        fb = i + 1 if i + 1 < t else -1
-        rows.append([frame_offset + i, 1, (frame_offset + fb) if fb >= 0 else -1, 1, 0, 0])
-    return torch.tensor(rows, dtype=torch.int32).to(device, non_blocking=True)
+    from ._common import cached_device_tensor
+
+    def build():
+        rows = []
+        for i in range(0, t, 2):
+            fb = i + 1 if i + 1 < t else -1
+            rows.append([frame_offset + i, 1, (frame_offset + fb) if fb >= 0 else -1, 1, 0, 0])
+        return torch.tensor(rows, dtype=torch.int32)
+
+    return cached_device_tensor(("frame_pair_jobs", t, frame_offset), build, device)
 
 
 def pair_products(spec: torch.Tensor, ref_plane: torch.Tensor, cur_plane: torch.Tensor, plane_elems: int) -> torch.Tensor:

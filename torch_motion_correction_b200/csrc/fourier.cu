@@ -800,9 +800,9 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
     if constexpr (use_fast_path<MM, BB>()) {
-      if (int e = enable_smem(rows_inverse_argmax_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
+      if (int e = enable_smem(rows_inverse_argmax_p2<MM>, rows_inverse_smem_bytes<MM>())) return e;
       dim3 grid(nparts, nitems);
-      rows_inverse_argmax_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
+      rows_inverse_argmax_p2<MM><<<grid, fft2::kThreads, rows_inverse_smem_bytes<MM>(), stream>>>(
           (const float2*)tmp, ny, kx_count, px.tw, (PeakCandidate*)partial); tmc_count_launch();
       return TMC_OK;
     }
@@ -847,9 +847,9 @@ TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const 
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
     if constexpr (use_fast_path<MM, BB>()) {
-      if (int e = enable_smem(rows_inverse_store_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
+      if (int e = enable_smem(rows_inverse_store_p2<MM>, rows_inverse_smem_bytes<MM>())) return e;
       dim3 grid(tmc_div_up(ny, rows_per_cta_inverse<MM>()), nitems);
-      rows_inverse_store_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
+      rows_inverse_store_p2<MM><<<grid, fft2::kThreads, rows_inverse_smem_bytes<MM>(), stream>>>(
           (const float2*)tmp, ny, kx, px.tw, 1.0f / ((float)nx * (float)ny), out); tmc_count_launch();
       return TMC_OK;
     }
@@ -927,9 +927,9 @@ TMC_API int tmc_fourier_shift_frames(const float* image, int t, int ny, int nx, 
   rc = dispatch_fft(nx, "fourier_shift_frames", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     if constexpr (use_fast_path<MM, decltype(BLU)::value>()) {
-      if (int e = enable_smem(rows_inverse_store_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
+      if (int e = enable_smem(rows_inverse_store_p2<MM>, rows_inverse_smem_bytes<MM>())) return e;
       dim3 grid(tmc_div_up(ny, rows_per_cta_inverse<MM>()), t);
-      rows_inverse_store_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
+      rows_inverse_store_p2<MM><<<grid, fft2::kThreads, rows_inverse_smem_bytes<MM>(), stream>>>(
           (const float2*)tmp, ny, kx, px.tw, 1.0f / ((float)nx * (float)ny), out); tmc_count_launch();
     }
     return TMC_OK;

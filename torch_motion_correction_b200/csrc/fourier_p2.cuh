@@ -210,22 +210,16 @@ cols_inverse_p2(const float2* __restrict__ in, int KX, int KY, int ky_start, con
     }
 }
 
-// packed, re/im-swapped spectrum entry i of the row pair (rowa -> real part, rowb -> imaginary part)
-template <int N>
-__device__ __forceinline__ float2 c2r_pair_entry(const float2* __restrict__ rowa, const float2* __restrict__ rowb, int KX, int i) {
-  if (i < KX) {
-    const float2 ca = rowa[i];
-    const float2 cb = rowb ? rowb[i] : make_float2(0.f, 0.f);
-    if (i == 0 || 2 * i == N) return make_float2(cb.x, ca.x);
-    return make_float2(ca.y + cb.x, ca.x - cb.y);
-  }
-  const int k = N - i;
-  if (k < KX && 2 * k != N) {
-    const float2 ca = rowa[k];
-    const float2 cb = rowb ? rowb[k] : make_float2(0.f, 0.f);
-    return make_float2(cb.x - ca.y, ca.x + cb.y);
-  }
-  return make_float2(0.f, 0.f);
+// ---- inverse rows (complex-to-real, two rows per transform) ------------------------------------------------
+//
+// Entry i of the packed spectrum of rows (ya -> real part, yb -> imaginary part) is built from
+// Ca = rowa[k], Cb = rowb[k] with k = i (i < KX) or k = N - i (mirrored, conjugated); everything else is
+// zero.  The (Ca, Cb) pairs of the NEXT batch of row pairs are prefetched with cp.async into per-thread
+// shared-memory slots while the current batch is transformed.
+
+__device__ __forceinline__ void cp_async_f32x2(float2* smem_dst, const float2* gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(gmem_src));
 }
 
 constexpr int kRowIters = 4;  // row-pair batches per CTA in the inverse row kernels
@@ -235,55 +229,117 @@ __host__ __device__ constexpr int rows_per_cta_inverse() {
   return 2 * fft2::Cfg<N>::B * kRowIters;
 }
 
+template <int N>
+constexpr size_t rows_inverse_smem_bytes() {
+  return fft2::Cfg<N>::smem_bytes + 2ull * fft2::Cfg<N>::B * N * sizeof(float2);
+}
+
+// k index (into the band-limited rows) feeding packed entry i, or -1 if the entry is zero
+template <int N>
+__device__ __forceinline__ int c2r_source_index(int i, int KX) {
+  if (i < KX) return i;
+  const int k = N - i;
+  return (k < KX && 2 * k != N) ? k : -1;
+}
+
+template <int N>
+__device__ __forceinline__ float2 c2r_pack(float2 ca, float2 cb, int i, int KX) {
+  if (i < KX) {
+    if (i == 0 || 2 * i == N) return make_float2(cb.x, ca.x);  // c2r ignores Im of the DC / Nyquist bins
+    return make_float2(ca.y + cb.x, ca.x - cb.y);              // Z[k] = Ca + i Cb, stored (im, re)
+  }
+  return make_float2(cb.x - ca.y, ca.x + cb.y);                // Z[N-k] = conj(Ca) + i conj(Cb), stored (im, re)
+}
+
+// Shared driver of the two inverse row kernels: calls consume(ya, has_b, v) with the last-pass outputs of
+// every row pair of this CTA (v swapped: .y = row ya, .x = row ya + 1).
+template <int N, typename Consume>
+__device__ __forceinline__ void rows_inverse_driver(const float2* __restrict__ src, int NY, int KX,
+                                                    const float2* __restrict__ tw, float2* smem, Consume&& consume) {
+  using C = fft2::Cfg<N>;
+  using P = fft2::Plan<N>;
+  const fft2::Smem<N> sm(smem);
+  fft2::load_twiddles<N>(sm, tw);
+  const int seq = threadIdx.x / C::TPS, j = threadIdx.x % C::TPS;
+  float2* myseq = sm.data + seq * C::STRIDE;
+  float2* stage_a = smem + C::B * C::STRIDE + 64 + C::TW_HI;
+  float2* stage_b = stage_a + C::B * N;
+  auto row_of = [&](int it) { return (int)blockIdx.x * rows_per_cta_inverse<N>() + (it * C::B + seq) * 2; };
+  auto prefetch = [&](int it) {
+    const int ya = row_of(it);
+    if (ya >= NY) return;
+    const float2* rowa = src + (long)ya * KX;
+    const bool has_b = ya + 1 < NY;
+#pragma unroll
+    for (int e = 0; e < C::VPT; ++e) {
+      constexpr int R = P::First::R;
+      // whole blocks of entries are zero for a band-limited spectrum: warp-uniform skip
+      const int lo = (e / R) * C::TPS + (e % R) * P::First::NBR;
+      if (lo >= KX && lo + C::TPS <= N - KX + 1) continue;
+      const int k = c2r_source_index<N>(P::First::in_index(j, e / R, e % R), KX);
+      if (k >= 0) {
+        const int slot = e * fft2::kThreads + threadIdx.x;
+        cp_async_f32x2(stage_a + slot, rowa + k);
+        if (has_b) cp_async_f32x2(stage_b + slot, rowa + KX + k);
+      }
+    }
+  };
+  prefetch(0);
+  __syncthreads();
+  for (int it = 0; it < kRowIters; ++it) {
+    const int ya = row_of(it);
+    const bool active = ya < NY;
+    const bool has_b = ya + 1 < NY;
+    cp_async_commit_and_wait();
+    float2 v[C::VPT];
+#pragma unroll
+    for (int e = 0; e < C::VPT; ++e) {
+      constexpr int R = P::First::R;
+      float2 z = make_float2(0.f, 0.f);
+      const int lo = (e / R) * C::TPS + (e % R) * P::First::NBR;
+      if (active && !(lo >= KX && lo + C::TPS <= N - KX + 1)) {
+        const int i = P::First::in_index(j, e / R, e % R);
+        if (c2r_source_index<N>(i, KX) >= 0) {
+          const int slot = e * fft2::kThreads + threadIdx.x;
+          z = c2r_pack<N>(stage_a[slot], has_b ? stage_b[slot] : make_float2(0.f, 0.f), i, KX);
+        }
+      }
+      v[e] = z;
+    }
+    if (it + 1 < kRowIters) prefetch(it + 1);
+    fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+    if (active) consume(ya, has_b, j, v);
+    __syncthreads();
+  }
+}
+
 // ---- inverse rows + argmax: tmp[item][y][kx] -> partial[item][cta] ------------------------------------
 template <int N>
 __global__ void __launch_bounds__(fft2::kThreads)
 rows_inverse_argmax_p2(const float2* __restrict__ tmp, int NY, int KX, const float2* __restrict__ tw,
                        PeakCandidate* __restrict__ partial) {
-  using C = fft2::Cfg<N>;
   using P = fft2::Plan<N>;
   extern __shared__ float2 smem[];
-  const fft2::Smem<N> sm(smem);
-  fft2::load_twiddles<N>(sm, tw);
-  const int seq = threadIdx.x / C::TPS, j = threadIdx.x % C::TPS;
-  float2* myseq = sm.data + seq * C::STRIDE;
   const long item = blockIdx.y;
-  const float2* src = tmp + item * NY * KX;
   float best = -INFINITY;
   int best_idx = 0x7fffffff;
-  __syncthreads();
-  for (int it = 0; it < kRowIters; ++it) {
-    const int ya = blockIdx.x * rows_per_cta_inverse<N>() + (it * C::B + seq) * 2;
-    const bool active = ya < NY;
-    const float2* rowa = src + (long)ya * KX;
-    const float2* rowb = (ya + 1 < NY) ? rowa + KX : nullptr;
-    float2 v[C::VPT];
+  rows_inverse_driver<N>(tmp + item * NY * KX, NY, KX, tw, smem, [&](int ya, bool has_b, int j, const float2* v) {
 #pragma unroll
-    for (int g = 0; g < P::First::G; ++g)
+    for (int g = 0; g < P::Last::G; ++g)
 #pragma unroll
-      for (int r = 0; r < P::First::R; ++r)
-        v[g * P::First::R + r] =
-            active ? c2r_pair_entry<N>(rowa, rowb, KX, P::First::in_index(j, g, r)) : make_float2(0.f, 0.f);
-    fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
-    if (active) {
-#pragma unroll
-      for (int g = 0; g < P::Last::G; ++g)
-#pragma unroll
-        for (int r = 0; r < P::Last::R; ++r) {
-          const float2 val = P::Last::result(v, g, r);  // swapped: .y = row ya, .x = row ya + 1
-          const int ia = ya * N + P::Last::out_index(j, g, r);
-          if (better(val.y, ia, best, best_idx)) {
-            best = val.y;
-            best_idx = ia;
-          }
-          if (rowb && better(val.x, ia + N, best, best_idx)) {
-            best = val.x;
-            best_idx = ia + N;
-          }
+      for (int r = 0; r < P::Last::R; ++r) {
+        const float2 val = P::Last::result(v, g, r);  // swapped: .y = row ya, .x = row ya + 1
+        const int ia = ya * N + P::Last::out_index(j, g, r);
+        if (better(val.y, ia, best, best_idx)) {
+          best = val.y;
+          best_idx = ia;
         }
-    }
-    __syncthreads();
-  }
+        if (has_b && better(val.x, ia + N, best, best_idx)) {
+          best = val.x;
+          best_idx = ia + N;
+        }
+      }
+  });
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -318,43 +374,21 @@ template <int N>
 __global__ void __launch_bounds__(fft2::kThreads)
 rows_inverse_store_p2(const float2* __restrict__ tmp, int NY, int KX, const float2* __restrict__ tw, float scale,
                       float* __restrict__ out) {
-  using C = fft2::Cfg<N>;
   using P = fft2::Plan<N>;
   extern __shared__ float2 smem[];
-  const fft2::Smem<N> sm(smem);
-  fft2::load_twiddles<N>(sm, tw);
-  const int seq = threadIdx.x / C::TPS, j = threadIdx.x % C::TPS;
-  float2* myseq = sm.data + seq * C::STRIDE;
   const long item = blockIdx.y;
-  const float2* src = tmp + item * NY * KX;
   float* dst = out + item * NY * N;
-  __syncthreads();
-  for (int it = 0; it < kRowIters; ++it) {
-    const int ya = blockIdx.x * rows_per_cta_inverse<N>() + (it * C::B + seq) * 2;
-    const bool active = ya < NY;
-    const float2* rowa = src + (long)ya * KX;
-    const float2* rowb = (ya + 1 < NY) ? rowa + KX : nullptr;
-    float2 v[C::VPT];
+  rows_inverse_driver<N>(tmp + item * NY * KX, NY, KX, tw, smem, [&](int ya, bool has_b, int j, const float2* v) {
 #pragma unroll
-    for (int g = 0; g < P::First::G; ++g)
+    for (int g = 0; g < P::Last::G; ++g)
 #pragma unroll
-      for (int r = 0; r < P::First::R; ++r)
-        v[g * P::First::R + r] =
-            active ? c2r_pair_entry<N>(rowa, rowb, KX, P::First::in_index(j, g, r)) : make_float2(0.f, 0.f);
-    fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
-    if (active) {
-#pragma unroll
-      for (int g = 0; g < P::Last::G; ++g)
-#pragma unroll
-        for (int r = 0; r < P::Last::R; ++r) {
-          const float2 val = P::Last::result(v, g, r);
-          const int x = P::Last::out_index(j, g, r);
-          dst[(long)ya * N + x] = val.y * scale;
-          if (rowb) dst[(long)(ya + 1) * N + x] = val.x * scale;
-        }
-    }
-    __syncthreads();
-  }
+      for (int r = 0; r < P::Last::R; ++r) {
+        const float2 val = P::Last::result(v, g, r);
+        const int x = P::Last::out_index(j, g, r);
+        dst[(long)ya * N + x] = val.y * scale;
+        if (has_b) dst[(long)(ya + 1) * N + x] = val.x * scale;
+      }
+  });
 }
 
 // ---- whole-frame Fourier shift, column pass: FFT along y, phase multiply, inverse FFT along y ----------
@@ -364,7 +398,7 @@ rows_inverse_store_p2(const float2* __restrict__ tmp, int NY, int KX, const floa
 // per thread.  exp(i(a+b)) = exp(ia) exp(ib): differs from the reference's cos/sin of the summed angle by
 // fp32 rounding only.
 template <int N>
-__global__ void __launch_bounds__(fft2::kThreads)
+__global__ void __launch_bounds__(fft2::kThreads, N <= 4096 ? 3 : 1)
 cols_shift_p2(float2* __restrict__ tmp, int KX, int NX, const float2* __restrict__ phase_y, const float* __restrict__ field,
               int T, float sign, const float2* __restrict__ tw) {
   using C = fft2::Cfg<N>;

@@ -15,7 +15,7 @@ from typing import Any, cast
 import torch
 
 from . import _fourier, _ops
-from ._common import as_f32, grid_kind, resolve_device
+from ._common import as_f32, cached_device_tensor, grid_kind, resolve_device, to_device_async
 from ._lib import call, ptr, query, stream_ptr
 from .deformation_field_utils import resample_deformation_field
 from .optimization_state import OptimizationTracker
@@ -98,11 +98,14 @@ class LocalMotionProblem:
         self.plan = _fourier.BandPlan(ph, pw, dev, pixel_spacing, b_factor, frequency_range)
         mask, ylo, yhi = _fourier.soft_disc_mask((ph, pw), pw / 4, pw / 4, dev)  # quirk Q18: smoothing pw/4
         self.tp = 2 * ((t + 1) // 2)
-        jobs = []
-        for gi in range(self.g):
-            for i in range(0, t, 2):
-                jobs.append([i, 1, i + 1 if i + 1 < t else -1, 1, y0[gi], x0[gi]])
-        jobs = torch.tensor(jobs, dtype=torch.int32).to(dev)
+        def build_jobs():
+            jobs = []
+            for gi in range(self.g):
+                for i in range(0, t, 2):
+                    jobs.append([i, 1, i + 1 if i + 1 < t else -1, 1, y0[gi], x0[gi]])
+            return torch.tensor(jobs, dtype=torch.int32)
+
+        jobs = cached_device_tensor(("local_jobs", (t, h, w, ph, pw)), build_jobs, dev)
         self.spec = self.plan.forward(movie, stats, mask, ylo, yhi, jobs, job_mode=2)  # (g * tp, KY, KX, 2)
         self.norms = torch.empty((self.g, t, 2), dtype=torch.float64, device=dev)
         p = self.plan
@@ -111,11 +114,14 @@ class LocalMotionProblem:
                  ptr(self.norms), stream_ptr(dev))
 
         # normalised (t, y, x) centres, (T, G, 3) time-major (patch_utils.py:88-93,157-172; quirk Q10)
-        norm = centers.clone().float()
-        norm[..., 0] /= float(t - 1) if t > 1 else float("nan")
-        norm[..., 1] /= float(h - 1)
-        norm[..., 2] /= float(w - 1)
-        self.centres_norm = norm.reshape(t, self.g, 3).contiguous().to(dev)
+        def build_centres():
+            norm = centers.clone().float()
+            norm[..., 0] /= float(t - 1) if t > 1 else float("nan")
+            norm[..., 1] /= float(h - 1)
+            norm[..., 2] /= float(w - 1)
+            return norm.reshape(t, self.g, 3).contiguous()
+
+        self.centres_norm = cached_device_tensor(("local_centres", (t, h, w, ph, pw)), build_centres, dev)
         self.eval_base = _ops.spline_eval(base, self.kind, self.centres_norm)  # (T, G, 2)
         ws_bytes = query("tmc_local_loss_workspace_bytes", self.g, t, p.ky, p.kx)
         self.workspace = torch.empty(((ws_bytes + 7) // 8,), dtype=torch.float64, device=dev)
@@ -282,7 +288,7 @@ def estimate_local_motion(
     elif n_iterations > 0:
         # the mini-batch weighting of every iteration, uploaded once (same random.shuffle stream as the reference)
         all_batches = [_shuffled_batches(problem.g, 8) for _ in range(n_iterations)]
-        scales = torch.tensor([problem.patch_scales(b) for b in all_batches], dtype=torch.float32).to(dev)
+        scales = to_device_async(torch.tensor([problem.patch_scales(b) for b in all_batches], dtype=torch.float32), dev)
         counter = torch.zeros((1,), dtype=torch.int32, device=dev)
         fused = problem.loss_type != 2  # mse / cc: the kernel picks the row from the device-side counter
 

@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 
 from . import _fourier, _ops
-from ._common import as_f32, resolve_device
+from ._common import as_f32, cached_device_tensor, resolve_device
 from ._lib import call, ptr, stream_ptr
 from .correct_motion import correct_motion, correct_motion_fast
 from .deformation_field_utils import resample_deformation_field
@@ -165,18 +165,29 @@ def estimate_motion_cross_correlation_patches(
 
     skip = -1
     if reference_strategy == "mean_except_current":
-        offsets, deltas = _aliasing_schedule(t, reference_strategy, reference_frame)
-        jobs = [[k, 1, k, 2, y0, x0] for k in range(t) for (y0, x0) in origins]
-        jobs = torch.tensor(jobs, dtype=torch.int32).to(dev)
+        geometry = (t, h, w, p)
+        jobs = cached_device_tensor(
+            ("xc_jobs_mean", geometry),
+            lambda: torch.tensor([[k, 1, k, 2, y0, x0] for k in range(t) for (y0, x0) in origins], dtype=torch.int32), dev)
         spec = plan.forward(source, source_stats, mask, ylo, yhi, jobs, job_mode=1)
-        d_off = torch.tensor(offsets, dtype=torch.int32).to(dev)
-        d_val = torch.tensor(deltas if deltas else [0], dtype=torch.int32).to(dev)
+
+        def schedule(part):
+            offsets, deltas = _aliasing_schedule(t, reference_strategy, reference_frame)
+            return torch.tensor(offsets if part == 0 else (deltas if deltas else [0]), dtype=torch.int32)
+
+        d_off = cached_device_tensor(("xc_delta_offsets", t), lambda: schedule(0), dev)
+        d_val = cached_device_tensor(("xc_deltas", t), lambda: schedule(1), dev)
         prod = _fourier.leave_one_out_products(spec, t, n_patches, plan.plane_elems, d_off, d_val)
     else:
-        power = _aliasing_schedule(t, reference_strategy, reference_frame)
         skip = int(reference_frame)
-        jobs = [[k, 1, reference_frame, max(power[k], 1), y0, x0] for k in range(t) for (y0, x0) in origins]
-        jobs = torch.tensor(jobs, dtype=torch.int32).to(dev)
+
+        def middle_jobs():
+            power = _aliasing_schedule(t, reference_strategy, reference_frame)
+            return torch.tensor(
+                [[k, 1, reference_frame, max(power[k], 1), y0, x0] for k in range(t) for (y0, x0) in origins], dtype=torch.int32
+            )
+
+        jobs = cached_device_tensor(("xc_jobs_middle", (t, h, w, p), int(reference_frame)), middle_jobs, dev)
         spec = plan.forward(source, source_stats, mask, ylo, yhi, jobs)
         items = torch.arange(t * n_patches, dtype=torch.int32, device=dev)
         prod = _fourier.pair_products(spec, 2 * items + 1, 2 * items, plan.plane_elems)
@@ -187,4 +198,4 @@ def estimate_motion_cross_correlation_patches(
         call("tmc_xc_postprocess", ptr(shifts), t, n_patches, float(pixel_spacing), skip, int(bool(outlier_rejection)),
              float(outlier_threshold), int(bool(temporal_smoothing)), int(smoothing_window_size), 1, ptr(field), ptr(scratch),
              stream_ptr(dev))
-    return field, centers.to(dev)
+    return field, cached_device_tensor(("patch_centres", (t, h, w, p)), lambda: centers, dev).clone()
