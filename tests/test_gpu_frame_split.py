@@ -66,3 +66,22 @@ def test_frame_split_world1_degenerates_to_single_gpu():
     want_total, want_field = tmc.motion_correct(movie, 1.1, patch_sidelength=64, frequency_range=(80, 5))
     assert float((field - want_field).abs().max()) <= 1e-5
     assert float(torch.linalg.norm(total - want_total) / torch.linalg.norm(want_total)) <= 1e-6
+
+
+def test_motion_correct_many_matches_single_calls():
+    """Pipelined host->device->host processing returns the same sums/fields as one call per movie."""
+    import torch_motion_correction_b200 as tmc
+    from oracle import reference_path as rp
+
+    dev = torch.device("cuda:0")
+    movies = [rp.synthetic_movie(5, 128, 128, seed=s, noise=0.5, drift=2.0, local=0.3)[0].pin_memory() for s in (1, 2, 3)]
+    kwargs = dict(patch_sidelength=64, frequency_range=(80, 5), n_iterations=0)
+    got = []
+    for host_sum, field in tmc.motion_correct_many(movies, 1.1, device=dev, **kwargs):
+        torch.cuda.synchronize()
+        got.append((host_sum.clone(), field.cpu()))
+    assert len(got) == 3
+    for m, (host_sum, field) in zip(movies, got):
+        want_sum, want_field = tmc.motion_correct(m.to(dev), 1.1, **kwargs)
+        assert torch.equal(field, want_field.cpu())
+        assert float(torch.linalg.norm(host_sum - want_sum.cpu()) / torch.linalg.norm(want_sum.cpu())) <= 1e-6

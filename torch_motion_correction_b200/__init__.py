@@ -26,7 +26,7 @@ from .estimate_motion_xc import estimate_global_motion, estimate_motion_cross_co
 from .optimization_state import OptimizationState, OptimizationTracker
 from .patch_grid import patch_grid_centers
 from .spline_grids import CubicBSplineGrid3d, CubicCatmullRomGrid3d
-from .pipeline import estimate_motion, motion_correct
+from .pipeline import estimate_motion, motion_correct, motion_correct_many
 from .utils import normalize_image
 
 __version__ = "0.1.0"
@@ -46,4 +46,5 @@ __all__ = [
     "estimate_motion_cross_correlation_patches",
     "estimate_motion",
     "motion_correct",
+    "motion_correct_many",
 ]

@@ -52,3 +52,52 @@ def motion_correct(image: torch.Tensor, pixel_spacing: float, grid_type: str = "
     field, _ = estimate_motion(image, pixel_spacing, grid_type=grid_type, device=device, **estimate_kwargs)
     total = correct_motion_sum(image, field, pixel_spacing, grid_type=grid_type, device=device)
     return total, field
+
+
+def motion_correct_many(host_movies, pixel_spacing: float, device=None, out_host=None, **kwargs):
+    """Align a sequence of movies held in (ideally pinned) HOST memory; yields ``(sum_host, field)``.
+
+    The H2D copy of movie i+1 runs on a side stream while movie i is being estimated and corrected
+    (two device buffers), and each result is copied back asynchronously: dataset-scale processing
+    is bounded by max(PCIe, compute) instead of their sum."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    movies = iter(host_movies)
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    buffers = [None, None]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def start_copy(slot, host):
+        if buffers[slot] is None or buffers[slot].shape != host.shape:
+            buffers[slot] = torch.empty(host.shape, dtype=torch.float32, device=dev)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])  # the previous occupant of this buffer has been processed
+            buffers[slot].copy_(host, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    try:
+        nxt = next(movies)
+    except StopIteration:
+        return
+    consumed[0].record(main)
+    consumed[1].record(main)
+    start_copy(0, nxt)
+    slot = 0
+    while nxt is not None:
+        try:
+            upcoming = next(movies)
+        except StopIteration:
+            upcoming = None
+        if upcoming is not None:
+            start_copy(1 - slot, upcoming)
+        main.wait_event(ready[slot])
+        total, field = motion_correct(buffers[slot], pixel_spacing, device=dev, **kwargs)
+        consumed[slot].record(main)
+        if out_host is not None:
+            host_sum = out_host
+        else:
+            host_sum = torch.empty(total.shape, dtype=torch.float32, pin_memory=True)
+        host_sum.copy_(total, non_blocking=True)
+        yield host_sum, field
+        nxt, slot = upcoming, 1 - slot
