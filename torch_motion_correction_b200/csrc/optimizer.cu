@@ -449,7 +449,9 @@ TMC_API int tmc_local_loss_grad(const void* spec, const double* norms, const flo
   predicted_shifts_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(eval_new, eval_base, t, g, pixel_spacing, shifts); tmc_count_launch();
   if (loss_type != 2) {
     phase_tables_kernel<<<g * t, 128, 0, stream>>>(shifts, t, geom, E); tmc_count_launch();
-    // (a variant that kept all frames of a bin tile in shared memory was measured 20-75 % slower: occupancy)
+    // Measured alternatives that were SLOWER than this streaming kernel (C2, 100 iterations per movie: 16.3 ms):
+    // all frames of a bin tile kept in shared memory (+20..75 %), all frames of one bin kept in registers with a
+    // shared-memory transpose for the per-frame reductions (+45 %), 64-register / high-occupancy variants (+10..45 %).
     {
       // 4 bins per thread, 4 frames in flight: measured fastest (ILP beats occupancy here; the 64-register
       // variants with 2-8 CTAs/SM were 10-45 % slower)
