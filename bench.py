@@ -171,6 +171,7 @@ def algorithmic_bytes(cfg, iterations, band_bins, n_patches):
         "tmc_fourier_shift_frames": 2 * t * frame,
         # optimiser: the band-limited spectra are read once per iteration
         "graph:optimiser_steps": iterations * spectra,
+        "tmc_local_steps": iterations * spectra,
         # inverse transforms + peak search read the band-limited products (patch + whole-frame) once
         "tmc_xc_peaks": spectra + 8 * t * band_bins,
     }
@@ -379,6 +380,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
     kernel_names = {
         "graph:optimiser_steps": "loss_fused_kernel (+ ~12 tiny kernels per optimiser step, CUDA-graph replay)",
+        "tmc_local_steps": "local_loss_tile_kernel + local_coefficient_kernel (two launches per optimiser iteration)",
         "tmc_rfft2_band": "rows_forward_p2 + cols_forward_p2", "tmc_fourier_shift_frames": "rows_forward_p2 + cols_shift_p2 + rows_inverse_store_p2",
         "tmc_warp_lattice": "warp_lattice_kernel", "tmc_xc_peaks": "cols_inverse_p2 + rows_inverse_argmax_p2",
     }

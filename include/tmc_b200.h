@@ -187,6 +187,29 @@ int tmc_advance_counter(int* counter, tmc_stream_t stream);
 int tmc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int n, double lr, double beta1,
                   double beta2, double eps, double weight_decay, const int* step_counter, tmc_stream_t stream);
 
+/* ---- one optimiser iteration as two launches ("mse" / "cc"): estimate_motion_optimizer.py:361-416 (loop over the
+ *      shuffled mini-batches, loss.backward(), optimizer.step()) with the spline evaluation of :487-490, the Fourier
+ *      shift + filters of :495-508, the leave-one-out reference of :391-399 and _compute_loss :611-671 inside ---- */
+/* 1 if tmc_local_steps supports the problem (t frames fit the shared-memory tile of t KB, ...), else 0 (use
+ * tmc_local_loss_grad) */
+int tmc_local_steps_supported(int g, int t, int nt, int nhw);
+/* re-lay spec (g, tp, ky_count, kx_count) complex64 into tiles of 8 (ky) x 16 (kx) bins with the t frames of a tile
+ * contiguous, real and imaginary parts in separate planes: out (g, n_tiles, t, 2, 128) float32, zero padded;
+ * tiles (n_tiles, 2) int32 = (ty, tx) lists the tiles that hold at least one pass-band bin */
+int tmc_local_tile_spectra(const void* spec, int g, int t, int tp, int ky_count, int kx_count, const int* tiles,
+                           int n_tiles, void* out, tmc_stream_t stream);
+long tmc_local_steps_workspace_bytes(int g, int t, int nt);
+/* n_steps iterations (1 + 2 n_steps launches).  sum_norms (g) double = sum_t A_t; eval_base (t, g, 2) Angstrom; w_t (t, nt)
+ * and w_sp (g, nhw): dense separable spline weights of the patch centres (time / space); patch_scale (rows, g), step i
+ * uses row first_row + i; coef (2, nt, nhw).  mode 0: Adam update in place (step number first_row + i + 1),
+ * loss_out[first_row + i]; mode 1 (n_steps == 1): gradient only -> grad_out (2, nt, nhw), loss_out[0]. */
+int tmc_local_steps(const void* tiled, const int* tiles, int n_tiles, int g, int t, int ny, int nx, int ky_count,
+                    int kx_count, int ky_start, const double* sum_norms, const float* eval_base, const float* w_t,
+                    const float* w_sp, int nt, int nhw, const float* patch_scale, float pixel_spacing, int loss_type,
+                    float* coef, float* exp_avg, float* exp_avg_sq, double lr, double beta1, double beta2, double eps,
+                    double weight_decay, int first_row, int mode, int n_steps, double* loss_out, float* grad_out,
+                    void* workspace, tmc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,3 +101,43 @@ def test_invalid_arguments(dev, small):
         tmc.estimate_local_motion(movie.to(dev), px, (32, 32), (2, 2, 2), None, n_iterations=1, grid_type="linear")
     with pytest.raises(ValueError, match="Unsupported optimizer"):
         tmc.estimate_local_motion(movie.to(dev), px, (32, 32), (2, 2, 2), None, n_iterations=1, optimizer_type="adagrad")
+
+
+@pytest.mark.parametrize("name", ["adam_catmull_mse", "adam_bspline_mse"])
+def test_one_kernel_iterations_match_golden(dev, small, name):
+    """Without a trajectory the Adam run is ``n_iterations`` launches of the one-kernel iteration
+    (tmc_local_steps, mode 0); it must land on the same golden field as the step-by-step path."""
+    g, movie, px, fr = small
+    init = torch.as_tensor(g["xc_full_mean_except_current"]).to(dev)
+    random.seed(1234)
+    res = tmc.estimate_local_motion(
+        movie.to(dev), px, (32, 32), (3, 3, 3), init, n_iterations=6, frequency_range=fr, **LOCAL_CASES[name]
+    )
+    want = torch.as_tensor(g[f"local_{name}"])
+    assert float((res.cpu() - want).abs().max()) <= SHIFT_PX * px
+
+
+def test_one_kernel_iterations_match_generic_kernels(dev, small, monkeypatch):
+    """tmc_local_steps (tiled spectra, shared-memory passes, fused Adam) against the generic
+    loss/gradient kernels + tmc_adam_step on the same shuffled mini-batch schedule, 25 iterations."""
+    from torch_motion_correction_b200 import estimate_motion_optimizer as emo
+
+    g, movie, px, fr = small
+    init = torch.as_tensor(g["xc_full_mean_except_current"]).to(dev)
+    kwargs = dict(n_iterations=25, frequency_range=fr, grid_type="bspline", loss_type="cc")
+    random.seed(99)
+    fused = tmc.estimate_local_motion(movie.to(dev), px, (32, 32), (3, 4, 4), init, **kwargs)
+    monkeypatch.setattr(emo, "FUSED_STEPS", False)
+    random.seed(99)
+    generic = tmc.estimate_local_motion(movie.to(dev), px, (32, 32), (3, 4, 4), init, **kwargs)
+    assert float((fused - generic).abs().max()) <= 1e-3 * px
+    assert float(generic.abs().max()) > 0.01
+
+
+def test_one_kernel_iterations_c1_golden(dev, golden_c1):
+    g = golden_c1
+    movie, _ = rp.synthetic_movie(10, 512, 512, seed=0, noise=1.0, drift=6.0, integer_shifts=True, sigma_f=0.08)
+    init = torch.as_tensor(g["xc_field"]).to(dev)
+    random.seed(5)
+    res = tmc.estimate_local_motion(movie.to(dev), 1.0, (128, 128), (3, 5, 5), init, n_iterations=3, grid_type="bspline")
+    assert float((res.cpu() - torch.as_tensor(g["local_field"])).abs().max()) <= SHIFT_PX

@@ -95,6 +95,7 @@ class BandPlan:
         else:
             self.ky, self.ky_start = 2 * kym + 1, -kym
         key = (_dev_key(device), ny, nx, float(pixel_spacing), float(b_factor), low, high)
+        self.key = key
         wt = _weights.get(key)
         if wt is None:
             wt = torch.empty((self.ky, self.kx), dtype=torch.float32, device=device)
@@ -188,6 +189,27 @@ class BandPlan:
                 call("tmc_irfft2_full", spec.data_ptr() + i0 * per_item, m, self.ny, self.nx, ptr(self.tw_x), ptr(self.tw_y),
                      ptr(tmp), out.data_ptr() + i0 * self.ny * self.nx * 4, stream)
         return out
+
+
+_tiles: dict = {}
+
+
+def band_tiles(plan: "BandPlan") -> torch.Tensor:
+    """(n_tiles, 2) int32 device tensor (ty, tx): the 8 x 16-bin tiles of the band box that hold at least one
+    pass-band bin (layout of tmc_local_tile_spectra).  Cached per plan geometry."""
+    key = plan.key
+    hit = _tiles.get(key)
+    if hit is None:
+        w = plan.weight
+        ky, kx = w.shape
+        pad = torch.zeros((8 * ((ky + 7) // 8), 16 * ((kx + 15) // 16)), dtype=torch.float32, device=w.device)
+        pad[:ky, :kx] = w
+        live = pad.reshape(pad.shape[0] // 8, 8, pad.shape[1] // 16, 16).abs().amax(dim=(1, 3)) > 0
+        hit = live.nonzero().to(torch.int32).contiguous()
+        if hit.shape[0] == 0:
+            hit = torch.zeros((1, 2), dtype=torch.int32, device=w.device)
+        _tiles[key] = hit
+    return hit
 
 
 def frame_pair_jobs(t: int, device: torch.device, frame_offset: int = 0) -> torch.Tensor:

@@ -9,6 +9,7 @@ drives the coefficient update exactly as in the reference (same defaults)."""
 
 from __future__ import annotations
 
+import os
 import random
 from typing import Any, cast
 
@@ -22,6 +23,9 @@ from .optimization_state import OptimizationTracker
 from .patch_grid import patch_grid_centers
 
 LOSS_TYPES = {"mse": 0, "cc": 1, "ncc": 2}
+
+#: use the one-kernel iteration (csrc/optimizer_tiled.cu) for the "mse" / "cc" losses when the frame count fits
+FUSED_STEPS = os.environ.get("TMC_FUSED_STEPS", "1") != "0"
 
 
 def _setup_optimizer(optimizer_type: str, parameters, **kwargs: Any) -> torch.optim.Optimizer:
@@ -133,6 +137,58 @@ class LocalMotionProblem:
         n_ws = query("tmc_spline_workspace_floats", 2, *self.resolution)
         self.ws_eval = torch.empty((n_ws,), dtype=torch.float32, device=dev)
         self.ws_back = torch.empty((n_ws,), dtype=torch.float32, device=dev)
+        self.fused = FUSED_STEPS and self.loss_type != 2 and bool(
+            query("tmc_local_steps_supported", self.g, t, self.resolution[0], self.resolution[1] * self.resolution[2]))
+        if self.fused:
+            self._setup_fused_steps()
+
+    def _setup_fused_steps(self):
+        """State of the one-kernel iteration (csrc/optimizer_tiled.cu): tiled spectra, the separable dense spline
+        weights of the patch centres, accumulators.  The (g * tp, KY, KX) spectra are released."""
+        dev, t, p = self.dev, self.t, self.plan
+        nt, nh, nw = self.resolution
+        self.tiles = _fourier.band_tiles(p)
+        n_tiles = self.tiles.shape[0]
+        self.tiled = torch.empty((self.g, n_tiles, t, 2, 128), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call("tmc_local_tile_spectra", ptr(self.spec), self.g, t, self.tp, p.ky, p.kx, ptr(self.tiles), n_tiles,
+                 ptr(self.tiled), stream_ptr(dev))
+        self.spec = None
+        self.sum_norms = self.norms[:, :, 0 if self.loss_type == 0 else 1].sum(dim=1).contiguous()
+        # the patch centres are a product grid (frame) x (patch): the 64-tap spline weights factor into a dense
+        # (T, nt) time matrix and a dense (G, nh nw) spatial matrix, phantom nodes folded in (spline of unit grids)
+        key = ("local_weights", self.kind, self.resolution, tuple(self.centres_norm.shape), self.centres_norm.data_ptr())
+        hit = _separable_weights.get(key)
+        if hit is None:
+            if len(_separable_weights) > 64:
+                _separable_weights.clear()
+            cn = self.centres_norm
+            pts_t = torch.zeros((t, 3), dtype=torch.float32, device=dev)
+            pts_t[:, 0] = cn[:, 0, 0]
+            pts_s = cn[0].clone()
+            pts_s[:, 0] = 0.0
+            eye_t = torch.eye(nt, dtype=torch.float32, device=dev).reshape(nt, nt, 1, 1).contiguous()
+            eye_s = torch.eye(nh * nw, dtype=torch.float32, device=dev).reshape(nh * nw, 1, nh, nw).contiguous()
+            hit = (_ops.spline_eval(eye_t, self.kind, pts_t).contiguous(), _ops.spline_eval(eye_s, self.kind, pts_s).contiguous(),
+                   cn)  # keep cn alive: its data_ptr is part of the key
+            _separable_weights[key] = hit
+        self.w_t, self.w_sp = hit[0], hit[1]
+        ws_bytes = query("tmc_local_steps_workspace_bytes", self.g, t, nt)
+        self.step_ws = torch.empty(((ws_bytes + 7) // 8,), dtype=torch.float64, device=dev)
+
+    def fused_steps(self, coef, scales, first_row, n_steps, mode, loss_out, adam=None):
+        """``n_steps`` iterations (loss/gradient kernel + coefficient kernel each).  mode 0: Adam (``adam`` = (exp_avg,
+        exp_avg_sq, lr, b1, b2, eps, wd)) updating ``coef`` in place; mode 1: gradient into ``self.grad`` and loss into
+        ``loss_out[0]``.  ``scales`` (rows, G): step i uses row ``first_row + i``."""
+        p = self.plan
+        nt, nh, nw = self.resolution
+        exp_avg, exp_avg_sq, lr, b1, b2, eps, wd = adam if adam is not None else (None, None, 0.0, 0.0, 0.0, 0.0, 0.0)
+        with torch.cuda.device(self.dev):
+            call("tmc_local_steps", ptr(self.tiled), ptr(self.tiles), self.tiles.shape[0], self.g, self.t, self.ph, self.pw,
+                 p.ky, p.kx, p.ky_start, ptr(self.sum_norms), ptr(self.eval_base), ptr(self.w_t), ptr(self.w_sp), nt, nh * nw,
+                 ptr(scales), self.px, self.loss_type, ptr(coef), ptr(exp_avg), ptr(exp_avg_sq), float(lr), float(b1),
+                 float(b2), float(eps), float(wd), int(first_row), int(mode), int(n_steps), ptr(loss_out), ptr(self.grad),
+                 ptr(self.step_ws), stream_ptr(self.dev))
 
     def patch_scales(self, batches) -> torch.Tensor:
         """Per-patch weight reproducing the reference's per-mini-batch ``mean`` (quirk Q11): the
@@ -148,10 +204,14 @@ class LocalMotionProblem:
                 scale[gi] = s
         return scale
 
-    def loss_and_grad(self, new_data: torch.Tensor, scale: torch.Tensor, iteration: torch.Tensor | None = None):
+    def loss_and_grad(self, new_data: torch.Tensor, scale: torch.Tensor, iteration: torch.Tensor | None = None, row: int = 0):
         """Sum over mini-batches of the batch losses (device float64 (1,)) and d/d new_data.
 
-        ``scale`` is (G,) or, with ``iteration`` (device int32 counter; mse / cc only), (n, G)."""
+        ``scale`` is (G,) or (n, G) with the row picked by ``row`` (host int; tiled two-kernel path) or by
+        ``iteration`` (device int32 counter; generic mse / cc path inside a captured graph)."""
+        if self.fused:
+            self.fused_steps(new_data, scale, row, 1, 1, self.loss)
+            return self.loss, self.grad
         eval_new = _ops.spline_eval(new_data, self.kind, self.centres_norm, out=self.eval_new.view(-1, 2), ws=self.ws_eval)
         p = self.plan
         with torch.cuda.device(self.dev):
@@ -162,6 +222,9 @@ class LocalMotionProblem:
             (2, *self.resolution), self.kind, self.centres_norm, self.grad_eval, out=self.grad, ws=self.ws_back
         )
         return self.loss, grad
+
+
+_separable_weights: dict = {}
 
 
 def _graph_capable(optimizer: torch.optim.Optimizer) -> bool:
@@ -301,7 +364,9 @@ def estimate_local_motion(
             eps, wd = float(kwargs.get("eps", 1e-08)), float(kwargs.get("weight_decay", 0))
 
         def one_step(i: int):
-            if fused:
+            if problem.fused:
+                loss, grad = problem.loss_and_grad(new.data, scales, row=i)
+            elif fused:
                 loss, grad = problem.loss_and_grad(new.data, scales, counter)
             else:
                 loss, grad = problem.loss_and_grad(new.data, scales[i])
@@ -317,7 +382,11 @@ def estimate_local_motion(
             return loss
 
         done = 0
-        if fused and not return_trajectory and n_iterations >= 4 and (fused_adam or _graph_capable(optimizer)):
+        if problem.fused and fused_adam and not return_trajectory:
+            losses = torch.empty((n_iterations,), dtype=torch.float64, device=dev)
+            problem.fused_steps(new.data, scales, 0, n_iterations, 0, losses, (exp_avg, exp_avg_sq, lr, b1, b2, eps, wd))
+            done = n_iterations
+        elif fused and not problem.fused and not return_trajectory and n_iterations >= 4 and (fused_adam or _graph_capable(optimizer)):
             done = _run_captured(one_step, n_iterations, dev)
         for iter_idx in range(done, n_iterations):
             loss = one_step(iter_idx)
