@@ -207,10 +207,9 @@ def cpu_sample_plan(cfg, n_steps_total):
     t, h, w = cfg["t"], cfg["h"], cfg["w"]
     if h * w <= 1024 * 1024:
         return dict(frames=min(t, 10), crop=(h, w))
+    # ~25 s of CPU work per pass on 16 cores: 3 frames of a half-size crop (2 x 2 patches of the workload's size)
     if n_steps_total <= 4:
-        return dict(frames=3, crop=(h, w))
-    if n_steps_total <= 8:
-        return dict(frames=2, crop=(h, w))
+        return dict(frames=3, crop=(h // 2, w // 2))
     return dict(frames=2, crop=(h // 2, w // 2))
 
 

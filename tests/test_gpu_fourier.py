@@ -202,3 +202,65 @@ def test_global_motion_non_power_of_two_frames(dev):
     got = tmc.estimate_global_motion(movie.to(dev), 1.0, frequency_range=(60, 4)).cpu()
     assert torch.equal(got, want)
     assert torch.equal(got[:, :, 0, 0].T, walk)
+
+
+@pytest.mark.parametrize("job_mode,x0", [(1, 36), (2, 36), (2, 37)])
+def test_polyphase_rows_1024_patch_spectra(dev, job_mode, x0):
+    """1024-px patches run the polyphase row kernel (four 256-point warp FFTs per row, csrc/fourier_poly.cuh):
+    rfft2(mask^e * normalised patch) * W on the band box against torch.fft in float64; x0 = 37 exercises the
+    misaligned (scalar-load) path."""
+    g = torch.Generator().manual_seed(11)
+    movie = torch.randn((3, 1100, 1100), generator=g) * 2.0 + 1.0
+    p, px, fr = 1024, 0.9, (300, 10)
+    m = movie.to(dev)
+    stats = _ops.stack_stats(m)
+    plan = _fourier.BandPlan(p, p, dev, px, 500, fr)
+    assert plan.kx <= 128
+    mask, ylo, yhi = _fourier.soft_disc_mask((p, p), p / 4, p / 8, dev)
+    if job_mode == 1:
+        jobs = [[0, 1, 0, 2, 40, x0], [2, 1, 2, 2, 3, 5]]
+    else:
+        jobs = [[0, 1, 1, 1, 40, x0], [2, 1, -1, 1, 3, 5]]
+    jobs_dev = torch.tensor(jobs, dtype=torch.int32).to(dev)
+    spec = as_complex(plan.forward(m, stats, mask, ylo, yhi, jobs_dev, job_mode=job_mode)).cpu()
+    norm = rp.normalize_image(movie).double()
+    mk = deps.circle(p / 4, (p, p), smoothing_radius=p / 8).double()
+    band, env = rp.fourier_weight((p, p), px, 500, fr)
+    ky = (torch.arange(plan.ky) + plan.ky_start) % p
+    for j, (fa, ea, fb, eb, y0, xx) in enumerate(jobs):
+        for part, (f, e) in enumerate(((fa, ea), (fb, eb))):
+            if f < 0:
+                continue
+            want = torch.fft.rfftn(norm[f, y0 : y0 + p, xx : xx + p] * mk**e, dim=(-2, -1)) * (band * env).double()
+            want = want[ky][:, : plan.kx]
+            err = (spec[2 * j + part].to(torch.complex128) - want).abs().max() / want.abs().max()
+            assert float(err) < 5e-6, (j, part, float(err))
+
+
+def test_polyphase_rows_1024_peaks(dev):
+    """Inverse polyphase rows + argmax on 1024 x 1024 surfaces: a band-limited product whose correlation peak
+    sits at a known integer position, plus agreement with torch.fft.irfftn's argmax on random band-limited data."""
+    p, px, fr = 1024, 1.0, (300, 10)
+    plan = _fourier.BandPlan(p, p, dev, px, 500, fr)
+    ky = ((torch.arange(plan.ky) + plan.ky_start) % p).to(dev)
+    g = torch.Generator().manual_seed(5)
+    n = 5
+    # band-limit the spectrum of a REAL random image: Hermitian-consistent input, as the products of real patches are
+    img = torch.randn((n, p, p), generator=g).to(dev)
+    spec = torch.fft.rfftn(img, dim=(-2, -1))
+    kxs = torch.arange(plan.kx, device=dev)
+    box = torch.view_as_real(spec[:, ky[:, None], kxs[None, :]].contiguous()) * (plan.weight != 0)[None, :, :, None]
+    full = torch.zeros((n, p, p // 2 + 1), dtype=torch.complex64, device=dev)
+    full[:, ky[:, None], kxs[None, :]] = torch.view_as_complex(box.contiguous())
+    surf = torch.fft.irfftn(full, s=(p, p), dim=(-2, -1))
+    want = surf.reshape(n, -1).argmax(dim=1)
+    wy, wx = (want // p).float(), (want % p).float()
+    wy = torch.where(wy > p // 2, wy - p, wy)
+    wx = torch.where(wx > p // 2, wx - p, wx)
+    got = plan.peaks(box.contiguous(), sub_pixel=False)
+    # the argmax itself, up to fp32 near-ties of the band-limited (smooth) surface between the two transforms
+    gy, gx = got[:, 0].long() % p, got[:, 1].long() % p
+    picked = surf[torch.arange(n, device=dev), gy, gx]
+    top = surf.reshape(n, -1).max(dim=1).values
+    assert bool((picked >= top - 1e-4 * top.abs()).all()), (got, wy, wx, picked, top)
+    assert int(((gy == want // p) & (gx == want % p)).sum()) >= n - 1

@@ -16,7 +16,8 @@ KEYS = [
 ]
 UNIT = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
 rows = []
-for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{tag}_*_raw.csv")), key=lambda p: int(re.findall(r"_(\d+)_raw", p)[0])):
+paths = [p for p in glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{tag}_*_raw.csv")) if re.findall(r"_(\d+)_raw", p)]
+for path in sorted(paths, key=lambda p: int(re.findall(r"_(\d+)_raw", p)[0])):
     r = list(csv.reader(open(path)))
     if len(r) < 3:
         continue

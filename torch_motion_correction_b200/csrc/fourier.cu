@@ -12,6 +12,7 @@
 //  * rows outside the mask support are skipped; the inverse row pass feeds a block-wide argmax
 //    instead of storing the correlation surface.
 #include "common.cuh"
+#include <stdlib.h>
 #include "fft_core.cuh"
 #include "fft_core2.cuh"
 
@@ -462,6 +463,16 @@ rows_inverse_store_kernel(const float2* __restrict__ tmp, int NY, int KX, AxisPl
 }
 
 #include "fourier_p2.cuh"
+#include "fourier_poly.cuh"
+
+// TMC_FFT_POLY=0 selects the 1024-point block-level row kernels instead of the polyphase ones (A/B testing)
+inline bool use_poly() {
+  static const bool on = [] {
+    const char* e = getenv("TMC_FFT_POLY");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 template <int M, bool BLU>
 constexpr bool use_fast_path() {
@@ -680,6 +691,25 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
   int rc = dispatch_fft(nx, "rfft2_band", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
+    if constexpr (MM == 1024 && !BB) {
+      // polyphase path: four 256-point warp-level FFTs per row, only the band is ever formed
+      if (yhi > ylo && kx_count <= 128 && job_mode != 0 && use_poly()) {
+        int rows_per_cta = 32;
+        while (rows_per_cta > 8 && (long)tmc_div_up(yhi - ylo, rows_per_cta) * njobs < 148 * 6) rows_per_cta -= 8;
+        dim3 grid(tmc_div_up(yhi - ylo, rows_per_cta), njobs);
+        if (job_mode == 1) {
+          if (int e = enable_smem(poly::rows_forward_poly<1>, poly::smem_bytes)) return e;
+          poly::rows_forward_poly<1><<<grid, poly::kThreads, poly::smem_bytes, stream>>>(image, h, w, mean_std, mask, jobs, ylo, yhi, ny,
+                                                                                     kx_count, px.tw, (float2*)tmp, rows_per_cta);
+        } else {
+          if (int e = enable_smem(poly::rows_forward_poly<2>, poly::smem_bytes)) return e;
+          poly::rows_forward_poly<2><<<grid, poly::kThreads, poly::smem_bytes, stream>>>(image, h, w, mean_std, mask, jobs, ylo, yhi, ny,
+                                                                                     kx_count, px.tw, (float2*)tmp, rows_per_cta);
+        }
+        tmc_count_launch();
+        return TMC_OK;
+      }
+    }
     if constexpr (use_fast_path<MM, BB>()) {
       if (yhi > ylo) {
         constexpr int B = fft2::Cfg<MM>::B;
@@ -799,6 +829,15 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
   rc = dispatch_fft(nx, "xc_peaks", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
+    if constexpr (MM == 1024 && !BB) {
+      if (kx_count <= 128 && use_poly()) {
+        if (int e = enable_smem(poly::rows_inverse_argmax_poly, poly::smem_bytes)) return e;
+        dim3 grid(nparts, nitems);
+        poly::rows_inverse_argmax_poly<<<grid, poly::kThreads, poly::smem_bytes, stream>>>((const float2*)tmp, ny, kx_count, px.tw,
+                                                                                         (PeakCandidate*)partial); tmc_count_launch();
+        return TMC_OK;
+      }
+    }
     if constexpr (use_fast_path<MM, BB>()) {
       if (int e = enable_smem(rows_inverse_argmax_p2<MM>, rows_inverse_smem_bytes<MM>())) return e;
       dim3 grid(nparts, nitems);

@@ -132,9 +132,12 @@ __device__ __forceinline__ float gather_bicubic(const float* __restrict__ frame,
   return acc;
 }
 
-constexpr int kTileX = 128;  // threads along x
-constexpr int kTileYGroups = 8;
-constexpr int kRowsPerThread = 1;
+constexpr int kTileX = 128;    // threads along x
+#ifndef TMC_WARP_ROWS
+#define TMC_WARP_ROWS 4
+#endif
+constexpr int kTileYGroups = 2;  // thread rows per CTA
+constexpr int kRows = TMC_WARP_ROWS;         // vertically adjacent output pixels per thread
 
 // Stage 1: interpolate every lattice row along x once per (frame, channel, lattice row, image
 // column): RX[f][ch][a][x] = sum_b wx_b(x) * L[f][ch][a][jx_b(x)].  Same x-then-y order as ATen.
@@ -150,25 +153,84 @@ __global__ void lattice_xinterp_kernel(const float* __restrict__ lattice, int T,
   }
 }
 
-// Stage 2: one thread = kRowsPerThread vertically adjacent output pixels of one column.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
+
+// ATen get_cubic_upsample_coefficients on two fractions at once (.x = y axis, .y = x axis), same FMA chains
+__device__ __forceinline__ void cubic_weights2(float2 t, float2 (&w)[4]) {
+  const float2 A = dup(kA), m5A = dup(-5.0f * kA), p8A = dup(8.0f * kA), m4A = dup(-4.0f * kA);
+  const float2 A2 = dup(kA + 2.0f), mA3 = dup(-(kA + 3.0f)), one = dup(1.0f);
+  float2 x = __fadd2_rn(t, one);
+  w[0] = __ffma2_rn(__ffma2_rn(__ffma2_rn(A, x, m5A), x, p8A), x, m4A);
+  w[1] = __ffma2_rn(__fmul2_rn(__ffma2_rn(A2, t, mA3), t), t, one);
+  x = __ffma2_rn(t, dup(-1.0f), one);  // 1 - t, one rounding
+  w[2] = __ffma2_rn(__fmul2_rn(__ffma2_rn(A2, x, mA3), x), x, one);
+  x = __ffma2_rn(t, dup(-1.0f), dup(2.0f));  // 2 - t
+  w[3] = __ffma2_rn(__ffma2_rn(__ffma2_rn(A, x, m5A), x, p8A), x, m4A);
+}
+
+// border / outside pixels (grid_sample padding_mode="border" taps, zero outside): the generic scalar path
+__device__ __noinline__ float gather_border(const float* __restrict__ frame, int H, int W, float cy, float cx) {
+  if (!(cy >= 0.0f && cy <= (float)(H - 1) && cx >= 0.0f && cx <= (float)(W - 1))) return 0.f;
+  const ImageAxis ay = image_axis(cy, H), ax = image_axis(cx, W);
+  return gather_bicubic(frame, W, ay, ax);
+}
+
+// One output pixel over all frames on the generic scalar path (threads whose rows straddle a lattice cell)
+template <bool WRITE_STACK, bool NORMALISE>
+__device__ __noinline__ float warp_pixel_generic(const float* __restrict__ image, int T, int H, int W, const float* __restrict__ rx,
+                                                 int lh, float inv_px, float mean, float inv_std, float* __restrict__ out_stack,
+                                                 int x, int y) {
+  const LatticeAxis a = lattice_axis(y, H, lh);
+  const size_t rx_plane = (size_t)lh * W;
+  float acc = 0.f;
+  for (int f = 0; f < T; ++f) {
+    const float* Ry = rx + (size_t)f * 2 * rx_plane + x;
+    const float* Rx = Ry + rx_plane;
+    float sy = a.w[0] * __ldg(Ry + (size_t)a.j[0] * W), sx = a.w[0] * __ldg(Rx + (size_t)a.j[0] * W);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      sy = fmaf(a.w[k], __ldg(Ry + (size_t)a.j[k] * W), sy);
+      sx = fmaf(a.w[k], __ldg(Rx + (size_t)a.j[k] * W), sx);
+    }
+    const float cy = __fadd_rn((float)y, __fmul_rn(sy, inv_px));
+    const float cx = __fadd_rn((float)x, __fmul_rn(sx, inv_px));
+    float v = gather_border(image + (size_t)f * H * W, H, W, cy, cx);
+    if (NORMALISE) v = (v - mean) * inv_std;
+    if (WRITE_STACK) out_stack[((size_t)f * H + y) * W + x] = v;
+    acc += v;
+  }
+  return acc;
+}
+
+// Stage 2: one thread = kRows vertically adjacent output pixels of one column; the coordinate chain of a pixel
+// (Angstrom -> px, grid_sample round trip, cubic weights) runs on both axes at once as packed fp32x2 arithmetic
+// and the 8 lattice taps of a frame are shared by the thread's pixels.
 template <bool WRITE_STACK, bool WRITE_SUM, bool NORMALISE>
-__global__ void __launch_bounds__(kTileX* kTileYGroups, 1)
+__global__ void __launch_bounds__(kTileX* kTileYGroups)
 warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const float* __restrict__ rx, int lh,
                     float pixel_spacing, const float* __restrict__ mean_std, float* __restrict__ out_stack,
                     float* __restrict__ out_sum, int accumulate_sum) {
   const int x = blockIdx.x * kTileX + threadIdx.x;
-  const int y_base = (blockIdx.y * kTileYGroups + threadIdx.y) * kRowsPerThread;
+  const int y_base = (blockIdx.y * kTileYGroups + threadIdx.y) * kRows;
   if (x >= W || y_base >= H) return;
 
-  int jy[kRowsPerThread][4];
-  float wy[kRowsPerThread][4];
+  // lattice taps along y: rows of RX (offsets in floats) and duplicated weights per pixel
+  int jy[4];
+  float2 wy[kRows][4];
+  bool same_cell = true;
+  {
+    const LatticeAxis a0 = lattice_axis(y_base, H, lh);
 #pragma unroll
-  for (int r = 0; r < kRowsPerThread; ++r) {
-    LatticeAxis a = lattice_axis(min(y_base + r, H - 1), H, lh);
+    for (int k = 0; k < 4; ++k) jy[k] = a0.j[k] * W;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      jy[r][k] = a.j[k] * W;
-      wy[r][k] = a.w[k];
+    for (int r = 0; r < kRows; ++r) {
+      const LatticeAxis a = lattice_axis(min(y_base + r, H - 1), H, lh);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        wy[r][k] = dup(a.w[k]);
+        same_cell = same_cell && (a.j[k] == a0.j[k]);
+      }
     }
   }
   float mean = 0.f, inv_std = 1.f;
@@ -176,75 +238,121 @@ warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const 
     mean = __ldg(mean_std);
     inv_std = 1.0f / __ldg(mean_std + 1);
   }
-  float acc[kRowsPerThread];
+  float acc[kRows];
 #pragma unroll
-  for (int r = 0; r < kRowsPerThread; ++r) acc[r] = 0.f;
+  for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
+  if (!same_cell) {
+    // the rows of this thread straddle a lattice cell (warp-uniform, ~kRows in every H / lh rows)
+    for (int r = 0; r < kRows; ++r) {
+      const int y = y_base + r;
+      if (y >= H) break;
+      const float a = warp_pixel_generic<WRITE_STACK, NORMALISE>(image, T, H, W, rx, lh, 1.0f / pixel_spacing, mean, inv_std,
+                                                                   out_stack, x, y);
+      if (WRITE_SUM) {
+        float* o = out_sum + (long)y * W + x;
+        *o = accumulate_sum ? (*o + a) : a;
+      }
+    }
+    return;
+  }
 
-  const RoundTrip rty = make_round_trip(H), rtx = make_round_trip(W);
-  const float inv_px = 1.0f / pixel_spacing;
-  const float hmax = (float)(H - 1), wmax = (float)(W - 1);
+  // grid_sample round trip constants, .x = y axis (H), .y = x axis (W)
+  const float dy = __fsub_rn(__fmul_rn(0.5f, (float)H), 0.5f), dx = __fsub_rn(__fmul_rn(0.5f, (float)W), 0.5f);
+  const float2 nden = f2(-dy, -dx), rcp = f2(__frcp_rn(dy), __frcp_rn(dx));
+  const float2 scale = f2((float)(H - 1), (float)(W - 1));
+  const float2 inv_px = dup(1.0f / pixel_spacing);
+  const float xf = (float)x;
+  // all loads are (CTA-uniform 64-bit base) + (32-bit offset): no per-thread 64-bit pointer arithmetic
   const unsigned rx_plane = (unsigned)lh * (unsigned)W;
-  const float* rx_frame = rx + x;
-  const float* frame = image;
-  for (int f = 0; f < T; ++f, rx_frame += 2 * (size_t)rx_plane, frame += (size_t)H * W) {
+  unsigned jo[4];
 #pragma unroll
-    for (int r = 0; r < kRowsPerThread; ++r) {
+  for (int k = 0; k < 4; ++k) jo[k] = (unsigned)jy[k] + (unsigned)x;
+  const float* rx_frame = rx;
+  const float* frame = image;
+  float2 Rn[4];  // (y shift, x shift) lattice rows at this column, loaded one frame ahead
+#pragma unroll
+  for (int k = 0; k < 4; ++k) Rn[k] = f2(__ldg(rx_frame + jo[k]), __ldg(rx_frame + rx_plane + jo[k]));
+  for (int f = 0; f < T; ++f, frame += (size_t)H * W) {
+    float2 R[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) R[k] = Rn[k];
+    if (f + 1 < T) {
+      rx_frame += 2 * (size_t)rx_plane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) Rn[k] = f2(__ldg(rx_frame + jo[k]), __ldg(rx_frame + rx_plane + jo[k]));
+    }
+    // stage A: sampling coordinates of the thread's pixels -> tap pointers and fractions
+    float2 c[kRows], frac[kRows];
+    const float* p[kRows];
+    bool all_interior = true;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      float2 s = __fmul2_rn(wy[r][0], R[0]);
+      s = __ffma2_rn(wy[r][1], R[1], s);
+      s = __ffma2_rn(wy[r][2], R[2], s);
+      s = __ffma2_rn(wy[r][3], R[3], s);
+      // Angstrom -> px, then pixel_grid + pixel_shifts (two roundings, like the reference)
+      c[r] = __fadd2_rn(f2((float)min(y_base + r, H - 1), xf), __fmul2_rn(s, inv_px));
+      // grid_sample round trip: g = c / (0.5 n - 0.5) - 1 ; u = ((g + 1) / 2) (n - 1); the division as
+      // q0 = c * rcp, one Newton step on the residual (Divisor above)
+      const float2 q0 = __fmul2_rn(c[r], rcp);
+      const float2 q = __ffma2_rn(__ffma2_rn(q0, nden, c[r]), rcp, q0);
+      const float2 g = __fadd2_rn(q, dup(-1.0f));
+      const float2 u = __fmul2_rn(__fmul2_rn(__fadd2_rn(g, dup(1.0f)), dup(0.5f)), scale);
+      const float2 fl = f2(floorf(u.x), floorf(u.y));
+      frac[r] = __ffma2_rn(fl, dup(-1.0f), u);
+      const int iy = (int)fl.x, ix = (int)fl.y;
+      // interior (implies 0 <= c <= n - 1): all 16 taps at immediate offsets of one pointer
+      const bool interior = (unsigned)(iy - 1) <= (unsigned)(H - 4) && (unsigned)(ix - 1) <= (unsigned)(W - 4);
+      all_interior = all_interior && interior;
+      p[r] = frame + (interior ? (unsigned)((iy - 1) * W + (ix - 1)) : 0u);
+    }
+    float v[kRows];
+    if (all_interior) {
+      // stage B: every tap of every pixel in flight at once; stage C: weights (while the loads fly) and the sums
+      float tap[kRows][4][4];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const float* row = p[r];
+#pragma unroll
+        for (int a = 0; a < 4; ++a, row += W)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) tap[r][a][b] = __ldg(row + b);
+      }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        float2 w[4];  // .x = weight along y, .y = weight along x
+        cubic_weights2(frac[r], w);
+        // rows (0,1) and (2,3) as packed pairs
+        float2 r01 = __fmul2_rn(dup(w[0].y), f2(tap[r][0][0], tap[r][1][0]));
+        float2 r23 = __fmul2_rn(dup(w[0].y), f2(tap[r][2][0], tap[r][3][0]));
+#pragma unroll
+        for (int b = 1; b < 4; ++b) {
+          r01 = __ffma2_rn(dup(w[b].y), f2(tap[r][0][b], tap[r][1][b]), r01);
+          r23 = __ffma2_rn(dup(w[b].y), f2(tap[r][2][b], tap[r][3][b]), r23);
+        }
+        const float2 t2 = __ffma2_rn(f2(w[2].x, w[3].x), r23, __fmul2_rn(f2(w[0].x, w[1].x), r01));
+        v[r] = t2.x + t2.y;
+      }
+    } else {
+      // image border in reach: border-clamped taps / zero outside on the generic scalar path
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) v[r] = gather_border(frame, H, W, c[r].x, c[r].y);
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
       const int y = y_base + r;
       if (y < H) {
-        const float* Ry = rx_frame;
-        const float* Rx = rx_frame + rx_plane;
-        float sy = wy[r][0] * __ldg(Ry + jy[r][0]);
-        sy = fmaf(wy[r][1], __ldg(Ry + jy[r][1]), sy);
-        sy = fmaf(wy[r][2], __ldg(Ry + jy[r][2]), sy);
-        sy = fmaf(wy[r][3], __ldg(Ry + jy[r][3]), sy);
-        float sx = wy[r][0] * __ldg(Rx + jy[r][0]);
-        sx = fmaf(wy[r][1], __ldg(Rx + jy[r][1]), sx);
-        sx = fmaf(wy[r][2], __ldg(Rx + jy[r][2]), sx);
-        sx = fmaf(wy[r][3], __ldg(Rx + jy[r][3]), sx);
-        // Angstrom -> px, then pixel_grid + pixel_shifts (two roundings, like the reference)
-        const float cy = __fadd_rn((float)y, __fmul_rn(sy, inv_px));
-        const float cx = __fadd_rn((float)x, __fmul_rn(sx, inv_px));
-        float v = 0.f;
-        if (cy >= 0.0f && cy <= hmax && cx >= 0.0f && cx <= wmax) {
-          const float uy = round_trip(cy, rty), ux = round_trip(cx, rtx);
-          const float fy = floorf(uy), fx = floorf(ux);
-          float ay[4], ax[4];
-          cubic_weights(__fsub_rn(uy, fy), ay);
-          cubic_weights(__fsub_rn(ux, fx), ax);
-          const int iy = (int)fy, ix = (int)fx;
-          if (iy >= 1 && iy <= H - 3 && ix >= 1 && ix <= W - 3) {
-            // interior: 4 row pointers, taps at immediate offsets
-            const float* p = frame + (unsigned)((iy - 1) * W + (ix - 1));
-#pragma unroll
-            for (int a = 0; a < 4; ++a, p += W) {
-              float row = ax[0] * __ldg(p);
-              row = fmaf(ax[1], __ldg(p + 1), row);
-              row = fmaf(ax[2], __ldg(p + 2), row);
-              row = fmaf(ax[3], __ldg(p + 3), row);
-              v = fmaf(ay[a], row, v);
-            }
-          } else {
-            // border: every tap index clamped individually (grid_sample padding_mode="border")
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              const float* p = frame + (size_t)min(max(iy - 1 + a, 0), H - 1) * W;
-              float row = ax[0] * __ldg(p + min(max(ix - 1, 0), W - 1));
-              row = fmaf(ax[1], __ldg(p + min(max(ix, 0), W - 1)), row);
-              row = fmaf(ax[2], __ldg(p + min(max(ix + 1, 0), W - 1)), row);
-              row = fmaf(ax[3], __ldg(p + min(max(ix + 2, 0), W - 1)), row);
-              v = fmaf(ay[a], row, v);
-            }
-          }
-          if (NORMALISE) v = (v - mean) * inv_std;
-        }
-        if (WRITE_STACK) out_stack[((size_t)f * H + y) * W + x] = v;
-        if (WRITE_SUM) acc[r] += v;
+        float o = v[r];
+        if (NORMALISE) o = (o - mean) * inv_std;
+        if (WRITE_STACK) out_stack[((size_t)f * H + y) * W + x] = o;
+        if (WRITE_SUM) acc[r] += o;
       }
     }
   }
   if (WRITE_SUM) {
 #pragma unroll
-    for (int r = 0; r < kRowsPerThread; ++r) {
+    for (int r = 0; r < kRows; ++r) {
       const int y = y_base + r;
       if (y < H) {
         float* o = out_sum + (long)y * W + x;
@@ -435,7 +543,7 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
     lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, workspace); tmc_count_launch();
   }
   dim3 block(kTileX, kTileYGroups);
-  dim3 grid(tmc_div_up(w, kTileX), tmc_div_up(h, kTileYGroups * kRowsPerThread));
+  dim3 grid(tmc_div_up(w, kTileX), tmc_div_up(h, kTileYGroups * kRows));
 #define LAUNCH(S, A, N)                                                                                          \
   warp_lattice_kernel<S, A, N><<<grid, block, 0, stream>>>(image, t, h, w, workspace, lh, pixel_spacing, mean_std, \
                                                            out_stack, out_sum, accumulate_sum)
