@@ -34,6 +34,9 @@ int tmc_version(void);            /* 100 = 0.1.0 */
 const char* tmc_last_error(void); /* thread-local message of the last failing call (host pointer) */
 int tmc_sm_count(void);           /* SM count of the current device, -1 on error */
 long tmc_launch_count(void);      /* kernels launched by this library since load (bench bookkeeping) */
+/* copy nbytes (multiple of 4) from PAGE-LOCKED host memory to device memory with a kernel reading the host mapping:
+ * unlike cudaMemcpyAsync it does not queue behind a large host-to-device copy of a pipelined run */
+int tmc_upload_pinned(const void* host_pinned, void* dst, long nbytes, tmc_stream_t stream);
 
 /* ---- normalize_image statistics: utils.py:49-84 ------------------------------------------------ */
 /* mean and unbiased std of image[:, y0:y1, x0:x1] over ALL frames -> mean_std[2] (device).

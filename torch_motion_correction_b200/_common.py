@@ -62,8 +62,36 @@ def cached_device_tensor(key, build, device: torch.device) -> torch.Tensor:
     return hit
 
 
+_staging: dict = {}
+_STAGING_SLOTS = 4
+
+
 def to_device_async(host_tensor: torch.Tensor, device: torch.device) -> torch.Tensor:
-    """H2D copy through pinned staging memory that does not block the host."""
-    staged = torch.empty(host_tensor.shape, dtype=host_tensor.dtype, pin_memory=True)
-    staged.copy_(host_tensor)
-    return staged.to(device, non_blocking=True)
+    """Small H2D upload that neither blocks the host nor queues behind a large H2D copy on the copy engine (the next
+    movie of a pipelined run): the data is staged in a ring of pinned buffers and copied by a kernel reading the host
+    mapping (tmc_upload_pinned).  A slot is reused only after the upload that read it has completed."""
+    src = host_tensor.contiguous()
+    nbytes = src.numel() * src.element_size()
+    if nbytes % 4 != 0 or nbytes == 0:
+        staged = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+        staged.copy_(src)
+        return staged.to(device, non_blocking=True)
+    key = (device.type, device.index)
+    ring = _staging.setdefault(key, {"next": 0, "slots": [None] * _STAGING_SLOTS})
+    i = ring["next"]
+    ring["next"] = (i + 1) % _STAGING_SLOTS
+    slot = ring["slots"][i]
+    if slot is None or slot[0].numel() < nbytes:
+        if slot is not None:
+            slot[1].synchronize()
+        slot = [torch.empty((max(nbytes, 1 << 16),), dtype=torch.uint8, pin_memory=True), torch.cuda.Event()]
+        ring["slots"][i] = slot
+    else:
+        slot[1].synchronize()  # the previous upload from this slot has run
+    buf, event = slot
+    buf[:nbytes].view(src.dtype).copy_(src.reshape(-1))
+    out = torch.empty(src.shape, dtype=src.dtype, device=device)
+    with torch.cuda.device(device):
+        _lib.call("tmc_upload_pinned", buf.data_ptr(), out.data_ptr(), nbytes, _lib.stream_ptr(device))
+        event.record(torch.cuda.current_stream(device))
+    return out

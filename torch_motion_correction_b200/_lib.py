@@ -29,6 +29,7 @@ _SIGNATURES = {
     "tmc_last_error": (c_char_p, []),
     "tmc_sm_count": (I, []),
     "tmc_launch_count": (L, []),
+    "tmc_upload_pinned": (I, [P, P, L, P]),
     "tmc_stack_stats_workspace_doubles": (I, []),
     "tmc_stack_stats": (I, [P, I, I, I, I, I, I, I, P, P, P]),
     "tmc_stack_moments": (I, [P, I, I, I, I, I, I, I, P, P, P]),
