@@ -137,6 +137,28 @@ def test_correct_motion_ragged_sizes_and_big_shifts(dev, shape):
     assert float((want == 0).float().mean()) > 0.01  # the case really exercises the zero fill
 
 
+@pytest.mark.parametrize("tiled", ["0", "1"])
+@pytest.mark.parametrize("amplitude", [2.0, 40.0])
+def test_correct_motion_shared_memory_tiles(dev, amplitude, tiled, monkeypatch):
+    """With TMC_WARP_TILED=1 images wider than 192 px with 16-byte aligned rows run the interior on the shared-memory
+    tile kernel and the 64-px border strips on the global-memory kernel (rectangle launches): smooth fields (taps
+    inside the staged boxes), and a wild field (boxes leave the image / taps leave the boxes: per-CTA and per-pixel
+    fall-backs), stack and fused sum.  TMC_WARP_TILED=0 (default) is the global-memory kernel alone."""
+    monkeypatch.setenv("TMC_WARP_TILED", tiled)
+    g = torch.Generator().manual_seed(21)
+    img = torch.randn((5, 300, 388), generator=g)
+    field = torch.randn((2, 3, 4, 5), generator=g) * amplitude
+    want = rp.correct_motion(img, field, 1.1, "bspline")
+    got = tmc.correct_motion(img.to(dev), field.to(dev), 1.1, grid_type="bspline")
+    assert rel_l2(got, want) <= REL_L2
+    total = tmc.correct_motion_sum(img.to(dev), field.to(dev), 1.1, grid_type="bspline")
+    assert rel_l2(total, want.sum(dim=0)) <= REL_L2
+    # accumulate into an existing sum (frame blocks of one movie)
+    again = total.clone()
+    tmc.correct_motion_sum(img.to(dev), field.to(dev), 1.1, grid_type="bspline", out=again, accumulate=True)
+    assert rel_l2(again, 2 * want.sum(dim=0)) <= REL_L2
+
+
 def test_frame_split_sum_matches_whole(dev):
     """Frame-split (multi-GPU style) partial sums add up to the whole-movie sum."""
     movie, _ = rp.synthetic_movie(8, 128, 128, seed=5)
