@@ -104,6 +104,14 @@ int tmc_soft_disc_mask(int h, int w, float radius, float smoothing_radius, float
 int tmc_band_weights(int ny, int nx, int ky_count, int kx_count, int ky_start, float low, float high, int use_band,
                      float b_factor, float pixel_size, int use_envelope, float* weight, tmc_stream_t stream);
 
+/* dose-weighted frame sum in Fourier space: examples/ttMotion.py:331-351 + torch_fourier_filter.dose_weight_movie
+ * (Grant & Grigorieff critical exposure).  spec (t, ny, nx/2+1) complex64 -> out (ny, nx/2+1) complex64 =
+ * sum_t spec_t q_t / sqrt(sum_t q_t^2); den2 (ny, nx/2+1) f32 nullable accumulates sum q^2 over frame blocks (then out
+ * accumulates too and only the call with finalize != 0 normalises); frames are frame_offset .. frame_offset + t - 1 */
+int tmc_dose_weighted_sum(const void* spec, int t, int ny, int nx, float pixel_size, float pre_exposure,
+                          float dose_per_frame, float voltage_kv, int frame_offset, void* out, float* den2, int finalize,
+                          tmc_stream_t stream);
+
 /* ---- FFT plans ------------------------------------------------------------------------------------ */
 int tmc_fft_supported_length(int n); /* powers of two in [16, 8192]; any other n in [2, 4096] (Bluestein) */
 long tmc_fft_plan_elems(int n);      /* complex64 elements of a plan buffer, 0 if unsupported */

@@ -283,6 +283,17 @@ def correct_motion_fast(image, deformation_grid):
 # --------------------------------------------------------------------------------------
 
 
+def dose_weight(movie: torch.Tensor, pixel_size: float, pre_exposure: float = 0.0, dose_per_frame: float = 1.0,
+                voltage: float = 300.0):
+    """Dose-weighted sum of an aligned stack, as the reference's example script does it
+    (``examples/ttMotion.py:331-351``): rfft2 (ortho) -> ``dose_weight_movie`` -> irfft2 (ortho) -> sum over frames.
+    PARITY UNPINNED: ``torch_fourier_filter.dose_weight`` is restated in ``oracle/deps.py``."""
+    shape = (movie.shape[-2], movie.shape[-1])
+    dft = torch.fft.rfft2(movie, dim=(-2, -1), norm="ortho")
+    dw = deps.dose_weight_movie(dft, shape, pixel_size, pre_exposure, dose_per_frame, voltage, -1, True, False)
+    return torch.fft.irfft2(dw, s=shape, dim=(-2, -1), norm="ortho").sum(dim=0)
+
+
 def _wrap(peak, n: int):
     return torch.where(peak <= n // 2, peak, peak - n)
 

@@ -264,3 +264,20 @@ def test_polyphase_rows_1024_peaks(dev):
     top = surf.reshape(n, -1).max(dim=1).values
     assert bool((picked >= top - 1e-4 * top.abs()).all()), (got, wy, wx, picked, top)
     assert int(((gy == want // p) & (gx == want % p)).sum()) >= n - 1
+
+
+@pytest.mark.parametrize("shape,voltage", [((6, 96, 128), 300.0), ((5, 300, 256), 200.0), ((7, 64, 90), 300.0)])
+def test_dose_weighted_sum_matches_oracle(dev, shape, voltage, monkeypatch):
+    """tmc.dose_weight (full rfft2 of every frame, exposure-filtered sum in Fourier space, ONE inverse transform)
+    against the example script's per-frame filter + irfft2 + sum; frame blocks accumulate (forced small blocks)."""
+    import sys
+
+    dw_mod = sys.modules["torch_motion_correction_b200.dose_weight"]  # the package attribute of that name is the function
+    g = torch.Generator().manual_seed(31)
+    movie = torch.randn(shape, generator=g) + 3.0
+    want = rp.dose_weight(movie, 0.936, pre_exposure=1.5, dose_per_frame=1.2, voltage=voltage)
+    got = tmc.dose_weight(movie.to(dev), 0.936, pre_exposure=1.5, dose_per_frame=1.2, voltage=voltage).cpu()
+    assert float(torch.linalg.norm(got - want) / torch.linalg.norm(want)) <= 1e-5
+    monkeypatch.setattr(dw_mod, "_BLOCK_BYTES", 2 * shape[1] * (shape[2] // 2 + 1) * 8)
+    blocked = tmc.dose_weight(movie.to(dev), 0.936, pre_exposure=1.5, dose_per_frame=1.2, voltage=voltage).cpu()
+    assert float(torch.linalg.norm(blocked - want) / torch.linalg.norm(want)) <= 1e-5

@@ -105,3 +105,20 @@ def test_circle_mask():
     assert float(m[16, 16 + 12]) == 0.0 or abs(float(m[16, 16 + 11]) - math.cos(math.pi / 2)) < 1e-6
     hard = deps.circle(8, (32, 32), smoothing_radius=0)
     assert set(np.unique(hard.numpy())) == {0.0, 1.0}
+
+
+def test_dose_weight_known_answers():
+    """Exposure filter restated from Grant & Grigorieff: q = 1 at DC, monotonically stronger damping of late frames at
+    high resolution, unit total power (sum_t q_t^2 / norm^2 == 1), and the example-script pipeline is linear."""
+    from oracle import reference_path as rp
+
+    t, h, w = 5, 32, 48
+    ones = torch.ones((t, h, w // 2 + 1), dtype=torch.complex64)
+    q = deps.dose_weight_movie(ones, (h, w), 1.0, 0.0, 2.0, 300.0, -1, True, False).real
+    assert torch.allclose((q**2).sum(dim=0), torch.ones((h, w // 2 + 1)), atol=1e-5)
+    assert torch.allclose(q[:, 0, 0], torch.full((t,), 1 / t**0.5), atol=1e-6)  # DC: every frame weighted equally
+    assert bool((q[0, 5:, 5:] > q[-1, 5:, 5:]).all())  # early frames carry the high resolution
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn((t, h, w), generator=g), torch.randn((t, h, w), generator=g)
+    lhs = rp.dose_weight(a + 2 * b, 1.1, 0.5, 1.0)
+    assert torch.allclose(lhs, rp.dose_weight(a, 1.1, 0.5, 1.0) + 2 * rp.dose_weight(b, 1.1, 0.5, 1.0), atol=1e-4)

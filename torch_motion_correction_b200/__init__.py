@@ -20,6 +20,7 @@ from .deformation_field_utils import (
     resample_deformation_field,
 )
 
+from .dose_weight import dose_weight
 from .data_io import read_deformation_field_from_csv, write_deformation_field_to_csv
 from .estimate_motion_optimizer import estimate_local_motion
 from .estimate_motion_xc import estimate_global_motion, estimate_motion_cross_correlation_patches
@@ -47,4 +48,5 @@ __all__ = [
     "estimate_motion",
     "motion_correct",
     "motion_correct_many",
+    "dose_weight",
 ]

@@ -108,7 +108,8 @@ __device__ __forceinline__ float2 fast_cis(float x) {
 
 // ---- the coefficient kernel -------------------------------------------------------------------------------------------
 // flags: 1 = backward (gradient, loss, re-arm), 2 = Adam update, 4 = shifts of the (updated) coefficients
-// dynamic shared memory (floats): grad_shifts 2GT | eval_base 2GT | W_t T nt | W_sp G nhw | coef 2 nt nhw | u G 2 nt
+// dynamic shared memory (floats): grad_shifts 2GT | eval_base 2GT | W_t T nt | W_sp G nhw | coef 2 nt nhw | u G 2 nt |
+// exp_avg, exp_avg_sq 2 nt nhw each
 // Everything the kernel reads is staged with one batch of independent loads (one memory latency), the rest is
 // shared-memory arithmetic: the kernel sits on the critical path of every iteration.
 __global__ void __launch_bounds__(kCoefThreads) local_coefficient_kernel(const StepParams p, int flags) {
@@ -123,6 +124,8 @@ __global__ void __launch_bounds__(kCoefThreads) local_coefficient_kernel(const S
   float* wsp_s = wt_s + T * nt;
   float* coef_s = wsp_s + G * nhw;
   float* u_s = coef_s + ncoef;
+  float* ea_s = u_s + G * 2 * nt;  // Adam state, staged with everything else
+  float* eas_s = ea_s + ncoef;
   // the next loss kernel may start its prologue (bulk copies of the spectra) now; it waits for this grid to
   // complete before it reads the shifts (programmatic dependent launch)
   asm volatile("griddepcontrol.launch_dependents;");
@@ -134,6 +137,11 @@ __global__ void __launch_bounds__(kCoefThreads) local_coefficient_kernel(const S
   for (int i = tid; i < T * nt; i += kCoefThreads) wt_s[i] = __ldg(p.w_t + i);
   for (int i = tid; i < G * nhw; i += kCoefThreads) wsp_s[i] = __ldg(p.w_sp + i);
   for (int i = tid; i < ncoef; i += kCoefThreads) coef_s[i] = p.coef[i];
+  if (flags & 2)
+    for (int i = tid; i < ncoef; i += kCoefThreads) {
+      ea_s[i] = p.exp_avg[i];
+      eas_s[i] = p.exp_avg_sq[i];
+    }
   double l = 0.0;
   if (flags & 1) {
     // loss = sum_g scale_g l_g(q_g, sum_t A_t)
@@ -181,8 +189,8 @@ __global__ void __launch_bounds__(kCoefThreads) local_coefficient_kernel(const S
         float gr = acc;
         float par = coef_s[o];
         if (p.weight_decay != 0.f) gr = __fadd_rn(gr, __fmul_rn(p.weight_decay, par));
-        const float m = __fadd_rn(p.exp_avg[o], __fmul_rn(w1, __fsub_rn(gr, p.exp_avg[o])));
-        const float v = __fadd_rn(__fmul_rn(p.exp_avg_sq[o], b2), __fmul_rn(w2, __fmul_rn(gr, gr)));
+        const float m = __fadd_rn(ea_s[o], __fmul_rn(w1, __fsub_rn(gr, ea_s[o])));
+        const float v = __fadd_rn(__fmul_rn(eas_s[o], b2), __fmul_rn(w2, __fmul_rn(gr, gr)));
         p.exp_avg[o] = m;
         p.exp_avg_sq[o] = v;
         const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), epsf);
@@ -250,46 +258,51 @@ __global__ void __launch_bounds__(kTileThreads) local_loss_tile_kernel(const Ste
   const float sc = __ldg(p.patch_scale + g);
   const int ty = __ldg(p.tiles + 2 * tile_id), tx = __ldg(p.tiles + 2 * tile_id + 1);
   // frequency factors fp32(-2 pi) * fp32(k * fp32(1/n)) (torch_fourier_shift on torch.fft.fftfreq grids) of the tile's
-  // 8 rows and 16 columns (clamped inside the band box: the padding holds zeros)
-  if (tid >= 224 && tid < 248) {
-    const int r = tid - 224;
-    float f;
-    if (r < kTileKy) {
-      int ky = p.ky_start + min(ty * kTileKy + r, p.KY - 1);
+  // 8 rows and 16 columns (clamped inside the band box: the padding holds zeros); every thread forms the one it needs
+  // for the phase table below, threads 224..247 also publish the table for the gradient factors
+  const int my_r = tid < 128 ? (tid & 7) : kTileKy + (tid & 15);  // phase-table slot of this thread (see the loops below)
+  float my_cf;
+  {
+    if (my_r < kTileKy) {
+      int ky = p.ky_start + min(ty * kTileKy + my_r, p.KY - 1);
       if (ky >= (p.ny + 1) / 2) ky -= p.ny;
       if (ky < -(p.ny / 2)) ky += p.ny;
-      f = __fmul_rn(-6.283185307179586f, __fmul_rn((float)ky, p.inv_ny));
+      my_cf = __fmul_rn(-6.283185307179586f, __fmul_rn((float)ky, p.inv_ny));
     } else {
-      f = __fmul_rn(-6.283185307179586f, __fmul_rn((float)min(tx * kTileKx + r - kTileKy, p.KX - 1), p.inv_nx));
+      my_cf = __fmul_rn(-6.283185307179586f, __fmul_rn((float)min(tx * kTileKx + my_r - kTileKy, p.KX - 1), p.inv_nx));
     }
-    cf[r] = f;
+    if (tid < kTileKy) cf[tid] = my_cf;
+    if (tid >= 128 && tid < 128 + kTileKx) cf[kTileKy + tid - 128] = my_cf;
   }
   sigma[tid] = 0.f;
   // everything above is independent of the coefficient kernel that precedes this launch (programmatic dependent
   // launch): wait for it to complete before touching the shifts and the accumulators
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  for (int i = tid; i < 2 * T; i += THREADS) sh[i] = p.shifts[(long)g * T * 2 + i];
-  __syncthreads();  // barriers initialised; sh, cf complete
   if (sc == 0.f || T < 2) {
     // nothing to add for this patch, but the bulk copies must land before the CTA may retire
+    __syncthreads();  // barriers initialised
     for (int c = 0; c < nchunks; ++c) mbar_wait(bars + c, 0);
     return;
   }
-  // phase factors exp(i c f_y s_y) of the 8 rows (duplicated for the packed arithmetic) and exp(i c f_x s_x) of
-  // the 8 column pairs, every frame
-  for (int i = tid; i < T * 8; i += THREADS) {
-    const int t = i >> 3, r = i & 7;
-    const float2 e = fast_cis(__fmul_rn(cf[r], sh[2 * t]));
-    Ey[i] = make_float4(e.x, e.x, e.y, e.y);
+  // phase factors exp(i c f_y s_y) of the 8 rows (duplicated for the packed arithmetic: threads 0..127, 16 frames per
+  // sweep) and exp(i c f_x s_x) of the 8 column pairs (threads 128..255, 8 frames per sweep), every frame; the shifts
+  // come straight from the coefficient kernel's (G, T, 2) table
+  const float* shg = p.shifts + (long)g * T * 2;
+  if (tid < 128) {
+    for (int t = tid >> 3; t < T; t += 16) {
+      const float2 e = fast_cis(__fmul_rn(my_cf, shg[2 * t]));
+      Ey[t * 8 + my_r] = make_float4(e.x, e.x, e.y, e.y);
+    }
+  } else {
+    const int j = tid & 15;
+    for (int t = (tid - 128) >> 4; t < T; t += 8) {
+      const float2 e = fast_cis(__fmul_rn(my_cf, shg[2 * t + 1]));
+      float* o = reinterpret_cast<float*>(Ex + t * 8 + (j >> 1)) + (j & 1);
+      o[0] = e.x;
+      o[2] = e.y;
+    }
   }
-  for (int i = tid; i < T * 16; i += THREADS) {
-    const int t = i >> 4, j = i & 15;
-    const float2 e = fast_cis(__fmul_rn(cf[kTileKy + j], sh[2 * t + 1]));
-    float* o = reinterpret_cast<float*>(Ex + t * 8 + (j >> 1)) + (j & 1);
-    o[0] = e.x;
-    o[2] = e.y;
-  }
-  __syncthreads();
+  __syncthreads();  // barriers initialised; cf, sigma, Ey, Ex complete
 
   // pass 1 (thread = 2 adjacent columns of one row, every NW-th frame): S_t = FW_t e_t in place, Sigma
   {
@@ -409,7 +422,7 @@ size_t tile_smem_bytes(int t) {
          (size_t)((t + kChunkFrames - 1) / kChunkFrames) * 8;
 }
 size_t coef_smem_bytes(int g, int t, int nt, int nhw) {
-  return ((size_t)4 * g * t + (size_t)t * nt + (size_t)g * nhw + (size_t)2 * nt * nhw + (size_t)g * 2 * nt) * 4;
+  return ((size_t)4 * g * t + (size_t)t * nt + (size_t)g * nhw + (size_t)6 * nt * nhw + (size_t)g * 2 * nt) * 4;
 }
 
 }  // namespace

@@ -83,7 +83,65 @@ __global__ void band_weight_kernel(int ny, int nx, int KY, int KX, int ky_start,
   weight[(long)kyb * KX + kx] = v;
 }
 
+// Dose-weighted frame sum in Fourier space (examples/ttMotion.py:331-351 -> torch_fourier_filter.dose_weight_movie,
+// SURVEY.md A.6): out[ky][kx] = sum_t spec[t][ky][kx] q_t(k) / sqrt(sum_t q_t(k)^2),
+// q_t = exp(-N_t / (2 N_e(k))), N_t = pre_exposure + (t + 1) dose_per_frame, N_e(k) = scale (0.24499 k^-1.6649 + 2.8141),
+// k = |f| / pixel_size in 1/Angstrom.  One thread per bin, frames streamed (coalesced over kx).
+__global__ void dose_weighted_sum_kernel(const float2* __restrict__ spec, int T, int ny, int nx, float pixel_size,
+                                         float pre_exposure, float dose_per_frame, float ne_scale, int frame_offset,
+                                         float2* __restrict__ out_num, float* __restrict__ out_den2, int finalize) {
+  const int kxn = nx / 2 + 1;
+  const int kx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int kyi = blockIdx.y;
+  if (kx >= kxn) return;
+  const int ky = kyi < (ny + 1) / 2 ? kyi : kyi - ny;
+  const float fy = __fmul_rn((float)ky, (float)(1.0 / (double)ny));
+  const float fx = __fmul_rn((float)kx, (float)(1.0 / (double)nx));
+  const float f = __fsqrt_rn(__fadd_rn(__fmul_rn(fy, fy), __fmul_rn(fx, fx)));
+  const float k = fmaxf(__fdiv_rn(f, pixel_size), 1e-10f);
+  const float ne = ne_scale * (0.24499f * powf(k, -1.6649f) + 2.8141f);
+  const long bin = (long)kyi * kxn + kx;
+  float2 num = make_float2(0.f, 0.f);
+  float den2 = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float dose = pre_exposure + dose_per_frame * (float)(frame_offset + t + 1);
+    const float q = expf(-0.5f * dose / ne);
+    const float2 z = spec[(long)t * ny * kxn + bin];
+    num.x = fmaf(q, z.x, num.x);
+    num.y = fmaf(q, z.y, num.y);
+    den2 = fmaf(q, q, den2);
+  }
+  if (out_den2) {  // frame blocks / frame-split ranks accumulate numerator and sum of squares, the last call finalises
+    num.x += out_num[bin].x;
+    num.y += out_num[bin].y;
+    den2 += out_den2[bin];
+    out_den2[bin] = den2;
+  }
+  if (finalize) {
+    const float inv = rsqrtf(den2);
+    num.x *= inv;
+    num.y *= inv;
+  }
+  out_num[bin] = num;
+}
+
 }  // namespace
+
+// spec (t, ny, nx/2+1) complex64 spectra of t frames (frames frame_offset .. of the movie) -> out (ny, nx/2+1) complex64.
+// den2 (ny, nx/2+1) f32 nullable: running sum of q^2 for accumulation over frame blocks (zero it before the first
+// block; then out is accumulated too); finalize != 0 divides by sqrt(sum q^2).  voltage_kv < 300 uses the 0.8 scaling.
+TMC_API int tmc_dose_weighted_sum(const void* spec, int t, int ny, int nx, float pixel_size, float pre_exposure,
+                                  float dose_per_frame, float voltage_kv, int frame_offset, void* out, float* den2,
+                                  int finalize, cudaStream_t stream) {
+  TMC_CHECK_ARG(spec && out && t >= 1 && ny >= 1 && nx >= 2 && pixel_size > 0.f && frame_offset >= 0,
+                "dose_weighted_sum: bad arguments");
+  dim3 grid(tmc_div_up(nx / 2 + 1, 128), ny);
+  dose_weighted_sum_kernel<<<grid, 128, 0, stream>>>((const float2*)spec, t, ny, nx, pixel_size, pre_exposure, dose_per_frame,
+                                                    voltage_kv >= 300.f ? 1.0f : 0.8f, frame_offset, (float2*)out, den2,
+                                                    finalize); tmc_count_launch();
+  TMC_CHECK_LAUNCH("tmc_dose_weighted_sum");
+  return TMC_OK;
+}
 
 // mask (h, w) f32; workspace: h ints.  Non-zero rows lie within |y - h/2| <= radius + smoothing_radius.
 TMC_API int tmc_soft_disc_mask(int h, int w, float radius, float smoothing_radius, float* mask, int* workspace,

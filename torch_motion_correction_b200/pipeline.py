@@ -47,10 +47,21 @@ def estimate_motion(
     return field, centres
 
 
-def motion_correct(image: torch.Tensor, pixel_spacing: float, grid_type: str = "bspline", device=None, **estimate_kwargs):
-    """Estimate + correct: returns ``(aligned frame sum (h, w), field)``."""
+def motion_correct(image: torch.Tensor, pixel_spacing: float, grid_type: str = "bspline", device=None,
+                   dose_per_frame: float | None = None, pre_exposure: float = 0.0, voltage: float = 300.0, **estimate_kwargs):
+    """Estimate + correct: returns ``(aligned frame sum (h, w), field)``.
+
+    With ``dose_per_frame`` (e-/A^2 per frame) the sum is dose weighted (``examples/ttMotion.py:331-351,383-398``:
+    correct -> per-frame exposure filter -> sum), which needs the corrected stack instead of the fused sum."""
     field, _ = estimate_motion(image, pixel_spacing, grid_type=grid_type, device=device, **estimate_kwargs)
-    total = correct_motion_sum(image, field, pixel_spacing, grid_type=grid_type, device=device)
+    if dose_per_frame is None:
+        total = correct_motion_sum(image, field, pixel_spacing, grid_type=grid_type, device=device)
+    else:
+        from .correct_motion import correct_motion
+        from .dose_weight import dose_weight
+
+        corrected = correct_motion(image, field, pixel_spacing, grid_type=grid_type, device=device)
+        total = dose_weight(corrected, pixel_spacing, pre_exposure, dose_per_frame, voltage, device=device)
     return total, field
 
 
