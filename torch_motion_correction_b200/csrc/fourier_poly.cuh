@@ -51,8 +51,10 @@ __device__ __forceinline__ void load_tables(float2* tw_step, float2* tw_comb, co
 
 // ---- forward rows: image window * mask^e (two real signals packed) -> tmp[plane][y][kx < KX] --------
 // MODE 1: frame_b == frame_a with mask powers (1, 2); MODE 2: two frames (or one, frame_b < 0), power 1 each.
+// 3 CTAs per SM (80 registers) pay off for MODE 1 and the inverse (measured -0.3 ms per movie); MODE 2 holds a second
+// image row pair and would spill (+1.2 ms), it stays at 2 CTAs per SM
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, MODE == 1 ? 3 : 2)
 rows_forward_poly(const float* __restrict__ image, int H, int W, const float* __restrict__ mean_std,
                   const float* __restrict__ mask, const int* __restrict__ jobs, int ylo, int yhi, int NY, int KX,
                   const float2* __restrict__ tw, float2* __restrict__ tmp, int rows_per_cta) {
@@ -164,7 +166,7 @@ rows_forward_poly(const float* __restrict__ image, int H, int W, const float* __
 
 // ---- inverse rows + argmax: tmp[item][y][kx] -> partial[item][cta] ------------------------------------
 // CTA = 32 rows (16 row pairs, two per warp); same partial layout as rows_inverse_argmax_p2<1024>.
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 rows_inverse_argmax_poly(const float2* __restrict__ tmp, int NY, int KX, const float2* __restrict__ tw,
                          PeakCandidate* __restrict__ partial) {
   constexpr int N = 1024;

@@ -207,8 +207,11 @@ __device__ __noinline__ float warp_pixel_generic(const float* __restrict__ image
 // Stage 2: one thread = kRows vertically adjacent output pixels of one column; the coordinate chain of a pixel
 // (Angstrom -> px, grid_sample round trip, cubic weights) runs on both axes at once as packed fp32x2 arithmetic
 // and the 8 lattice taps of a frame are shared by the thread's pixels.
+#ifndef TMC_WARP_MINB
+#define TMC_WARP_MINB 1
+#endif
 template <bool WRITE_STACK, bool WRITE_SUM, bool NORMALISE>
-__global__ void __launch_bounds__(kTileX* kTileYGroups)
+__global__ void __launch_bounds__(kTileX* kTileYGroups, TMC_WARP_MINB)
 warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const float* __restrict__ rx, int lh,
                     float pixel_spacing, const float* __restrict__ mean_std, float* __restrict__ out_stack,
                     float* __restrict__ out_sum, int accumulate_sum, int x_begin, int x_end, int y_begin, int y_end) {
