@@ -130,12 +130,14 @@ __global__ void __launch_bounds__(kCoefThreads) local_coefficient_kernel(const S
   // complete before it reads the shifts (programmatic dependent launch)
   asm volatile("griddepcontrol.launch_dependents;");
   const float neg_inv_px = -1.0f / p.pixel_spacing;
-  if (flags & 1)
-    for (int i = tid; i < ngt; i += kCoefThreads) gs_s[i] = p.grad_shifts[i] * neg_inv_px;  // dL/d eval_new = -(1/px) dL/ds
+  // constants first: they do not depend on the loss kernel this launch is a programmatic dependent of
   if (flags & 4)
     for (int i = tid; i < ngt; i += kCoefThreads) eb_s[i] = __ldg(p.eval_base + i);
   for (int i = tid; i < T * nt; i += kCoefThreads) wt_s[i] = __ldg(p.w_t + i);
   for (int i = tid; i < G * nhw; i += kCoefThreads) wsp_s[i] = __ldg(p.w_sp + i);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the preceding loss kernel (and everything before it) is complete
+  if (flags & 1)
+    for (int i = tid; i < ngt; i += kCoefThreads) gs_s[i] = p.grad_shifts[i] * neg_inv_px;  // dL/d eval_new = -(1/px) dL/ds
   for (int i = tid; i < ncoef; i += kCoefThreads) coef_s[i] = p.coef[i];
   if (flags & 2)
     for (int i = tid; i < ncoef; i += kCoefThreads) {
@@ -242,6 +244,9 @@ __global__ void __launch_bounds__(kTileThreads) local_loss_tile_kernel(const Ste
   const int tid = threadIdx.x;
   const int g = blockIdx.y, tile_id = blockIdx.x;
   const int nchunks = (T + kChunkFrames - 1) / kChunkFrames;
+  // the coefficient kernel that follows may be scheduled as soon as every CTA of this grid has started; it waits
+  // for this grid to complete before it reads the accumulators
+  asm volatile("griddepcontrol.launch_dependents;");
 
   if (tid == 0) {
     for (int c = 0; c < nchunks; ++c) mbar_init(bars + c, 1);
@@ -536,6 +541,13 @@ TMC_API int tmc_local_steps(const void* tiled, const int* tiles, int n_tiles, in
   cfg.stream = stream;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  cudaLaunchConfig_t ccfg = {};  // the coefficient kernel as a programmatic dependent of the loss kernel before it
+  ccfg.gridDim = dim3(1);
+  ccfg.blockDim = dim3(kCoefThreads);
+  ccfg.dynamicSmemBytes = csmem;
+  ccfg.stream = stream;
+  ccfg.attrs = attr;
+  ccfg.numAttrs = 1;
   for (int i = 0; i < n_steps; ++i) {
     const int row = first_row + i;
     p.patch_scale = patch_scale + (long)row * g;
@@ -546,7 +558,7 @@ TMC_API int tmc_local_steps(const void* tiled, const int* tiles, int n_tiles, in
     TMC_CUDA(cudaLaunchKernelEx(&cfg, local_loss_tile_kernel, p));
     tmc_count_launch();
     const int last = i == n_steps - 1;
-    local_coefficient_kernel<<<1, kCoefThreads, csmem, stream>>>(p, mode == 0 ? (last ? 3 : 7) : 1);
+    TMC_CUDA(cudaLaunchKernelEx(&ccfg, local_coefficient_kernel, p, mode == 0 ? (last ? 3 : 7) : 1));
     tmc_count_launch();
   }
   TMC_CHECK_LAUNCH("tmc_local_steps");
