@@ -112,6 +112,14 @@ int tmc_dose_weighted_sum(const void* spec, int t, int ny, int nx, float pixel_s
                           float dose_per_frame, float voltage_kv, int frame_offset, void* out, float* den2, int finalize,
                           tmc_stream_t stream);
 
+/* the same exposure filter q_frame / sqrt(sum_t q_t^2) applied per frame to the band-limited spectra of tmc_rfft2_band
+ * (planes 2 job + {0, 1} belong to jobs[job].frame_a / frame_b): additive pre-filter of the patch cross-correlation
+ * (the reference filters with band-pass and B-factor only, estimate_motion_xc.py:338-346).
+ * tables: 2 * ky_count * kx_count floats of scratch; 2 * njobs <= 65535 per call */
+int tmc_dose_filter_spectra(void* spec, const int* jobs, int njobs, int ny, int nx, int ky_count, int kx_count, int ky_start,
+                            int total_frames, float pixel_size, float pre_exposure, float dose_per_frame, float voltage_kv,
+                            float* tables, tmc_stream_t stream);
+
 /* ---- FFT plans ------------------------------------------------------------------------------------ */
 int tmc_fft_supported_length(int n); /* powers of two in [16, 8192]; any other n in [2, 4096] (Bluestein) */
 long tmc_fft_plan_elems(int n);      /* complex64 elements of a plan buffer, 0 if unsupported */

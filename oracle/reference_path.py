@@ -386,8 +386,13 @@ def estimate_motion_cross_correlation_patches(
     reject_outliers: bool = True,
     outlier_threshold: float = 3.0,
     return_raw: bool = False,
+    dose=None,
 ):
-    """estimate_motion_xc.py:138-411 incl. Q1 (aliased cache), Q2/Q3 pre-correction, Q4."""
+    """estimate_motion_xc.py:138-411 incl. Q1 (aliased cache), Q2/Q3 pre-correction, Q4.
+
+    ``dose = (pre_exposure, dose_per_frame, voltage)`` (NOT in the reference; additive option of the B200 build,
+    parity unpinned): every frame's masked patch spectra are multiplied by ``dose_weight_movie``'s exposure filter
+    before the leave-one-out mean (formed in Fourier space, which is the same linear operation) and the product."""
     t, h, w = image.shape
     if reference_frame is None:
         reference_frame = t // 2
@@ -424,13 +429,30 @@ def estimate_motion_cross_correlation_patches(
         return state[j]
 
     raw = torch.zeros((2, t, gh, gw))
+    q = None
+    if dose is not None:
+        ones = torch.ones((t, p, p // 2 + 1), dtype=torch.complex64)
+        q = deps.dose_weight_movie(ones, (p, p), pixel_spacing, dose[0], dose[1], dose[2], -1, True, False).real
     for k in range(t):
+        rf_dose = None
         if reference_strategy == "middle_frame":
             if k == reference_frame:
                 continue
             ref = fetch(reference_frame)
             ref *= mask  # in place on the cached tensor (Q1)
             ref_m = ref
+            if q is not None:
+                rf_dose = torch.fft.rfftn(ref_m, dim=(-2, -1)) * q[reference_frame]
+        elif reference_strategy == "mean_except_current" and q is not None:
+            acc_f, count = None, 0
+            for j in range(t):
+                if j == k:
+                    continue
+                term = torch.fft.rfftn(fetch(j) * mask, dim=(-2, -1)) * q[j]
+                acc_f = term if acc_f is None else acc_f + term
+                count += 1
+            rf_dose = acc_f / count
+            ref_m = None
         elif reference_strategy == "mean_except_current":
             acc, count = None, 0
             for j in range(t):
@@ -444,8 +466,12 @@ def estimate_motion_cross_correlation_patches(
             raise ValueError(f"Unknown reference_strategy: {reference_strategy}")
         cur = fetch(k)
         cur *= mask  # Q1: mutates the cache entry
-        rf = torch.fft.rfftn(ref_m, dim=(-2, -1)) * band * env
-        ff = torch.fft.rfftn(cur, dim=(-2, -1)) * band * env
+        if rf_dose is not None:
+            rf = rf_dose * band * env
+            ff = torch.fft.rfftn(cur, dim=(-2, -1)) * band * env * q[k]
+        else:
+            rf = torch.fft.rfftn(ref_m, dim=(-2, -1)) * band * env
+            ff = torch.fft.rfftn(cur, dim=(-2, -1)) * band * env
         cc = torch.fft.irfftn(torch.conj(rf) * ff, s=(p, p)).reshape(gh * gw, p, p)
         peak = torch.argmax(cc.reshape(gh * gw, -1), dim=1)
         if sub_pixel:

@@ -281,3 +281,20 @@ def test_dose_weighted_sum_matches_oracle(dev, shape, voltage, monkeypatch):
     monkeypatch.setattr(dw_mod, "_BLOCK_BYTES", 2 * shape[1] * (shape[2] // 2 + 1) * 8)
     blocked = tmc.dose_weight(movie.to(dev), 0.936, pre_exposure=1.5, dose_per_frame=1.2, voltage=voltage).cpu()
     assert float(torch.linalg.norm(blocked - want) / torch.linalg.norm(want)) <= 1e-5
+
+
+@pytest.mark.parametrize("strategy", ["mean_except_current", "middle_frame"])
+def test_xc_patches_exposure_prefilter(dev, golden_small, strategy):
+    """Additive option: per-frame exposure (dose) weights on the patch spectra before the leave-one-out sums and the
+    cross-correlation, against the oracle restatement with the same filter; the filter really changes the estimate."""
+    g = golden_small
+    movie = torch.as_tensor(g["movie"])
+    px, fr = float(g["pixel_spacing"]), tuple(float(v) for v in g["frequency_range"])
+    kw = dict(reference_strategy=strategy, patch_sidelength=32, frequency_range=fr)
+    want, _ = rp.estimate_motion_cross_correlation_patches(movie, px, smooth=False, reject_outliers=False, dose=(0.5, 4.0, 300.0), **kw)
+    got, _ = tmc.estimate_motion_cross_correlation_patches(
+        movie.to(dev), px, temporal_smoothing=False, outlier_rejection=False, dose_per_frame=4.0, pre_exposure=0.5, **kw
+    )
+    assert float((got.cpu() - want).abs().max()) <= SHIFT_PX * px
+    plain = torch.as_tensor(g[f"xc_raw_{strategy}"])
+    assert float((want - plain).abs().max()) > 1e-4

@@ -133,6 +133,20 @@ class BandPlan:
                      ptr(self.tw_x), ptr(self.tw_y), ptr(tmp), out_base + 2 * j0 * self.plane_elems * _C64, stream)
         return out
 
+    def dose_filter(self, spec: torch.Tensor, jobs: torch.Tensor, total_frames: int, pixel_size: float, pre_exposure: float,
+                    dose_per_frame: float, voltage: float) -> None:
+        """In place: plane 2 job + {0, 1} of ``spec`` *= exposure filter of jobs[job].frame_a / frame_b."""
+        njobs = jobs.shape[0]
+        dev = spec.device
+        tables = torch.empty((2, self.ky, self.kx), dtype=torch.float32, device=dev)
+        chunk = 32000
+        with torch.cuda.device(dev):
+            for j0 in range(0, njobs, chunk):
+                n = min(chunk, njobs - j0)
+                call("tmc_dose_filter_spectra", spec.data_ptr() + 2 * j0 * self.plane_elems * _C64, jobs.data_ptr() + j0 * 6 * 4, n,
+                     self.ny, self.nx, self.ky, self.kx, self.ky_start, int(total_frames), float(pixel_size), float(pre_exposure),
+                     float(dose_per_frame), float(voltage), ptr(tables), stream_ptr(dev))
+
     # -- inverse + peak ---------------------------------------------------------------------------
     def peaks(self, prod: torch.Tensor, sub_pixel: bool, shifts=None):
         """prod (nitems, KY, KX, 2) -> (nitems, 2) px shifts (dy, dx)."""

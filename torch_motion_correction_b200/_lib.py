@@ -60,6 +60,7 @@ _SIGNATURES = {
     "tmc_fourier_shift_frames": (I, [P, I, I, I, P, P, I, P, F, P, P, P, P, P, P]),
     "tmc_soft_disc_mask": (I, [I, I, F, F, P, P, P]),
     "tmc_band_weights": (I, [I, I, I, I, I, F, F, I, F, F, I, P, P]),
+    "tmc_dose_filter_spectra": (I, [P, P, I, I, I, I, I, I, I, F, F, F, F, P, P]),
     "tmc_dose_weighted_sum": (I, [P, I, I, I, F, F, F, F, I, P, P, I, P]),
     "tmc_xc_postprocess": (I, [P, I, I, F, I, I, F, I, I, I, P, P, P]),
     "tmc_global_shifts_to_field": (I, [P, I, F, I, P, P]),

@@ -125,7 +125,70 @@ __global__ void dose_weighted_sum_kernel(const float2* __restrict__ spec, int T,
   out_num[bin] = num;
 }
 
+// ---- exposure (dose) weights as a per-frame pre-filter of band-limited patch spectra ------------------------------------
+// ne[kyb][kx] = N_e(k) and inv_norm[kyb][kx] = 1 / sqrt(sum_t q_t(k)^2) on the band box (ky = ky_start + kyb)
+__global__ void dose_tables_kernel(int ny, int nx, int KY, int KX, int ky_start, int T, float pixel_size, float pre_exposure,
+                                   float dose_per_frame, float ne_scale, float* __restrict__ ne_out, float* __restrict__ inv_norm) {
+  const int kx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int kyb = blockIdx.y;
+  if (kx >= KX) return;
+  int ky = ky_start + kyb;
+  ky = ((ky % ny) + ny) % ny;
+  if (ky >= (ny + 1) / 2) ky -= ny;
+  const float fy = __fmul_rn((float)ky, (float)(1.0 / (double)ny));
+  const float fx = __fmul_rn((float)kx, (float)(1.0 / (double)nx));
+  const float f = __fsqrt_rn(__fadd_rn(__fmul_rn(fy, fy), __fmul_rn(fx, fx)));
+  const float k = fmaxf(__fdiv_rn(f, pixel_size), 1e-10f);
+  const float ne = ne_scale * (0.24499f * powf(k, -1.6649f) + 2.8141f);
+  float den2 = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float q = expf(-0.5f * (pre_exposure + dose_per_frame * (float)(t + 1)) / ne);
+    den2 = fmaf(q, q, den2);
+  }
+  ne_out[(long)kyb * KX + kx] = ne;
+  inv_norm[(long)kyb * KX + kx] = rsqrtf(den2);
+}
+
+// spec plane p (p = 2 job + {0: frame_a, 1: frame_b}) *= q_frame(k) / sqrt(sum_t q_t^2)
+__global__ void dose_filter_spectra_kernel(float2* __restrict__ spec, const int* __restrict__ jobs, long bins,
+                                           const float* __restrict__ ne, const float* __restrict__ inv_norm, float pre_exposure,
+                                           float dose_per_frame) {
+  const long bin = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int plane = blockIdx.y;
+  if (bin >= bins) return;
+  const int frame = jobs[(plane >> 1) * 6 + ((plane & 1) ? 2 : 0)];
+  if (frame < 0) return;
+  const float q = expf(-0.5f * (pre_exposure + dose_per_frame * (float)(frame + 1)) / __ldg(ne + bin)) * __ldg(inv_norm + bin);
+  float2* z = spec + (long)plane * bins + bin;
+  const float2 v = *z;
+  *z = make_float2(v.x * q, v.y * q);
+}
+
 }  // namespace
+
+// Exposure filter of torch_fourier_filter.dose_weight_movie applied per frame to the band-limited
+// spectra of tmc_rfft2_band (planes 2 job + {0,1} <-> jobs[job].frame_a / frame_b): an additive pre-filter of the
+// patch cross-correlation (the reference filters with band-pass and B-factor only, estimate_motion_xc.py:338-346).
+// tables: 2 * ky_count * kx_count floats of scratch; total_frames = frames of the movie (normalisation).
+TMC_API int tmc_dose_filter_spectra(void* spec, const int* jobs, int njobs, int ny, int nx, int ky_count, int kx_count,
+                                    int ky_start, int total_frames, float pixel_size, float pre_exposure, float dose_per_frame,
+                                    float voltage_kv, float* tables, cudaStream_t stream) {
+  TMC_CHECK_ARG(spec && jobs && tables && njobs >= 1 && ky_count >= 1 && kx_count >= 1 && total_frames >= 1 && pixel_size > 0.f,
+                "dose_filter_spectra: bad arguments");
+  const long bins = (long)ky_count * kx_count;
+  {
+    dim3 grid(tmc_div_up(kx_count, 128), ky_count);
+    dose_tables_kernel<<<grid, 128, 0, stream>>>(ny, nx, ky_count, kx_count, ky_start, total_frames, pixel_size, pre_exposure,
+                                                dose_per_frame, voltage_kv >= 300.f ? 1.0f : 0.8f, tables, tables + bins);
+    tmc_count_launch();
+  }
+  TMC_CHECK_ARG(2l * njobs <= 65535, "dose_filter_spectra: too many planes for one launch (chunk the jobs)");
+  dim3 grid(tmc_div_up(bins, 256), 2 * njobs);
+  dose_filter_spectra_kernel<<<grid, 256, 0, stream>>>((float2*)spec, jobs, bins, tables, tables + bins, pre_exposure,
+                                                      dose_per_frame); tmc_count_launch();
+  TMC_CHECK_LAUNCH("tmc_dose_filter_spectra");
+  return TMC_OK;
+}
 
 // spec (t, ny, nx/2+1) complex64 spectra of t frames (frames frame_offset .. of the movie) -> out (ny, nx/2+1) complex64.
 // den2 (ny, nx/2+1) f32 nullable: running sum of q^2 for accumulation over frame blocks (zero it before the first

@@ -122,8 +122,15 @@ def estimate_motion_cross_correlation_patches(
     outlier_rejection: bool = True,
     outlier_threshold: float = 3.0,
     device: torch.device = None,
+    dose_per_frame: float | None = None,
+    pre_exposure: float = 0.0,
+    voltage: float = 300.0,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """Patch-wise Fourier cross-correlation -> ((2, t, gh, gw) Angstrom field, (t, gh, gw, 3) centres).
+
+    ``dose_per_frame`` (additive, default off = the reference's behaviour): every frame's patch spectra are also
+    multiplied by the exposure filter ``q_t / sqrt(sum_t q_t^2)`` (Grant & Grigorieff; the filter the reference's
+    example applies to the corrected stack) before the leave-one-out sums and the cross-correlation.
 
     Reference: estimate_motion_xc.py:138-411, including the result-changing quirks Q1 (cached patches
     are masked in place, so earlier frames enter later references double-masked), Q2/Q3 (rigid
@@ -170,6 +177,8 @@ def estimate_motion_cross_correlation_patches(
             ("xc_jobs_mean", geometry),
             lambda: torch.tensor([[k, 1, k, 2, y0, x0] for k in range(t) for (y0, x0) in origins], dtype=torch.int32), dev)
         spec = plan.forward(source, source_stats, mask, ylo, yhi, jobs, job_mode=1)
+        if dose_per_frame is not None:
+            plan.dose_filter(spec, jobs, t, pixel_spacing, pre_exposure, dose_per_frame, voltage)
 
         def schedule(part):
             offsets, deltas = _aliasing_schedule(t, reference_strategy, reference_frame)
@@ -189,6 +198,8 @@ def estimate_motion_cross_correlation_patches(
 
         jobs = cached_device_tensor(("xc_jobs_middle", (t, h, w, p), int(reference_frame)), middle_jobs, dev)
         spec = plan.forward(source, source_stats, mask, ylo, yhi, jobs)
+        if dose_per_frame is not None:
+            plan.dose_filter(spec, jobs, t, pixel_spacing, pre_exposure, dose_per_frame, voltage)
         items = torch.arange(t * n_patches, dtype=torch.int32, device=dev)
         prod = _fourier.pair_products(spec, 2 * items + 1, 2 * items, plan.plane_elems)
     shifts = plan.peaks(prod.view(t * n_patches, plan.ky, plan.kx, 2), sub_pixel=bool(sub_pixel_refinement))

@@ -23,8 +23,13 @@ def estimate_motion(
     grid_type: str = "bspline",
     optimizer_kwargs: dict | None = None,
     device: torch.device = None,
+    dose_per_frame: float | None = None,
+    pre_exposure: float = 0.0,
+    voltage: float = 300.0,
 ):
     """Returns ``(field (2, nt, nh, nw) Angstrom, patch_centres)``.
+
+    ``dose_per_frame`` switches on the exposure pre-filter of the patch cross-correlation.
 
     With ``n_iterations > 0`` the patch-XC field initialises ``estimate_local_motion`` on a
     ``deformation_field_resolution`` spline grid (default (3, 5, 5), BASELINE config 2)."""
@@ -33,7 +38,7 @@ def estimate_motion(
     )
     field, centres = estimate_motion_cross_correlation_patches(
         image, pixel_spacing, b_factor=b_factor, frequency_range=frequency_range, patch_sidelength=patch_sidelength,
-        deformation_field=global_field, device=device,
+        deformation_field=global_field, device=device, dose_per_frame=dose_per_frame, pre_exposure=pre_exposure, voltage=voltage,
     )
     if n_iterations > 0:
         from .estimate_motion_optimizer import estimate_local_motion
@@ -51,9 +56,11 @@ def motion_correct(image: torch.Tensor, pixel_spacing: float, grid_type: str = "
                    dose_per_frame: float | None = None, pre_exposure: float = 0.0, voltage: float = 300.0, **estimate_kwargs):
     """Estimate + correct: returns ``(aligned frame sum (h, w), field)``.
 
-    With ``dose_per_frame`` (e-/A^2 per frame) the sum is dose weighted (``examples/ttMotion.py:331-351,383-398``:
-    correct -> per-frame exposure filter -> sum), which needs the corrected stack instead of the fused sum."""
-    field, _ = estimate_motion(image, pixel_spacing, grid_type=grid_type, device=device, **estimate_kwargs)
+    With ``dose_per_frame`` (e-/A^2 per frame) the patch cross-correlation is exposure pre-filtered and the sum is dose
+    weighted (``examples/ttMotion.py:331-351,383-398``: correct -> per-frame exposure filter -> sum), which needs the
+    corrected stack instead of the fused sum."""
+    field, _ = estimate_motion(image, pixel_spacing, grid_type=grid_type, device=device, dose_per_frame=dose_per_frame,
+                               pre_exposure=pre_exposure, voltage=voltage, **estimate_kwargs)
     if dose_per_frame is None:
         total = correct_motion_sum(image, field, pixel_spacing, grid_type=grid_type, device=device)
     else:
