@@ -414,11 +414,14 @@ def main():
         import glob
 
         for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full_kernels.csv")), reverse=True):
-            hit = [r for r in csv.DictReader(open(path)) if r["kernel"].startswith(kname)]
-            if hit and hit[0].get("dram_read_MB"):
-                roof["traffic"] = int((float(hit[0]["dram_read_MB"]) + float(hit[0]["dram_write_MB"] or 0)) * 1e6)
-                roof["traffic_source"] = os.path.basename(path)
-                break
+            try:
+                hit = [r for r in csv.DictReader(open(path)) if r["kernel"].startswith(kname)]
+                if hit and hit[0].get("dram_read_MB"):
+                    roof["traffic"] = int((float(hit[0]["dram_read_MB"]) + float(hit[0]["dram_write_MB"] or 0)) * 1e6)
+                    roof["traffic_source"] = os.path.basename(path)
+                    break
+            except Exception:  # a malformed summary must not break the benchmark line
+                continue
     else:
         roof.update(kernel=kernel_names.get(dominant, dominant), achieved=None, frac=None)
     breakdown = {k: round(v, 4) for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1])}

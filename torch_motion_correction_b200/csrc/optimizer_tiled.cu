@@ -55,7 +55,6 @@ struct StepParams {
   float* shifts;       // (G, T, 2) px, written by the coefficient kernel
   float* grad_shifts;  // (G, T, 2) accumulator, zero on entry, zero on exit
   double* q;           // (G) accumulator, zero on entry, zero on exit
-  float* gu;           // (G, 2, nt) scratch
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -224,7 +223,7 @@ __global__ void __launch_bounds__(kCoefThreads) local_coefficient_kernel(const S
 
 // ---- the loss / gradient kernel ---------------------------------------------------------------------------------------
 // dynamic shared memory (floats): tile T*256 (re[128] | im[128] per frame) | Ey T*8 float4 (c,c,s,s) |
-// Ex T*8 float4 (c0,c1,s0,s1) per column pair | Cy, Cx 64 float4 each | sigma 256 | sh 2T | cf 24 | red | bars
+// Ex T*8 float4 (c0,c1,s0,s1) per column pair | Cy, Cx 64 float4 each | sigma 256 | cf 24 | red | bars
 __global__ void __launch_bounds__(kTileThreads) local_loss_tile_kernel(const StepParams p) {
   constexpr int THREADS = kTileThreads;
   constexpr int NW = THREADS / 64;  // frame interleave of pass 1 (thread = 2 adjacent kx bins)
@@ -236,8 +235,7 @@ __global__ void __launch_bounds__(kTileThreads) local_loss_tile_kernel(const Ste
   float4* Cy = Ex + T * 8;                                        // [64] (cfy w Sig_re x2, -cfy w Sig_im x2)
   float4* Cx = Cy + 64;                                           // [64] the same with cfx
   float* sigma = reinterpret_cast<float*>(Cx + 64);               // [4][64]: re even / re odd / im even / im odd columns
-  float* sh = sigma + 256;                                        // [T][2]
-  float* cf = sh + ((2 * T + 3) & ~3);                            // [24]
+  float* cf = sigma + 256;                                        // [24]
   double* red = reinterpret_cast<double*>(cf + 24);               // [2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 2);          // [nchunks]
 
@@ -423,7 +421,7 @@ __global__ void tile_spectra_kernel(const float2* __restrict__ spec, int T, int 
 }
 
 size_t tile_smem_bytes(int t) {
-  return (size_t)t * kTileBins * 8 + (size_t)t * 16 * 16 + 128 * 16 + 256 * 4 + (size_t)((2 * t + 3) & ~3) * 4 + 24 * 4 + 2 * 8 +
+  return (size_t)t * kTileBins * 8 + (size_t)t * 16 * 16 + 128 * 16 + 256 * 4 + 24 * 4 + 2 * 8 +
          (size_t)((t + kChunkFrames - 1) / kChunkFrames) * 8;
 }
 size_t coef_smem_bytes(int g, int t, int nt, int nhw) {
@@ -451,9 +449,10 @@ TMC_API int tmc_local_tile_spectra(const void* spec, int g, int t, int tp, int k
   return TMC_OK;
 }
 
-// workspace of tmc_local_steps: shifts 2*g*t | grad_shifts 2*g*t | gu 2*g*nt floats | q g doubles
+// workspace of tmc_local_steps: shifts 2*g*t | grad_shifts 2*g*t floats | q g doubles
 TMC_API long tmc_local_steps_workspace_bytes(int g, int t, int nt) {
-  long floats = 4l * g * t + 2l * g * nt;
+  (void)nt;
+  long floats = 4l * g * t;
   floats = (floats + 1) & ~1l;
   return floats * 4 + 8l * g;
 }
@@ -516,8 +515,7 @@ TMC_API int tmc_local_steps(const void* tiled, const int* tiles, int n_tiles, in
   float* wf = (float*)workspace;
   p.shifts = wf;
   p.grad_shifts = wf + 2l * g * t;
-  p.gu = wf + 4l * g * t;
-  const long floats = (4l * g * t + 2l * g * nt + 1) & ~1l;
+  const long floats = (4l * g * t + 1) & ~1l;
   p.q = (double*)(wf + floats);
   TMC_CUDA(cudaMemsetAsync(workspace, 0, (size_t)tmc_local_steps_workspace_bytes(g, t, nt), stream));
   const size_t smem = tile_smem_bytes(t), csmem = coef_smem_bytes(g, t, nt, nhw);
