@@ -65,7 +65,7 @@ class LocalMotionProblem:
     their norms, normalised patch centres and the frozen base grid's values at the centres."""
 
     def __init__(self, image, pixel_spacing, patch_shape, resolution, initial_field, dev, b_factor, frequency_range,
-                 grid_type, loss_type):
+                 grid_type, loss_type, stats=None):
         if loss_type not in LOSS_TYPES:
             raise ValueError(f"Invalid loss type: {loss_type}. Must be 'mse', 'cc' or 'ncc'.")
         self.kind = grid_kind(grid_type)
@@ -77,7 +77,8 @@ class LocalMotionProblem:
         ph, pw = patch_shape
         self.t, self.ph, self.pw = t, ph, pw
         self.resolution = tuple(int(r) for r in resolution)
-        stats = _ops.stack_stats(movie)
+        if stats is None:
+            stats = _ops.stack_stats(movie)
         centers = patch_grid_centers((t, h, w), (1, ph, pw), (1, ph // 2, pw // 2), distribute_patches=True)
         self.centers = centers
         gh, gw = centers.shape[1:3]
@@ -306,6 +307,7 @@ def estimate_local_motion(
     optimizer_kwargs: dict | None = None,
     return_trajectory: bool = False,
     trajectory_kwargs: dict | None = None,
+    _stats: torch.Tensor | None = None,
 ) -> torch.Tensor | tuple[torch.Tensor, OptimizationTracker]:
     """Optimise a learnable (2, nt, nh, nw) spline grid added to a frozen base grid so that the
     Fourier-shifted patches of every frame agree with the mean of the other frames.
@@ -320,7 +322,7 @@ def estimate_local_motion(
         trajectory = OptimizationTracker(**trajectory_kwargs)
     problem = LocalMotionProblem(
         image, pixel_spacing, patch_shape, deformation_field_resolution, initial_deformation_field, dev, b_factor,
-        frequency_range, grid_type, loss_type,
+        frequency_range, grid_type, loss_type, stats=_stats,
     )
     kwargs = dict(optimizer_kwargs) if optimizer_kwargs is not None else {}
     new = torch.nn.Parameter(torch.zeros((2, *problem.resolution), dtype=torch.float32, device=dev))

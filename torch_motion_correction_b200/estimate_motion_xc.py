@@ -23,6 +23,7 @@ def estimate_global_motion(
     b_factor: float = 500,
     frequency_range: tuple[float, float] = (300, 10),
     device: torch.device = None,
+    _stats: torch.Tensor | None = None,
 ) -> torch.Tensor:
     """Integer-pixel whole-frame cross-correlation against one frame -> (2, t, 1, 1) Angstrom field.
 
@@ -32,7 +33,7 @@ def estimate_global_motion(
     t, h, w = movie.shape
     if reference_frame is None:
         reference_frame = t // 2
-    stats = _ops.stack_stats(movie)
+    stats = _stats if _stats is not None else _ops.stack_stats(movie)  # _stats: the pipeline computes them once per movie
     plan = _fourier.BandPlan(h, w, dev, pixel_spacing, b_factor, frequency_range)
     mask, ylo, yhi = _fourier.soft_disc_mask((h, w), min(h, w) / 4, min(h, w) / 8, dev)
     spec = plan.forward(movie, stats, mask, ylo, yhi, _fourier.frame_pair_jobs(t, dev), job_mode=2)
@@ -125,6 +126,7 @@ def estimate_motion_cross_correlation_patches(
     dose_per_frame: float | None = None,
     pre_exposure: float = 0.0,
     voltage: float = 300.0,
+    _stats: torch.Tensor | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """Patch-wise Fourier cross-correlation -> ((2, t, gh, gw) Angstrom field, (t, gh, gw, 3) centres).
 
@@ -145,7 +147,7 @@ def estimate_motion_cross_correlation_patches(
         raise ValueError(f"Unknown reference_strategy: {reference_strategy}")
     if reference_strategy == "mean_except_current" and t < 2:
         raise ValueError("mean_except_current needs at least two frames")
-    stats = _ops.stack_stats(movie)
+    stats = _stats if _stats is not None else _ops.stack_stats(movie)  # _stats: the pipeline computes them once per movie
 
     source, source_stats = movie, stats  # patches are read from here, normalised on load
     if deformation_field is not None:

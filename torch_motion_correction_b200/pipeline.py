@@ -33,12 +33,19 @@ def estimate_motion(
 
     With ``n_iterations > 0`` the patch-XC field initialises ``estimate_local_motion`` on a
     ``deformation_field_resolution`` spline grid (default (3, 5, 5), BASELINE config 2)."""
+    # normalisation statistics of the movie: computed once, shared by the three estimators (the reference's
+    # normalize_image recomputes them in each, utils.py:49-84)
+    from . import _ops
+    from ._common import as_f32, resolve_device
+
+    stats = _ops.stack_stats(as_f32(image, resolve_device(image, device)))
     global_field = estimate_global_motion(
-        image, pixel_spacing, b_factor=b_factor, frequency_range=frequency_range, device=device
+        image, pixel_spacing, b_factor=b_factor, frequency_range=frequency_range, device=device, _stats=stats
     )
     field, centres = estimate_motion_cross_correlation_patches(
         image, pixel_spacing, b_factor=b_factor, frequency_range=frequency_range, patch_sidelength=patch_sidelength,
         deformation_field=global_field, device=device, dose_per_frame=dose_per_frame, pre_exposure=pre_exposure, voltage=voltage,
+        _stats=stats,
     )
     if n_iterations > 0:
         from .estimate_motion_optimizer import estimate_local_motion
@@ -47,7 +54,7 @@ def estimate_motion(
         field = estimate_local_motion(
             image, pixel_spacing, (patch_sidelength, patch_sidelength), resolution, field, device=device,
             n_iterations=n_iterations, b_factor=b_factor, frequency_range=frequency_range, grid_type=grid_type,
-            optimizer_kwargs=optimizer_kwargs,
+            optimizer_kwargs=optimizer_kwargs, _stats=stats,
         )
     return field, centres
 
