@@ -187,9 +187,12 @@ int tmc_subtract_mean(float* data, long n, tmc_stream_t stream);
 
 /* ---- spline-coefficient optimiser: estimate_motion_optimizer.py:371-407,442-510,611-671 -------------- */
 /* spec (g, tp, ky_count, kx_count): band-limited filtered spectra of every patch and frame (tp >= t planes
- * per patch).  norms (g, t, 2) float64 = sum_f w |spec|^2 for w = 1 and Hermitian weights. */
+ * per patch); with frame_major != 0 the planes are ordered (tp / 2, g, 2, ...) instead, i.e. as tmc_rfft2_band writes
+ * them for frame-pair jobs listed frame pair by frame pair (every frame is then read from HBM once: the overlapping
+ * patches of a frame pair run back to back and hit L2).  norms (g, t, 2) float64 = sum_f w |spec|^2 for w = 1 and
+ * Hermitian weights. */
 int tmc_local_spectra_norms(const void* spec, int g, int t, int tp, int ny, int nx, int ky_count, int kx_count,
-                            int ky_start, double* norms, tmc_stream_t stream);
+                            int ky_start, int frame_major, double* norms, tmc_stream_t stream);
 long tmc_local_loss_workspace_bytes(int g, int t, int ky_count, int kx_count);
 /* one loss + gradient evaluation: eval_new / eval_base (t, g, 2) spline values (Angstrom) at the patch
  * centres; patch_scale (g): weight of each patch's mean-reduced mini-batch loss; loss_type 0 mse, 1 cc,
@@ -213,10 +216,11 @@ int tmc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
  * tmc_local_loss_grad) */
 int tmc_local_steps_supported(int g, int t, int nt, int nhw);
 /* re-lay spec (g, tp, ky_count, kx_count) complex64 into tiles of 8 (ky) x 16 (kx) bins with the t frames of a tile
- * contiguous, real and imaginary parts in separate planes: out (g, n_tiles, t, 2, 128) float32, zero padded;
+ * contiguous, real and imaginary parts in separate planes: out (g, n_tiles, t, 2, 128) float32, zero padded
+ * (frame_major: plane order of spec as for tmc_local_spectra_norms);
  * tiles (n_tiles, 2) int32 = (ty, tx) lists the tiles that hold at least one pass-band bin */
 int tmc_local_tile_spectra(const void* spec, int g, int t, int tp, int ky_count, int kx_count, const int* tiles,
-                           int n_tiles, void* out, tmc_stream_t stream);
+                           int n_tiles, int frame_major, void* out, tmc_stream_t stream);
 long tmc_local_steps_workspace_bytes(int g, int t, int nt);
 /* n_steps iterations (1 + 2 n_steps launches).  sum_norms (g) double = sum_t A_t; eval_base (t, g, 2) Angstrom; w_t (t, nt)
  * and w_sp (g, nhw): dense separable spline weights of the patch centres (time / space); patch_scale (rows, g), step i

@@ -65,13 +65,13 @@ _SIGNATURES = {
     "tmc_xc_postprocess": (I, [P, I, I, F, I, I, F, I, I, I, P, P, P]),
     "tmc_global_shifts_to_field": (I, [P, I, F, I, P, P]),
     "tmc_subtract_mean": (I, [P, L, P]),
-    "tmc_local_spectra_norms": (I, [P, I, I, I, I, I, I, I, I, P, P]),
+    "tmc_local_spectra_norms": (I, [P, I, I, I, I, I, I, I, I, I, P, P]),
     "tmc_local_loss_workspace_bytes": (L, [I, I, I, I]),
     "tmc_local_loss_grad": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, I, P, P, P, P]),
     "tmc_advance_counter": (I, [P, P]),
     "tmc_adam_step": (I, [P, P, P, P, I, D, D, D, D, D, P, P]),
     "tmc_local_steps_supported": (I, [I, I, I, I]),
-    "tmc_local_tile_spectra": (I, [P, I, I, I, I, I, P, I, P, P]),
+    "tmc_local_tile_spectra": (I, [P, I, I, I, I, I, P, I, I, P, P]),
     "tmc_local_steps_workspace_bytes": (L, [I, I, I]),
     "tmc_local_steps": (I, [P, P, I, I, I, I, I, I, I, I, P, P, P, P, I, I, P, F, I, P, P, P, D, D, D, D, D, I, I, I, P, P,
                             P, P]),

@@ -52,8 +52,9 @@ __device__ __forceinline__ void block_accumulate(double v, double* target, doubl
 
 // A[g][t] = sum_f w |FW_t|^2 for both weightings: norms[(g*T + t)*2 + {0: w=1, 1: hermitian}]
 __global__ void __launch_bounds__(kOptThreads)
-spectra_norms_kernel(const float2* __restrict__ spec, int T, int Tp, BandGeom geom, double* __restrict__ norms) {
-  const int g = blockIdx.y;
+spectra_norms_kernel(const float2* __restrict__ spec, int T, int Tp, BandGeom geom, int frame_major,
+                     double* __restrict__ norms) {
+  const int g = blockIdx.y, G = gridDim.y;
   const int bins = geom.KY * geom.KX;
   const int bin = blockIdx.x * kOptThreads + threadIdx.x;
   float cfy, cfx, herm = 0.f;
@@ -62,7 +63,9 @@ spectra_norms_kernel(const float2* __restrict__ spec, int T, int Tp, BandGeom ge
   for (int t = 0; t < T; ++t) {
     double v = 0.0;
     if (live) {
-      const float2 z = spec[((long)g * Tp + t) * bins + bin];
+      // plane of (patch g, frame t): patch-major g * Tp + t, or frame-pair-major ((t / 2) G + g) 2 + t % 2
+      const long plane = frame_major ? ((long)(t >> 1) * G + g) * 2 + (t & 1) : (long)g * Tp + t;
+      const float2 z = spec[plane * bins + bin];
       v = (double)z.x * z.x + (double)z.y * z.y;
     }
     double v1 = warp_sum(v), v2 = warp_sum(v * herm);
@@ -394,14 +397,15 @@ __global__ void shifts_grad_to_eval_kernel(const float* __restrict__ grad_shifts
 
 }  // namespace
 
-// spec (G, Tp, KY, KX) complex64 -> norms (G, T, 2) float64 (zeroed here)
+// spec (G, Tp, KY, KX) complex64 -- or, frame_major != 0, (Tp / 2, G, 2, KY, KX): the plane order of frame-pair jobs
+// listed frame pair by frame pair -- -> norms (G, T, 2) float64 (zeroed here)
 TMC_API int tmc_local_spectra_norms(const void* spec, int g, int t, int tp, int ny, int nx, int ky_count, int kx_count,
-                                    int ky_start, double* norms, cudaStream_t stream) {
+                                    int ky_start, int frame_major, double* norms, cudaStream_t stream) {
   TMC_CHECK_ARG(spec && norms && g >= 1 && t >= 1 && tp >= t, "local_spectra_norms: bad arguments");
   BandGeom geom{ny, nx, ky_count, kx_count, ky_start};
   TMC_CUDA(cudaMemsetAsync(norms, 0, sizeof(double) * (size_t)g * t * 2, stream));
   dim3 grid(tmc_div_up((long)ky_count * kx_count, kOptThreads), g);
-  spectra_norms_kernel<<<grid, kOptThreads, 0, stream>>>((const float2*)spec, t, tp, geom, norms); tmc_count_launch();
+  spectra_norms_kernel<<<grid, kOptThreads, 0, stream>>>((const float2*)spec, t, tp, geom, frame_major, norms); tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_local_spectra_norms");
   return TMC_OK;
 }

@@ -409,12 +409,13 @@ __global__ void __launch_bounds__(kTileThreads) local_loss_tile_kernel(const Ste
 
 // spec (G, Tp, KY, KX) -> tiled (G, n_tiles, T, 2 [re, im], 128), zero padded
 __global__ void tile_spectra_kernel(const float2* __restrict__ spec, int T, int Tp, int KY, int KX, const int* __restrict__ tiles,
-                                    int n_tiles, float* __restrict__ out) {
-  const int tile_id = blockIdx.x, t = blockIdx.y, g = blockIdx.z;
+                                    int n_tiles, int frame_major, float* __restrict__ out) {
+  const int tile_id = blockIdx.x, t = blockIdx.y, g = blockIdx.z, G = gridDim.z;
   const int b = threadIdx.x;
   const int kyb = tiles[2 * tile_id] * kTileKy + b / kTileKx, kx = tiles[2 * tile_id + 1] * kTileKx + b % kTileKx;
   float2 v = make_float2(0.f, 0.f);
-  if (kyb < KY && kx < KX) v = spec[(((long)g * Tp + t) * KY + kyb) * KX + kx];
+  const long plane = frame_major ? ((long)(t >> 1) * G + g) * 2 + (t & 1) : (long)g * Tp + t;
+  if (kyb < KY && kx < KX) v = spec[(plane * KY + kyb) * KX + kx];
   float* o = out + (((long)g * n_tiles + tile_id) * T + t) * 2 * kTileBins;
   o[b] = v.x;
   o[kTileBins + b] = v.y;
@@ -437,13 +438,14 @@ TMC_API int tmc_local_steps_supported(int g, int t, int nt, int nhw) {
   return coef_smem_bytes(g, t, nt, nhw) <= 160 * 1024 ? 1 : 0;
 }
 
-// spec (g, tp, ky_count, kx_count) complex64 -> out (g, n_tiles, t, 2, 128) float32; tiles (n_tiles, 2) int32 (ty, tx)
+// spec (g, tp, ky_count, kx_count) complex64 (frame_major != 0: (tp / 2, g, 2, ky_count, kx_count), see
+// tmc_local_spectra_norms) -> out (g, n_tiles, t, 2, 128) float32; tiles (n_tiles, 2) int32 (ty, tx)
 TMC_API int tmc_local_tile_spectra(const void* spec, int g, int t, int tp, int ky_count, int kx_count, const int* tiles,
-                                   int n_tiles, void* out, cudaStream_t stream) {
+                                   int n_tiles, int frame_major, void* out, cudaStream_t stream) {
   TMC_CHECK_ARG(spec && tiles && out && g >= 1 && t >= 1 && tp >= t && n_tiles >= 1 && t <= 65535 && g <= 65535,
                 "local_tile_spectra: bad arguments");
   dim3 grid(n_tiles, t, g);
-  tile_spectra_kernel<<<grid, kTileBins, 0, stream>>>((const float2*)spec, t, tp, ky_count, kx_count, tiles, n_tiles, (float*)out);
+  tile_spectra_kernel<<<grid, kTileBins, 0, stream>>>((const float2*)spec, t, tp, ky_count, kx_count, tiles, n_tiles, frame_major, (float*)out);
   tmc_count_launch();
   TMC_CHECK_LAUNCH("tmc_local_tile_spectra");
   return TMC_OK;
