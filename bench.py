@@ -458,7 +458,8 @@ def main():
         },
         "e2e": {
             "value": movies / (e2e_ms * 1e-3), "unit": "movies/s", "ms_per_step": e2e_ms / args.steps,
-            "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": cfg["h"] * cfg["w"] * 4,
+            # whole job: every rank copies its own movie in and its frame sum out each step
+            "h2d_bytes_per_step": host.numel() * 4 * world, "d2h_bytes_per_step": cfg["h"] * cfg["w"] * 4 * world,
         },
         "gpu_launches": launches,
         "c_abi_calls": calls,
