@@ -178,9 +178,14 @@ def motion_correct_frame_split(local_frames: torch.Tensor, pixel_spacing: float,
     global_field = estimate_global_motion_frame_split(
         frames, pixel_spacing, frame_offset, total_frames, stats, b_factor=b_factor, frequency_range=frequency_range, group=group
     )
-    field, _ = estimate_patch_motion_frame_split(
-        frames, pixel_spacing, frame_offset, total_frames, stats, deformation_field=global_field, b_factor=b_factor,
-        frequency_range=frequency_range, patch_sidelength=patch_sidelength, group=group,
+    from .pipeline import cumulative_patch_field
+
+    field, _ = cumulative_patch_field(
+        global_field, pixel_spacing,
+        lambda pre: estimate_patch_motion_frame_split(
+            frames, pixel_spacing, frame_offset, total_frames, stats, deformation_field=pre, b_factor=b_factor,
+            frequency_range=frequency_range, patch_sidelength=patch_sidelength, group=group,
+        ),
     )
     total = correct_motion_sum_frame_split(frames, field, pixel_spacing, frame_offset, total_frames, grid_type, group)
     return total, field

@@ -12,6 +12,30 @@ from .correct_motion import correct_motion_sum
 from .estimate_motion_xc import estimate_global_motion, estimate_motion_cross_correlation_patches
 
 
+def cumulative_patch_field(global_field: torch.Tensor, pixel_spacing: float, patch_estimator):
+    """Patch cross-correlation on top of a rigid (2, t, 1, 1) Angstrom field, composed so that the result is
+    ``global + patch residuals``.
+
+    The reference-compatible estimator takes the rigid field through ``correct_motion_fast``, which uses Angstrom values
+    as pixels and negates the caller's tensor in place, and then accumulates the patch shifts onto the NEGATED field
+    (quirk Q2; the reference's own example loop, ``examples/ttMotion.py:287-329``, only recovers from that in its later
+    iterations).  Here the estimator is handed ``global / pixel_spacing`` -- so the pre-correction moves every frame by
+    exactly minus its shift in pixels -- and the base it accumulated on is swapped for the true global field afterwards.
+    ``patch_estimator(pre)`` must return ``(field (2, t, gh, gw), centres)`` and may negate ``pre`` in place or not."""
+    from ._lib import call, ptr, stream_ptr
+    from .deformation_field_utils import resample_deformation_field
+
+    pre = global_field / float(pixel_spacing)
+    handed = pre.clone()
+    xc_field, centres = patch_estimator(pre)
+    t, gh, gw = xc_field.shape[1:]
+    used_base = resample_deformation_field(-handed, (t, gh, gw))  # what the estimator accumulated the patch shifts on
+    field = (xc_field - used_base + resample_deformation_field(global_field, (t, gh, gw))).contiguous()
+    with torch.cuda.device(field.device):
+        call("tmc_subtract_mean", ptr(field), field.numel(), stream_ptr(field.device))  # one joint mean, like quirk Q4
+    return field, centres
+
+
 def estimate_motion(
     image: torch.Tensor,
     pixel_spacing: float,
@@ -42,10 +66,13 @@ def estimate_motion(
     global_field = estimate_global_motion(
         image, pixel_spacing, b_factor=b_factor, frequency_range=frequency_range, device=device, _stats=stats
     )
-    field, centres = estimate_motion_cross_correlation_patches(
-        image, pixel_spacing, b_factor=b_factor, frequency_range=frequency_range, patch_sidelength=patch_sidelength,
-        deformation_field=global_field, device=device, dose_per_frame=dose_per_frame, pre_exposure=pre_exposure, voltage=voltage,
-        _stats=stats,
+    field, centres = cumulative_patch_field(
+        global_field, pixel_spacing,
+        lambda pre: estimate_motion_cross_correlation_patches(
+            image, pixel_spacing, b_factor=b_factor, frequency_range=frequency_range, patch_sidelength=patch_sidelength,
+            deformation_field=pre, device=device, dose_per_frame=dose_per_frame, pre_exposure=pre_exposure, voltage=voltage,
+            _stats=stats,
+        ),
     )
     if n_iterations > 0:
         from .estimate_motion_optimizer import estimate_local_motion
