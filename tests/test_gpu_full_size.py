@@ -93,6 +93,20 @@ def test_integer_fourier_shift_is_a_circular_roll(dev, movie_and_walk):
         assert rel_l2(out[k], want) <= 2e-5, k
 
 
+def test_fourier_shift_column_strips_agree_with_single_columns(dev, movie_and_walk, monkeypatch):
+    """4096-point whole-frame columns: the 4-column strip kernel (shared-memory staged, default) against the
+    one-column-per-CTA kernel on fractional shifts."""
+    movie, _ = movie_and_walk
+    sub = movie[:6].contiguous()
+    field = torch.tensor([[1.3, -2.7, 0.0, 4.25, -0.5, 7.9], [-3.1, 0.4, 0.0, 2.5, 6.6, -1.2]], device=dev).reshape(2, 6, 1, 1)
+    monkeypatch.setenv("TMC_FFT_COL_QUADS", "1")
+    quads = tmc.correct_motion_fast(sub, field.clone())
+    monkeypatch.setenv("TMC_FFT_COL_QUADS", "0")
+    single = tmc.correct_motion_fast(sub, field.clone())
+    assert rel_l2(quads, single) <= 2e-6
+    assert rel_l2(quads[2], sub[2]) <= 2e-5  # zero shift
+
+
 def test_one_launch_iterations_agree_with_the_generic_kernels(dev, movie_and_walk, monkeypatch):
     from torch_motion_correction_b200 import estimate_motion_optimizer as emo
 

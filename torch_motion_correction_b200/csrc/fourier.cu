@@ -474,6 +474,12 @@ inline bool use_poly() {
   return on;
 }
 
+// TMC_FFT_COL_QUADS=0 selects the one-column-per-CTA kernel for 4096-point whole-frame columns (A/B testing)
+inline bool use_col_quads() {
+  const char* e = getenv("TMC_FFT_COL_QUADS");
+  return !(e && e[0] == '0');
+}
+
 template <int M, bool BLU>
 constexpr bool use_fast_path() {
   return !BLU && M >= 256;
@@ -954,6 +960,16 @@ TMC_API int tmc_fourier_shift_frames(const float* image, int t, int ny, int nx, 
   }
   rc = dispatch_fft(ny, "fourier_shift_frames", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
+    if constexpr (MM == 4096 && !decltype(BLU)::value) {
+      if (use_col_quads()) {
+        constexpr size_t smem = (size_t)(4 * fft2::Cfg<MM>::STRIDE + 64 + fft2::Cfg<MM>::TW_HI) * sizeof(float2);
+        if (int e = enable_smem(cols_shift_quad_p2<MM>, smem)) return e;
+        dim3 grid(tmc_div_up(kx, 4), t);
+        cols_shift_quad_p2<MM><<<grid, 512, smem, stream>>>((float2*)tmp, kx, nx, (const float2*)phase, field, t, sign, py.tw);
+        tmc_count_launch();
+        return TMC_OK;
+      }
+    }
     if constexpr (use_fast_path<MM, decltype(BLU)::value>()) {
       if (int e = enable_smem(cols_shift_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
       dim3 grid(tmc_div_up(kx, fft2::Cfg<MM>::B), t);

@@ -452,6 +452,86 @@ cols_shift_p2(float2* __restrict__ tmp, int KX, int NX, const float2* __restrict
     }
 }
 
+// Four adjacent columns per CTA for the lengths whose FFT occupies a whole 256-thread group (Cfg<N>::B == 1, N = 4096):
+// with one column per CTA every 8-byte element of the (ny, nx/2+1) spectrum costs its own 32-byte sector on the way in
+// and on the way out (ncu r01g: 6.5x the algorithmic L2 traffic, the kernel's limiter).  Here a 512-thread CTA stages a
+// 4-column strip (lane = (row, column): a warp request covers 8 rows x 32 contiguous bytes) in shared memory, two
+// 256-thread groups transform two columns each in place, and the strip is written back the same way.
+template <int N>
+__global__ void __launch_bounds__(512, 1)
+cols_shift_quad_p2(float2* __restrict__ tmp, int KX, int NX, const float2* __restrict__ phase_y, const float* __restrict__ field,
+                   int T, float sign, const float2* __restrict__ tw) {
+  using C = fft2::Cfg<N>;
+  using P = fft2::Plan<N>;
+  static_assert(C::B == 1 && C::TPS == 256, "one sequence per 256-thread group");
+  extern __shared__ float2 smem[];
+  fft2::Smem<N> sm(smem);          // data = 4 sequences, the twiddle tables follow them
+  sm.tw_lo = smem + 4 * C::STRIDE;
+  sm.tw_hi = sm.tw_lo + 64;
+  for (int i = threadIdx.x; i < 64 + C::TW_HI; i += 512) sm.tw_lo[i] = i < 64 ? __ldg(tw + i) : __ldg(tw + (i - 64) * 64);
+  const int f = blockIdx.y;
+  const int kx0 = blockIdx.x * 4;
+  float2* strip = tmp + (long)f * N * KX + kx0;
+  // load: thread = (row slot, column)
+  {
+    const int c = threadIdx.x & 3, r0 = threadIdx.x >> 2;
+    const bool live = kx0 + c < KX;
+    float2* seq = smem + c * C::STRIDE;
+#pragma unroll 8
+    for (int y = r0; y < N; y += 128) seq[fft2::pad_idx(y)] = live ? strip[(long)y * KX + c] : make_float2(0.f, 0.f);
+  }
+  const int group = threadIdx.x >> 8, j = threadIdx.x & 255;
+  const float2* py = phase_y + (long)f * N;
+  const float sx = sign * __ldg(field + T + f);
+  const float inv_nx = (float)(1.0 / (double)NX);
+  __syncthreads();
+#pragma unroll 1
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c = group + 2 * cc;
+    float2* myseq = smem + c * C::STRIDE;
+    float2 ex;
+    {
+      float s, co;
+      sincosf(__fmul_rn(__fmul_rn(-6.283185307179586f, __fmul_rn((float)(kx0 + c), inv_nx)), sx), &s, &co);
+      ex = make_float2(co, s);
+    }
+    float2 v[C::VPT];
+    P::First::load(myseq, j, v);
+    __syncthreads();
+    fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+    __syncthreads();  // every thread has taken its last-pass inputs out of shared memory
+#pragma unroll
+    for (int g = 0; g < P::Last::G; ++g)
+#pragma unroll
+      for (int r = 0; r < P::Last::R; ++r) {
+        const int ky = P::Last::out_index(j, g, r);
+        const float2 val = cmul(P::Last::result(v, g, r), cmul(__ldg(py + ky), ex));
+        myseq[fft2::pad_idx(ky)] = make_float2(val.y, val.x);  // swapped: the next forward FFT is the inverse
+      }
+    __syncthreads();
+    P::First::load(myseq, j, v);
+    __syncthreads();
+    fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < P::Last::G; ++g)
+#pragma unroll
+      for (int r = 0; r < P::Last::R; ++r) {
+        const float2 val = P::Last::result(v, g, r);
+        myseq[fft2::pad_idx(P::Last::out_index(j, g, r))] = make_float2(val.y, val.x);
+      }
+    __syncthreads();
+  }
+  {
+    const int c = threadIdx.x & 3, r0 = threadIdx.x >> 2;
+    if (kx0 + c < KX) {
+      const float2* seq = smem + c * C::STRIDE;
+#pragma unroll 8
+      for (int y = r0; y < N; y += 128) strip[(long)y * KX + c] = seq[fft2::pad_idx(y)];
+    }
+  }
+}
+
 // phase_y[f][ky] for all frames (tiny)
 __global__ void shift_phase_y_kernel(const float* __restrict__ field, int T, int NY, float sign, float2* __restrict__ phase_y) {
   const int ky = blockIdx.x * blockDim.x + threadIdx.x;
