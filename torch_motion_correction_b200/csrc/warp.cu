@@ -208,7 +208,8 @@ __device__ __noinline__ float warp_pixel_generic(const float* __restrict__ image
 // (Angstrom -> px, grid_sample round trip, cubic weights) runs on both axes at once as packed fp32x2 arithmetic
 // and the 8 lattice taps of a frame are shared by the thread's pixels.
 // measured alternatives on B200 (C2, fused sum): 4 rows per thread at 128 registers (2 CTAs per SM) 4.3 ms; capped at
-// 80 registers (3 CTAs per SM) 5.4 ms; 2 rows per thread 4.6-4.8 ms; uncapped registers (1 CTA per SM) 6.2 ms
+// 80 registers (3 CTAs per SM) 5.4 ms; 2 rows per thread 4.6-4.8 ms; uncapped registers (1 CTA per SM) 6.2 ms;
+// prefetch.global.L2 of the next frame's rows +2 %
 template <bool WRITE_STACK, bool WRITE_SUM, bool NORMALISE>
 __global__ void __launch_bounds__(kTileX* kTileYGroups, 2)
 warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const float* __restrict__ rx, int lh,

@@ -106,7 +106,7 @@ class LocalMotionProblem:
         self.fused = FUSED_STEPS and self.loss_type != 2 and bool(
             query("tmc_local_steps_supported", self.g, t, self.resolution[0], self.resolution[1] * self.resolution[2]))
         # frame-pair jobs; for the tiled path they are listed frame pair by frame pair, so the 50 %-overlapping patches of
-        # a pair run back to back and every frame comes from HBM once (patch-major order re-reads it 2.3x: ncu r01g)
+        # a pair run back to back and every frame comes from HBM once (patch-major order re-read it 2.3x: ncu)
         self.frame_major = self.fused
 
         def build_jobs():
