@@ -207,11 +207,14 @@ __device__ __noinline__ float warp_pixel_generic(const float* __restrict__ image
 // Stage 2: one thread = kRows vertically adjacent output pixels of one column; the coordinate chain of a pixel
 // (Angstrom -> px, grid_sample round trip, cubic weights) runs on both axes at once as packed fp32x2 arithmetic
 // and the 8 lattice taps of a frame are shared by the thread's pixels.
-// measured alternatives on B200 (C2, fused sum): 4 rows per thread at 128 registers (2 CTAs per SM) 4.3 ms; capped at
-// 80 registers (3 CTAs per SM) 5.4 ms; 2 rows per thread 4.6-4.8 ms; uncapped registers (1 CTA per SM) 6.2 ms;
+// measured alternatives on B200 (C2, fused sum): 4 rows per thread at 128 registers (2 CTAs per SM) 4.3 ms (4.1 ms with
+// the shared tap rows); capped at 80 registers (3 CTAs per SM) 5.4 ms (4.9 ms with shared tap rows); 2 rows per thread 4.6-4.8 ms; uncapped registers (1 CTA per SM) 6.2 ms;
 // prefetch.global.L2 of the next frame's rows +2 %
 template <bool WRITE_STACK, bool WRITE_SUM, bool NORMALISE>
-__global__ void __launch_bounds__(kTileX* kTileYGroups, 2)
+#ifndef TMC_WARP_MINB
+#define TMC_WARP_MINB 2
+#endif
+__global__ void __launch_bounds__(kTileX* kTileYGroups, TMC_WARP_MINB)
 warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const float* __restrict__ rx, int lh,
                     float pixel_spacing, const float* __restrict__ mean_std, float* __restrict__ out_stack,
                     float* __restrict__ out_sum, int accumulate_sum, int x_begin, int x_end, int y_begin, int y_end) {
@@ -314,7 +317,35 @@ warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const 
       p[r] = frame + (interior ? (unsigned)((iy - 1) * W + (ix - 1)) : 0u);
     }
     float v[kRows];
-    if (all_interior) {
+    // vertically adjacent pixels whose sampling points are vertically adjacent too (same column of taps, consecutive
+    // rows: the shifts differ by ~1e-3 px per row, so almost always) share their tap rows: kRows + 3 rows of 4 taps
+    bool stacked = all_interior;
+#pragma unroll
+    for (int r = 1; r < kRows; ++r) stacked = stacked && (p[r] == p[0] + r * W);
+    if (stacked) {
+      float row[kRows + 3][4];
+      {
+        const float* q = p[0];
+#pragma unroll
+        for (int a = 0; a < kRows + 3; ++a, q += W)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) row[a][b] = __ldg(q + b);
+      }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        float2 w[4];  // .x = weight along y, .y = weight along x
+        cubic_weights2(frac[r], w);
+        float2 r01 = __fmul2_rn(dup(w[0].y), f2(row[r][0], row[r + 1][0]));
+        float2 r23 = __fmul2_rn(dup(w[0].y), f2(row[r + 2][0], row[r + 3][0]));
+#pragma unroll
+        for (int b = 1; b < 4; ++b) {
+          r01 = __ffma2_rn(dup(w[b].y), f2(row[r][b], row[r + 1][b]), r01);
+          r23 = __ffma2_rn(dup(w[b].y), f2(row[r + 2][b], row[r + 3][b]), r23);
+        }
+        const float2 t2 = __ffma2_rn(f2(w[2].x, w[3].x), r23, __fmul2_rn(f2(w[0].x, w[1].x), r01));
+        v[r] = t2.x + t2.y;
+      }
+    } else if (all_interior) {
       // stage B: every tap of every pixel in flight at once; stage C: weights (while the loads fly) and the sums
       float tap[kRows][4][4];
 #pragma unroll
