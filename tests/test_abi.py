@@ -67,3 +67,29 @@ def test_product_never_imports_the_oracle():
                 with open(os.path.join(dirpath, name)) as f:
                     src = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), name
+
+
+def test_header_binding_and_definitions_agree_on_arity():
+    """Every entry point has the same number of parameters in include/tmc_b200.h, in the ctypes binding and in its
+    definition under csrc/ (a drift would corrupt the call silently)."""
+    import glob
+
+    with open(os.path.join(ROOT, "include", "tmc_b200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    decls = re.findall(r"\b(tmc_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(decls) == len(_lib._SIGNATURES)
+
+    def arity(args):
+        args = args.strip()
+        return 0 if args in ("void", "") else args.count(",") + 1
+
+    for name, args in decls:
+        assert arity(args) == len(_lib._SIGNATURES[name][1]), name
+    src = ""
+    for path in glob.glob(os.path.join(ROOT, "torch_motion_correction_b200", "csrc", "*.cu")):
+        with open(path) as f:
+            src += f.read()
+    defs = re.findall(r"TMC_API\s+[a-z\s\*]+?\b(tmc_[a-z0-9_]+)\s*\(([^{;]*?)\)\s*\{", src, flags=re.S)
+    assert {n for n, _ in defs} == set(_lib._SIGNATURES)
+    for name, args in defs:
+        assert arity(args) == len(_lib._SIGNATURES[name][1]), name
