@@ -716,3 +716,42 @@ def synthetic_movie(t: int, h: int, w: int, seed: int = 0, noise: float = 1.0, d
             fr = deps.sample_image_2d(specimen, torch.stack([cy, cx], dim=-1), interpolation="bicubic")
         frames.append(fr + noise * torch.randn((h, w), generator=g))
     return torch.stack(frames).float().contiguous(), walk
+
+
+def synthetic_movie_large(t: int, h: int, w: int, seed: int = 0, noise: float = 1.0, drift: float = 6.0,
+                          local: float = 1.5, sigma_f: float = 0.08):
+    """Same recipe as :func:`synthetic_movie` at a cost that suits the benchmark-sized parity cases (seconds, not
+    minutes, for 40 x 2048^2): the smooth local field is evaluated on a coarse 33 x 33 lattice and brought to pixel
+    resolution with ``F.interpolate`` (bicubic), and frames are resampled with ``F.grid_sample`` (bicubic) directly.
+
+    Returns ``(movie (t,h,w) float32, global_shifts (t,2) px)``.  Used by ``tests/golden/make_golden.py`` and by the
+    ``-m gpu`` tests that regenerate the same movie from its seed."""
+    g = torch.Generator().manual_seed(seed)
+    pad = 64
+    H, W = h + 2 * pad, w + 2 * pad
+    white = torch.randn((H, W), generator=g)
+    fy = torch.fft.fftfreq(H)[:, None]
+    fx = torch.fft.rfftfreq(W)[None, :]
+    lp = torch.exp(-(fy**2 + fx**2) / (2 * sigma_f**2))
+    specimen = torch.fft.irfftn(torch.fft.rfftn(white) * lp, s=(H, W))
+    specimen = (specimen / specimen.std()).float()
+    steps = torch.randn((t, 2), generator=g)
+    walk = torch.cumsum(steps, dim=0)
+    walk = walk - walk[t // 2]
+    walk = walk / max(float(walk.abs().max()), 1e-6) * drift
+    coef = torch.randn((2, 3, 4, 4), generator=g) * local
+    n = 33
+    ly, lx = torch.meshgrid(torch.linspace(0, 1, n), torch.linspace(0, 1, n), indexing="ij")
+    yy = torch.arange(h, dtype=torch.float32)[:, None]
+    xx = torch.arange(w, dtype=torch.float32)[None, :]
+    frames = torch.empty((t, h, w), dtype=torch.float32)
+    for k in range(t):
+        tyx = torch.stack([torch.full_like(ly, k / max(t - 1, 1)), ly, lx], dim=-1)
+        coarse = deps.evaluate_cubic_grid_3d(coef, tyx, deps.BSPLINE_MATRIX)  # (n, n, 2)
+        loc = F.interpolate(coarse.permute(2, 0, 1)[None], size=(h, w), mode="bicubic", align_corners=True)[0]
+        cy = yy + (pad - float(walk[k, 0])) - loc[0]
+        cx = xx + (pad - float(walk[k, 1])) - loc[1]
+        grid = torch.stack([cx / (W - 1) * 2 - 1, cy / (H - 1) * 2 - 1], dim=-1)[None]
+        fr = F.grid_sample(specimen[None, None], grid, mode="bicubic", padding_mode="border", align_corners=True)[0, 0]
+        frames[k] = fr + noise * torch.randn((h, w), generator=g)
+    return frames.contiguous(), walk

@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import deps, verbatim  # noqa: E402
-from oracle.reference_path import synthetic_movie  # noqa: E402
+from oracle.reference_path import synthetic_movie, synthetic_movie_large  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -193,14 +193,110 @@ def case_c1(ref):
     print("c1.npz done")
 
 
+# ---- benchmark-sized cases (BASELINE configs 2-4 code paths: p = 1024 patches, T = 40 / 60, 4096-point whole-frame
+# transforms).  Only fields, crops and norms are stored (KBs); the tests regenerate the movies from their seeds with
+# oracle.reference_path.synthetic_movie_large / synthetic_movie.
+
+LARGE = dict(c2half=dict(t=40, size=2048, seed=40, px=0.83, resolution=(3, 5, 5), iters=4),
+             c3half=dict(t=60, size=2048, seed=60, px=0.83, resolution=(5, 6, 6), iters=3),
+             # BASELINE configs 2 and 3 at their full size (about 5 and 8 CPU-minutes, ~25 GB of host memory)
+             c2full=dict(t=40, size=4096, seed=41, px=0.83, resolution=(3, 5, 5), iters=3),
+             c3full=dict(t=60, size=4096, seed=61, px=0.83, resolution=(5, 6, 6), iters=2))
+
+
+def sum_samples(s):
+    """What is kept of an (h, w) frame sum: centre crop, corner crop (border taps / zero-outside), strided rows, norm."""
+    h, w = s.shape
+    return {
+        "sum_centre": np32(s[h // 2 - 96 : h // 2 + 96, w // 2 - 96 : w // 2 + 96]),
+        "sum_corner": np32(s[:96, :96]),
+        "sum_rows": np32(s[:: h // 16, :]),
+        "sum_norm": np.float64(torch.linalg.norm(s.double())),
+    }
+
+
+def case_large(ref, name):
+    import time
+
+    cfg = LARGE[name]
+    t, n, px = cfg["t"], cfg["size"], cfg["px"]
+    movie, walk = synthetic_movie_large(t, n, n, seed=cfg["seed"], noise=1.0, drift=6.0, local=1.5)
+    out = {"seed": np.int64(cfg["seed"]), "t": np.int64(t), "size": np.int64(n), "pixel_spacing": np.float64(px),
+           "true_global": np32(walk), "movie_checksum": np.float64(movie.double().sum()),
+           "movie_probe": np32(movie[:: max(t // 4, 1), ::257, ::263])}
+    tic = time.time()
+    with verbatim.quiet():
+        g = ref.estimate_global_motion(movie.clone(), px)
+        out["global_field"] = np32(g)
+        f, pos = ref.estimate_motion_cross_correlation_patches(movie.clone(), px, patch_sidelength=1024)
+        out["xc_field"] = np32(f)
+        out["xc_positions"] = np32(pos)
+        fraw, _ = ref.estimate_motion_cross_correlation_patches(
+            movie.clone(), px, patch_sidelength=1024, temporal_smoothing=False, outlier_rejection=False)
+        out["xc_raw"] = np32(fraw)
+        if name.startswith("c2"):
+            # the rigid pre-field route the pipeline drives: (2,t,1,1) field in PIXELS handed over (quirk Q2: used as px,
+            # negated in place, shifts accumulated on the negated field)
+            pre = (g / px).clone()
+            fp, _ = ref.estimate_motion_cross_correlation_patches(
+                movie.clone(), px, patch_sidelength=1024, deformation_field=pre, temporal_smoothing=False)
+            out["xc_pre_nosmooth"] = np32(fp)
+            out["xc_pre_field_after"] = np32(pre)
+            pre = (g / px).clone()
+            fp, _ = ref.estimate_motion_cross_correlation_patches(
+                movie.clone(), px, patch_sidelength=1024, deformation_field=pre)
+            out["xc_pre"] = np32(fp)
+        print(name, "xc done", time.time() - tic, file=sys.__stdout__, flush=True)
+        random.seed(2024)
+        res, traj = ref.estimate_local_motion(
+            movie.clone(), px, (1024, 1024), cfg["resolution"], f.clone(), n_iterations=cfg["iters"], grid_type="bspline",
+            return_trajectory=True,
+        )
+        out["local_field"] = np32(res)
+        out["local_losses"] = np.asarray([c.loss for c in traj.checkpoints])
+        print(name, "local done", time.time() - tic, file=sys.__stdout__, flush=True)
+        if name.startswith("c2"):
+            corr = ref.correct_motion(movie, res, px, grid_type="bspline")
+            out.update(sum_samples(corr.sum(dim=0)))
+            del corr
+            corr = ref.correct_motion(movie[:6], f[:, :6].contiguous(), px)  # (2, t, gh, gw) field, Catmull-Rom default
+            out.update({"xcfield_" + k: v for k, v in sum_samples(corr.sum(dim=0)).items()})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "done", time.time() - tic, file=sys.__stdout__, flush=True)
+
+
+def case_whole4096(ref):
+    """4 frames of 4096^2: the 4096-point whole-frame transforms (global estimate, rigid Fourier-shift correction)."""
+    out = {}
+    px = 0.83
+    movie, walk = synthetic_movie(4, 4096, 4096, seed=7, noise=1.0, drift=9.0, integer_shifts=True, sigma_f=0.08)
+    out["seed"] = np.int64(7)
+    out["true_shifts"] = np32(walk)
+    with verbatim.quiet():
+        g = ref.estimate_global_motion(movie.clone(), px)
+        out["global_field"] = np32(g)
+        field = torch.tensor([[1.5, -2.25, 0.0, 3.7], [-0.5, 4.125, 2.0, -6.3]]).reshape(2, 4, 1, 1)
+        out["fast_field"] = np32(field)
+        corr = ref.correct_motion_fast(movie, field.clone())
+        out["fast_centre"] = np32(corr[:, 2048 - 64 : 2048 + 64, 2048 - 64 : 2048 + 64])
+        out["fast_corner"] = np32(corr[:, :64, :64])
+        out["fast_rows"] = np32(corr[:, ::512, :])
+        out["fast_norm"] = np.float64(torch.linalg.norm(corr.double()))
+    np.savez_compressed(os.path.join(OUT, "whole4096.npz"), **out)
+    print("whole4096.npz done", file=sys.__stdout__, flush=True)
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     ref = verbatim.load()
     import torch_motion_correction.deformation_field_utils  # noqa: F401  (attribute access below)
 
-    case_small(ref)
-    case_eviction(ref)
-    case_c1(ref)
+    which = sys.argv[1:] or ["small", "eviction", "c1"]  # the benchmark-sized cases take ~10 CPU-minutes each: by name
+    for name in which:
+        if name in LARGE:
+            case_large(ref, name)
+        else:
+            {"small": case_small, "eviction": case_eviction, "c1": case_c1, "whole4096": case_whole4096}[name](ref)
 
 
 if __name__ == "__main__":
