@@ -136,8 +136,17 @@ int tmc_fft_c2c_rows(const void* in, int rows, int n, const void* plan, void* ou
  * job_mode: 0 generic; 1 all jobs are {f, 1, f, 2, ..} (one frame, mask powers 1 and 2); 2 all jobs use power 1.
  * tmp: 2 * njobs * ny * kx_count complex64. */
 int tmc_rfft2_band(const float* image, int t, int h, int w, const float* mean_std, const float* mask, int ny, int nx,
-                   const int* jobs, int njobs, int job_mode, int ylo, int yhi, int kx_count, int ky_count, int ky_start,
-                   const float* weight, const void* plan_x, const void* plan_y, void* tmp, void* out, tmc_stream_t stream);
+                   const int* jobs, int njobs, int job_mode, const int* frame_shifts, int x_margin, int ylo, int yhi,
+                   int kx_count, int ky_count, int ky_start, const float* weight, const void* plan_x, const void* plan_y,
+                   void* tmp, void* out, tmc_stream_t stream);
+/* frame_shifts (nullable, (t, 2) int32 device): whole-pixel (dy, dx) added to the window origin of every frame, the
+ * window wrapping around the frame edges -- the patches of the frames rolled by an integer Fourier shift, which is what
+ * the rigid pre-correction of estimate_motion_xc.py:232-241 (correct_motion_fast, correct_motion.py:430-498) produces for
+ * whole-pixel fields such as estimate_global_motion's (quirk Q5), without a pass over the stack.  x_margin: the first
+ * and last x_margin columns of `mask` are all zero (0 if unknown).
+ * tmc_integer_shifts: shifts[f] = rint(scale * field[c][f]) for a (2, t) field; *not_integer (device int) = 1 when a
+ * scaled value is further than 1e-4 from a whole number. */
+int tmc_integer_shifts(const float* field, int t, float scale, int* shifts, int* not_integer, tmc_stream_t stream);
 
 /* ---- cross-correlation products: estimate_motion_xc.py:112,310-349 ---------------------------------- */
 /* out[i] = conj(spec[ref_plane[i]]) * spec[cur_plane[i]] */

@@ -20,6 +20,7 @@ CHUNK_BYTES = int(os.environ.get("TMC_FFT_CHUNK_BYTES", str(1 << 30)))
 
 _twiddles: dict = {}
 _masks: dict = {}
+_mask_margins: dict = {}  # mask.data_ptr() -> number of all-zero columns at either side (masks live as long as the process)
 _weights: dict = {}
 
 
@@ -53,6 +54,7 @@ def soft_disc_mask(shape, radius: float, smoothing_radius: float, device: torch.
         reach = int(radius + smoothing_radius) + 2
         ylo, yhi = max(0, h // 2 - reach), min(h, h // 2 + reach + 1)
         hit = (mask, ylo, yhi)
+        _mask_margins[mask.data_ptr()] = max(0, min(w // 2 - reach, w - (w // 2 + reach + 1)))
         _masks[key] = hit
     return hit
 
@@ -112,8 +114,12 @@ class BandPlan:
         return self.ky * self.kx
 
     # -- forward ------------------------------------------------------------------------------
-    def forward(self, image: torch.Tensor, mean_std, mask, ylo: int, yhi: int, jobs: torch.Tensor, out=None, job_mode: int = 0):
+    def forward(self, image: torch.Tensor, mean_std, mask, ylo: int, yhi: int, jobs: torch.Tensor, out=None, job_mode: int = 0,
+                frame_shifts: torch.Tensor | None = None):
         """jobs (njobs, 6) int32 device -> spectra (2*njobs, KY, KX) complex64 (as float pairs).
+
+        ``frame_shifts`` (t, 2) int32 device: whole-pixel (dy, dx) added to the window origin of every frame (wrapping
+        around the frame edges), see ``integer_shifts``.
 
         ``job_mode`` promises a structure shared by all jobs (lets the row kernel drop its generic
         loops): 1 = one frame under mask powers (1, 2); 2 = two frames (or one), power 1; 0 = generic."""
@@ -126,12 +132,14 @@ class BandPlan:
         chunk = max(1, min(njobs, CHUNK_BYTES // per_job))
         tmp = torch.empty((chunk * per_job // 4,), dtype=torch.float32, device=dev)
         jobs_base, out_base = jobs.data_ptr(), out.data_ptr()
+        x_margin = _mask_margins.get(mask.data_ptr(), 0) if mask is not None else 0
         with torch.cuda.device(dev):
             stream = stream_ptr(dev)
             for j0 in range(0, njobs, chunk):
                 n = min(chunk, njobs - j0)
                 call("tmc_rfft2_band", ptr(image), t, h, w, ptr(mean_std), ptr(mask), self.ny, self.nx,
-                     jobs_base + j0 * 6 * 4, n, int(job_mode), ylo, yhi, self.kx, self.ky, self.ky_start, ptr(self.weight),
+                     jobs_base + j0 * 6 * 4, n, int(job_mode), ptr(frame_shifts), x_margin, ylo, yhi, self.kx, self.ky,
+                     self.ky_start, ptr(self.weight),
                      ptr(self.tw_x), ptr(self.tw_y), ptr(tmp), out_base + 2 * j0 * self.plane_elems * _C64, stream)
         return out
 
@@ -240,6 +248,18 @@ def frame_pair_jobs(t: int, device: torch.device, frame_offset: int = 0) -> torc
         return torch.tensor(rows, dtype=torch.int32)
 
     return cached_device_tensor(("frame_pair_jobs", t, frame_offset), build, device)
+
+
+def integer_shifts(field: torch.Tensor, scale: float = 1.0):
+    """(2, t, 1, 1) rigid field -> ((t, 2) int32 whole-pixel window shifts, device int flag "some value is not whole")."""
+    dev = field.device
+    t = field.shape[1]
+    flat = field.detach().to(torch.float32).reshape(2, t).contiguous()
+    shifts = torch.empty((t, 2), dtype=torch.int32, device=dev)
+    flag = torch.empty((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        call("tmc_integer_shifts", ptr(flat), t, float(scale), ptr(shifts), ptr(flag), stream_ptr(dev))
+    return shifts, flag
 
 
 def pair_products(spec: torch.Tensor, ref_plane: torch.Tensor, cur_plane: torch.Tensor, plane_elems: int) -> torch.Tensor:

@@ -49,7 +49,8 @@ _SIGNATURES = {
     "tmc_fft_plan_elems": (L, [I]),
     "tmc_fft_plan_init": (I, [I, P, P]),
     "tmc_fft_c2c_rows": (I, [P, I, I, P, P, P]),
-    "tmc_rfft2_band": (I, [P, I, I, I, P, P, I, I, P, I, I, I, I, I, I, I, P, P, P, P, P, P]),
+    "tmc_rfft2_band": (I, [P, I, I, I, P, P, I, I, P, I, I, P, I, I, I, I, I, I, P, P, P, P, P, P]),
+    "tmc_integer_shifts": (I, [P, I, F, P, P, P]),
     "tmc_xc_pair_products": (I, [P, P, P, I, L, P, P]),
     "tmc_xc_leave_one_out_products": (I, [P, I, I, L, P, P, I, I, P, P]),
     "tmc_xc_peak_partials": (I, [I, I]),

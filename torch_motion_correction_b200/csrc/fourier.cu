@@ -160,11 +160,49 @@ struct RowJob {  // one packed pair of real rows-sets: a -> real part, b -> imag
   int frame_a, exp_a, frame_b, exp_b, y0, x0;
 };
 
+// The window a job reads from one frame.  frame_shifts (nullable, (T, 2) int32 = (dy, dx)) moves the window of every
+// frame by a whole number of pixels: reading the window at origin + shift is what the reference gets by first rolling
+// the frame (an integer-pixel Fourier shift, correct_motion.py:484-496) and then extracting the patch at the origin.
+// The roll is circular, so a window that leaves the frame wraps around -- unless it only leaves it where the mask is
+// zero anyway (the first / last x_margin columns and the rows outside [ylo, yhi)): then the plain reads stay inside the
+// movie buffer, hit the neighbouring rows' finite pixels and are multiplied by zero like the wrapped ones.
+struct Window {
+  const float* frame;  // first pixel of the frame
+  int oy, ox;          // window origin inside the frame (may lie outside it)
+  bool wrap;           // reads have to be wrapped around the frame edges (slow path)
+  __device__ __forceinline__ const float* fast_base(int W) const { return frame + (long)oy * W + ox; }
+  __device__ __forceinline__ const float* wrapped(int y, int x, int H, int W) const {
+    int ry = (oy + y) % H, cx = (ox + x) % W;
+    if (ry < 0) ry += H;
+    if (cx < 0) cx += W;
+    return frame + (long)ry * W + cx;
+  }
+};
+
+__device__ __forceinline__ Window make_window(const float* image, int frame, int y0, int x0, const int* __restrict__ frame_shifts,
+                                              int H, int W, int ylo, int yhi, int NX, int x_margin) {
+  Window w;
+  w.frame = image + (long)frame * H * W;
+  w.oy = y0;
+  w.ox = x0;
+  if (frame_shifts != nullptr) {
+    w.oy += __ldg(frame_shifts + 2 * frame);
+    w.ox += __ldg(frame_shifts + 2 * frame + 1);
+  }
+  const bool rows_inside = w.oy + ylo >= 0 && w.oy + yhi <= H;
+  const bool cols_inside = w.ox >= 0 && w.ox + NX <= W;
+  const bool cols_masked = w.ox >= -x_margin && w.ox + NX <= W + x_margin;
+  // plain reads of the first / last frame row with columns beyond the row would leave the movie buffer
+  const bool buffer_end = (w.oy + ylo == 0 && w.ox < 0) || (w.oy + yhi == H && w.ox + NX > W);
+  w.wrap = !(rows_inside && (cols_inside || (cols_masked && !buffer_end)));
+  return w;
+}
+
 template <int MX, bool BLU>
 __global__ void __launch_bounds__(kThreads)
 rows_forward_kernel(const float* __restrict__ image, int H, int W, const float* __restrict__ mean_std,
-                    const float* __restrict__ mask, const int* __restrict__ jobs, int ylo, int yhi, int NY, int KX,
-                    AxisPlan plan, float2* __restrict__ tmp) {
+                    const float* __restrict__ mask, const int* __restrict__ jobs, const int* __restrict__ frame_shifts,
+                    int x_margin, int ylo, int yhi, int NY, int KX, AxisPlan plan, float2* __restrict__ tmp) {
   constexpr int B = batch_for(MX);
   constexpr int STRIDE = padded_len(MX);
   const int NX = BLU ? plan.n : MX;
@@ -181,20 +219,20 @@ rows_forward_kernel(const float* __restrict__ image, int H, int W, const float* 
     mean = __ldg(mean_std);
     stdv = __ldg(mean_std + 1);
   }
-  const long fs = (long)H * W;
+  const Window wa = make_window(image, fa, y0, x0, frame_shifts, H, W, ylo, yhi, NX, x_margin);
+  const Window wb = make_window(image, fb >= 0 ? fb : fa, y0, x0, frame_shifts, H, W, ylo, yhi, NX, x_margin);
   for (int idx = threadIdx.x; idx < B * NX; idx += kThreads) {
     const int s = idx / NX, x = idx % NX;
     const int y = row0 + s;
     float2 z = make_float2(0.f, 0.f);
     if (y < yhi) {
       const float m = mask ? __ldg(mask + (long)y * NX + x) : 1.0f;
-      const long off = (long)(y0 + y) * W + x0 + x;
-      float va = __ldg(image + fa * fs + off);
+      float va = __ldg(wa.wrap ? wa.wrapped(y, x, H, W) : wa.fast_base(W) + (long)y * W + x);
       if (norm) va = __fdiv_rn(__fsub_rn(va, mean), stdv);
       for (int e = 0; e < ea; ++e) va = __fmul_rn(va, m);
       z.x = va;
       if (fb >= 0) {
-        float vb = (fb == fa) ? __ldg(image + fa * fs + off) : __ldg(image + fb * fs + off);
+        float vb = __ldg(wb.wrap ? wb.wrapped(y, x, H, W) : wb.fast_base(W) + (long)y * W + x);
         if (norm) vb = __fdiv_rn(__fsub_rn(vb, mean), stdv);
         for (int e = 0; e < eb; ++e) vb = __fmul_rn(vb, m);
         z.y = vb;
@@ -680,17 +718,22 @@ TMC_API int tmc_fft_c2c_rows(const void* in, int rows, int n, const void* plan, 
 //  image (T,H,W) f32; mean_std nullable device float[2]; mask (ny,nx) f32 nullable;
 //  jobs (njobs,6) int32 device = {frame_a, exp_a, frame_b (-1: none), exp_b, y0, x0}; job_mode promises a
 //  structure shared by ALL jobs (1: frame_b == frame_a, powers (1,2); 2: powers (1,1)) or 0 for generic;
+//  frame_shifts nullable (t,2) int32 device = whole-pixel (dy, dx) added to the window origin of every frame (the
+//  window wraps around the frame edges: identical to rolling the frame by an integer Fourier shift first, which is
+//  what the reference's rigid pre-correction does, estimate_motion_xc.py:232-241); x_margin: the first and last
+//  x_margin columns of the mask are all zero (0 if unknown);
 //  rows [ylo,yhi) are the only non-zero rows of the mask; kx in [0,KX), ky in [ky_start, ky_start+KY);
 //  weight (KY,KX) f32 nullable; plan_x/plan_y: tmc_fft_plan_init buffers for nx/ny;
 //  tmp: 2*njobs*ny*KX complex64; out: (2*njobs, KY, KX) complex64, plane 2*job+0 = a, 2*job+1 = b.
 TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float* mean_std, const float* mask, int ny, int nx,
-                           const int* jobs, int njobs, int job_mode, int ylo, int yhi, int kx_count, int ky_count,
-                           int ky_start, const float* weight, const void* plan_x, const void* plan_y, void* tmp, void* out,
-                           cudaStream_t stream) {
+                           const int* jobs, int njobs, int job_mode, const int* frame_shifts, int x_margin, int ylo, int yhi,
+                           int kx_count, int ky_count, int ky_start, const float* weight, const void* plan_x,
+                           const void* plan_y, void* tmp, void* out, cudaStream_t stream) {
   TMC_CHECK_ARG(image && jobs && plan_x && plan_y && tmp && out, "rfft2_band: null pointer");
   TMC_CHECK_ARG(job_mode >= 0 && job_mode <= 2, "rfft2_band: job_mode must be 0 (generic), 1 (mask powers 1,2 of one frame) or 2 (two frames)");
   TMC_CHECK_ARG(njobs >= 0 && t >= 1 && h >= ny && w >= nx, "rfft2_band: window (%d,%d) larger than image (%d,%d)", ny, nx, h, w);
   TMC_CHECK_ARG(0 <= ylo && ylo <= yhi && yhi <= ny, "rfft2_band: bad row support [%d,%d)", ylo, yhi);
+  TMC_CHECK_ARG(x_margin >= 0 && 2 * x_margin <= nx, "rfft2_band: bad x_margin %d", x_margin);
   TMC_CHECK_ARG(kx_count >= 1 && kx_count <= nx / 2 + 1 && ky_count >= 1 && ky_count <= ny, "rfft2_band: bad band box");
   if (njobs == 0) return TMC_OK;
   const AxisPlan px = make_axis_plan(plan_x, nx), py = make_axis_plan(plan_y, ny);
@@ -705,11 +748,11 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
         dim3 grid(tmc_div_up(yhi - ylo, rows_per_cta), njobs);
         if (job_mode == 1) {
           if (int e = enable_smem(poly::rows_forward_poly<1>, poly::smem_bytes)) return e;
-          poly::rows_forward_poly<1><<<grid, poly::kThreads, poly::smem_bytes, stream>>>(image, h, w, mean_std, mask, jobs, ylo, yhi, ny,
+          poly::rows_forward_poly<1><<<grid, poly::kThreads, poly::smem_bytes, stream>>>(image, h, w, mean_std, mask, jobs, frame_shifts, x_margin, ylo, yhi, ny,
                                                                                      kx_count, px.tw, (float2*)tmp, rows_per_cta);
         } else {
           if (int e = enable_smem(poly::rows_forward_poly<2>, poly::smem_bytes)) return e;
-          poly::rows_forward_poly<2><<<grid, poly::kThreads, poly::smem_bytes, stream>>>(image, h, w, mean_std, mask, jobs, ylo, yhi, ny,
+          poly::rows_forward_poly<2><<<grid, poly::kThreads, poly::smem_bytes, stream>>>(image, h, w, mean_std, mask, jobs, frame_shifts, x_margin, ylo, yhi, ny,
                                                                                      kx_count, px.tw, (float2*)tmp, rows_per_cta);
         }
         tmc_count_launch();
@@ -727,8 +770,9 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
 #define TMC_ROWS_FWD(MODE)                                                                                      \
   {                                                                                                             \
     if (int e = enable_smem(rows_forward_p2<MM, MODE>, smem)) return e;                                         \
-    rows_forward_p2<MM, MODE><<<grid, fft2::kThreads, smem, stream>>>(image, h, w, mean_std, mask, jobs, ylo, yhi, \
-                                                                     ny, kx_count, px.tw, (float2*)tmp, rows_per_cta); \
+    rows_forward_p2<MM, MODE><<<grid, fft2::kThreads, smem, stream>>>(image, h, w, mean_std, mask, jobs, frame_shifts, \
+                                                                     x_margin, ylo, yhi, ny, kx_count, px.tw,          \
+                                                                     (float2*)tmp, rows_per_cta);                      \
   }
         if (job_mode == 1) TMC_ROWS_FWD(1) else if (job_mode == 2) TMC_ROWS_FWD(2) else TMC_ROWS_FWD(0)
 #undef TMC_ROWS_FWD
@@ -739,8 +783,8 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
     if (int e = enable_smem(rows_forward_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(tmc_div_up(yhi - ylo, batch_for(MM)), njobs);
     if (yhi > ylo) {
-      rows_forward_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>(image, h, w, mean_std, mask, jobs, ylo, yhi,
-                                                                                   ny, kx_count, px, (float2*)tmp); tmc_count_launch();
+      rows_forward_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>(
+          image, h, w, mean_std, mask, jobs, frame_shifts, x_margin, ylo, yhi, ny, kx_count, px, (float2*)tmp); tmc_count_launch();
     }
     return TMC_OK;
   });
@@ -764,6 +808,30 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
   });
   if (rc) return rc;
   TMC_CHECK_LAUNCH("tmc_rfft2_band(cols)");
+  return TMC_OK;
+}
+
+// shifts[f] = (rint(scale * field[0][f]), rint(scale * field[1][f])) for a (2, t) field; *not_integer is set to 1 when
+// some scaled value is further than 1e-4 from a whole number (the caller zeroes it first)
+__global__ void integer_shifts_kernel(const float* __restrict__ field, int t, float scale, int* __restrict__ shifts,
+                                      int* __restrict__ not_integer) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= t) return;
+  const float sy = scale * field[f], sx = scale * field[t + f];
+  const float ry = rintf(sy), rx = rintf(sx);
+  shifts[2 * f] = (int)ry;
+  shifts[2 * f + 1] = (int)rx;
+  if (!(fabsf(sy - ry) <= 1e-4f && fabsf(sx - rx) <= 1e-4f && fabsf(ry) < 1e6f && fabsf(rx) < 1e6f)) *not_integer = 1;
+}
+
+// Whole-pixel window shifts for tmc_rfft2_band(frame_shifts) from a rigid (2, t, 1, 1) field: shifts (t, 2) int32,
+// not_integer (device int, set to 0 / 1).  Replaces the rigid pre-correction pass of estimate_motion_xc.py:232-241 for
+// fields that are whole pixels (the integer estimate of estimate_global_motion, quirk Q5).
+TMC_API int tmc_integer_shifts(const float* field, int t, float scale, int* shifts, int* not_integer, cudaStream_t stream) {
+  TMC_CHECK_ARG(field && shifts && not_integer && t >= 1, "integer_shifts: bad arguments");
+  TMC_CUDA(cudaMemsetAsync(not_integer, 0, sizeof(int), stream));
+  integer_shifts_kernel<<<tmc_div_up(t, 128), 128, 0, stream>>>(field, t, scale, shifts, not_integer); tmc_count_launch();
+  TMC_CHECK_LAUNCH("tmc_integer_shifts");
   return TMC_OK;
 }
 
@@ -948,8 +1016,8 @@ TMC_API int tmc_fourier_shift_frames(const float* image, int t, int ny, int nx, 
       constexpr size_t smem = rows_forward_smem_bytes<MM>();
       if (int e = enable_smem(rows_forward_p2<MM, 2>, smem)) return e;
       dim3 grid(tmc_div_up(ny, rows_per_cta), njobs);
-      rows_forward_p2<MM, 2><<<grid, fft2::kThreads, smem, stream>>>(image, ny, nx, mean_std, nullptr, jobs, 0, ny, ny, kx, px.tw,
-                                                                    (float2*)tmp, rows_per_cta); tmc_count_launch();
+      rows_forward_p2<MM, 2><<<grid, fft2::kThreads, smem, stream>>>(image, ny, nx, mean_std, nullptr, jobs, nullptr, 0, 0, ny, ny,
+                                                                    kx, px.tw, (float2*)tmp, rows_per_cta); tmc_count_launch();
     }
     return TMC_OK;
   });

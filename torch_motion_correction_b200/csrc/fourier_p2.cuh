@@ -27,8 +27,9 @@ constexpr size_t rows_forward_smem_bytes() {
 template <int N, int MODE>
 __global__ void __launch_bounds__(fft2::kThreads)
 rows_forward_p2(const float* __restrict__ image, int H, int W, const float* __restrict__ mean_std,
-                const float* __restrict__ mask, const int* __restrict__ jobs, int ylo, int yhi, int NY, int KX,
-                const float2* __restrict__ tw, float2* __restrict__ tmp, int rows_per_cta) {
+                const float* __restrict__ mask, const int* __restrict__ jobs, const int* __restrict__ frame_shifts,
+                int x_margin, int ylo, int yhi, int NY, int KX, const float2* __restrict__ tw, float2* __restrict__ tmp,
+                int rows_per_cta) {
   using C = fft2::Cfg<N>;
   using P = fft2::Plan<N>;
   extern __shared__ float2 smem[];
@@ -48,11 +49,12 @@ rows_forward_p2(const float* __restrict__ image, int H, int W, const float* __re
     mean = __ldg(mean_std);
     inv_std = 1.0f / __ldg(mean_std + 1);
   }
-  const long fs = (long)H * W;
-  const float* img_a = image + fa * fs + (long)y0 * W + x0;
+  const Window wa = make_window(image, fa, y0, x0, frame_shifts, H, W, ylo, yhi, N, x_margin);
+  const Window wb = make_window(image, fb >= 0 ? fb : fa, y0, x0, frame_shifts, H, W, ylo, yhi, N, x_margin);
+  const float* img_a = wa.fast_base(W);
   const bool has_b = fb >= 0;
   const bool separate_b = has_b && (MODE == 2 || (MODE == 0 && fb != fa));
-  const float* img_b = has_b ? image + fb * fs + (long)y0 * W + x0 : nullptr;
+  const float* img_b = wb.fast_base(W);
   const int row_begin = ylo + blockIdx.x * rows_per_cta;
   const int row_end = min(yhi, row_begin + rows_per_cta);
   float2* plane_a = tmp + (long)(2 * job) * NY * KX;
@@ -65,8 +67,8 @@ rows_forward_p2(const float* __restrict__ image, int H, int W, const float* __re
       for (int e = 0; e < C::VPT; ++e) {
         const int x = P::First::in_index(j, e / P::First::R, e % P::First::R);
         const int slot = e * fft2::kThreads + threadIdx.x;
-        cp_async_f32(stage_a + slot, img_a + (long)y * W + x);
-        if (separate_b) cp_async_f32(stage_b + slot, img_b + (long)y * W + x);
+        cp_async_f32(stage_a + slot, wa.wrap ? wa.wrapped(y, x, H, W) : img_a + (long)y * W + x);
+        if (separate_b) cp_async_f32(stage_b + slot, wb.wrap ? wb.wrapped(y, x, H, W) : img_b + (long)y * W + x);
         if (mask) cp_async_f32(stage_m + slot, mask + (long)y * N + x);
       }
     }

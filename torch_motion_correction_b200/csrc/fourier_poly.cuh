@@ -56,8 +56,9 @@ __device__ __forceinline__ void load_tables(float2* tw_step, float2* tw_comb, co
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, MODE == 1 ? 3 : 2)
 rows_forward_poly(const float* __restrict__ image, int H, int W, const float* __restrict__ mean_std,
-                  const float* __restrict__ mask, const int* __restrict__ jobs, int ylo, int yhi, int NY, int KX,
-                  const float2* __restrict__ tw, float2* __restrict__ tmp, int rows_per_cta) {
+                  const float* __restrict__ mask, const int* __restrict__ jobs, const int* __restrict__ frame_shifts,
+                  int x_margin, int ylo, int yhi, int NY, int KX, const float2* __restrict__ tw, float2* __restrict__ tmp,
+                  int rows_per_cta) {
   constexpr int N = 1024;
   extern __shared__ float2 smem[];
   float2* tw_step = smem;
@@ -75,11 +76,12 @@ rows_forward_poly(const float* __restrict__ image, int H, int W, const float* __
     mean = __ldg(mean_std);
     inv_std = 1.0f / __ldg(mean_std + 1);
   }
-  const long fs = (long)H * W;
-  const float* img_a = image + fa * fs + (long)y0 * W + x0;
+  const Window wa = make_window(image, fa, y0, x0, frame_shifts, H, W, ylo, yhi, N, x_margin);
+  const Window wb = make_window(image, fb >= 0 ? fb : fa, y0, x0, frame_shifts, H, W, ylo, yhi, N, x_margin);
+  const float* img_a = wa.fast_base(W);
   const bool has_b = fb >= 0;
   const bool separate_b = MODE == 2 && has_b;
-  const float* img_b = has_b ? image + fb * fs + (long)y0 * W + x0 : nullptr;
+  const float* img_b = wb.fast_base(W);
   const int row_begin = ylo + blockIdx.x * rows_per_cta;
   const int row_end = min(yhi, row_begin + rows_per_cta);
   float2* plane_a = tmp + (long)(2 * job) * NY * KX;
@@ -98,7 +100,13 @@ rows_forward_poly(const float* __restrict__ image, int H, int W, const float* __
 #pragma unroll
       for (int h0 = 0; h0 < 16; h0 += 8) {
         float2 pa[8], pb[8], pm[8];
-        if (vec_a) {
+        if (wa.wrap) {  // CTA-uniform: the window leaves the frame where the mask is not zero
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int x = 4 * j + q0 + 64 * (h0 + r);
+            pa[r] = make_float2(__ldg(wa.wrapped(y, x, H, W)), __ldg(wa.wrapped(y, x + 1, H, W)));
+          }
+        } else if (vec_a) {
 #pragma unroll
           for (int r = 0; r < 8; ++r) pa[r] = __ldg(reinterpret_cast<const float2*>(ra + 64 * (h0 + r)));
         } else {
@@ -106,7 +114,13 @@ rows_forward_poly(const float* __restrict__ image, int H, int W, const float* __
           for (int r = 0; r < 8; ++r) pa[r] = make_float2(__ldg(ra + 64 * (h0 + r)), __ldg(ra + 64 * (h0 + r) + 1));
         }
         if (separate_b) {
-          if (vec_b) {
+          if (wb.wrap) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const int x = 4 * j + q0 + 64 * (h0 + r);
+              pb[r] = make_float2(__ldg(wb.wrapped(y, x, H, W)), __ldg(wb.wrapped(y, x + 1, H, W)));
+            }
+          } else if (vec_b) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) pb[r] = __ldg(reinterpret_cast<const float2*>(rb + 64 * (h0 + r)));
           } else {

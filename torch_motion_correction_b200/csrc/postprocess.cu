@@ -79,8 +79,10 @@ __global__ void reject_and_accumulate_kernel(const float* __restrict__ shifts, i
   }
 }
 
-// Savitzky-Golay, polyorder 1, odd window w <= T, scipy mode="interp": moving average inside,
-// least-squares line through the first / last w samples at the edges.  in/out (2, T, G).
+// Savitzky-Golay, polyorder 1, window w <= T, scipy mode="interp": moving average inside, least-squares line through
+// the first / last w samples at the edges.  in/out (2, T, G).  An even window (the reference caps an odd window at an
+// even frame count, quirk Q9; scipy >= 1.11 accepts it) averages x[i - w/2 + 1 .. i + w/2]: scipy evaluates the fit at
+// pos = w/2 - 0.5 and ndimage's convolve1d places an even kernel one sample to the right.
 __global__ void savgol_linear_kernel(const float* __restrict__ in, int T, int G, int window, float* __restrict__ out) {
   const int series = blockIdx.x * blockDim.x + threadIdx.x;  // (c, g)
   if (series >= 2 * G) return;
@@ -88,9 +90,10 @@ __global__ void savgol_linear_kernel(const float* __restrict__ in, int T, int G,
   const float* x = in + (long)c * T * G + g;
   float* y = out + (long)c * T * G + g;
   const int half = window / 2;
+  const int left = (window & 1) ? half : half - 1;  // samples before i inside the window
   for (int i = half; i < T - half; ++i) {
     double s = 0.0;
-    for (int j = -half; j <= half; ++j) s += (double)x[(long)(i + j) * G];
+    for (int j = -left; j <= half; ++j) s += (double)x[(long)(i + j) * G];
     y[(long)i * G] = (float)(s / window);
   }
   const double xm = 0.5 * (window - 1);
@@ -155,10 +158,8 @@ TMC_API int tmc_xc_postprocess(const float* shifts, int t, int g, float pixel_sp
     int window = smoothing_window;
     if (window % 2 == 0) window += 1;
     if (window > t) window = t;
-    // an even t caps the window at an even value; scipy then raises for polyorder... the reference
-    // guards only `< 3`, and savgol_filter accepts even windows since scipy 1.11 -- we require odd.
+    // an even t caps the window at an even value: savgol_filter accepts even windows since scipy 1.11
     if (window >= 3) {
-      TMC_CHECK_ARG(window % 2 == 1, "xc_postprocess: smoothing window %d (capped at t=%d) must be odd", window, t);
       TMC_CUDA(cudaMemcpyAsync(scratch, field, sizeof(float) * 2 * (size_t)t * g, cudaMemcpyDeviceToDevice, stream));
       savgol_linear_kernel<<<tmc_div_up(2 * g, 64), 64, 0, stream>>>(scratch, t, g, window, field); tmc_count_launch();
     }

@@ -118,7 +118,7 @@ def estimate_global_motion_frame_split(local_frames, pixel_spacing, frame_offset
 def estimate_patch_motion_frame_split(local_frames, pixel_spacing, frame_offset, total_frames, mean_std,
                                       deformation_field=None, b_factor=500, frequency_range=(300, 10), patch_sidelength=1024,
                                       sub_pixel_refinement=True, temporal_smoothing=True, smoothing_window_size=5,
-                                      outlier_rejection=True, outlier_threshold=3.0, group=None):
+                                      outlier_rejection=True, outlier_threshold=3.0, group=None, whole_pixel_field=False):
     """``estimate_motion_cross_correlation_patches`` (``mean_except_current``) for a frame-split movie.
 
     Each rank transforms the patches of its own frames; the band-limited spectra (both mask powers,
@@ -130,14 +130,20 @@ def estimate_patch_motion_frame_split(local_frames, pixel_spacing, frame_offset,
     if t < 2:
         raise ValueError("mean_except_current needs at least two frames")
     source, source_stats = local_frames, mean_std
+    frame_shifts = None
     if deformation_field is not None:
         deformation_field = deformation_field.to(dev)
         if tuple(deformation_field.shape[-2:]) != (1, 1):
             raise NotImplementedError("frame-split pre-correction supports the rigid (2, t, 1, 1) field")
         local_field = deformation_field[:, frame_offset : frame_offset + t_local].clone()
-        source = correct_motion_fast(local_frames, local_field, device=dev, _mean_std=mean_std)
+        if whole_pixel_field:
+            # whole-pixel rigid field (estimate_global_motion, quirk Q5): the integer Fourier shift is a circular roll,
+            # i.e. patch windows read at origins moved by each frame's shift -- no pre-correction pass
+            frame_shifts, _ = _fourier.integer_shifts(local_field)
+        else:
+            source = correct_motion_fast(local_frames, local_field, device=dev, _mean_std=mean_std)
+            source_stats = None
         deformation_field = deformation_field * -1  # the reference negates the caller's field in place (Q2)
-        source_stats = None
     p = int(patch_sidelength)
     centers = patch_grid_centers((t, h, w), (1, p, p), (1, p // 2, p // 2), distribute_patches=True)
     gh, gw = centers.shape[1:3]
@@ -150,7 +156,7 @@ def estimate_patch_motion_frame_split(local_frames, pixel_spacing, frame_offset,
     else:
         field = resample_deformation_field(deformation_field, (t, gh, gw))
     jobs = torch.tensor([[k, 1, k, 2, y0, x0] for k in range(t_local) for (y0, x0) in origins], dtype=torch.int32).to(dev)
-    spec_local = plan.forward(source, source_stats, mask, ylo, yhi, jobs, job_mode=1).view(t_local, g * 2 * plan.plane_elems * 2)
+    spec_local = plan.forward(source, source_stats, mask, ylo, yhi, jobs, job_mode=1, frame_shifts=frame_shifts).view(t_local, g * 2 * plan.plane_elems * 2)
     spec_all = all_gather_frames(spec_local, t, group)
     offsets, deltas = _aliasing_schedule(t, "mean_except_current", t // 2)
     d_off = torch.tensor(offsets, dtype=torch.int32).to(dev)
@@ -184,7 +190,8 @@ def motion_correct_frame_split(local_frames: torch.Tensor, pixel_spacing: float,
         global_field, pixel_spacing,
         lambda pre: estimate_patch_motion_frame_split(
             frames, pixel_spacing, frame_offset, total_frames, stats, deformation_field=pre, b_factor=b_factor,
-            frequency_range=frequency_range, patch_sidelength=patch_sidelength, group=group,
+            frequency_range=frequency_range, patch_sidelength=patch_sidelength, group=group, temporal_smoothing=False,
+            whole_pixel_field=True,
         ),
     )
     total = correct_motion_sum_frame_split(frames, field, pixel_spacing, frame_offset, total_frames, grid_type, group)

@@ -127,6 +127,7 @@ def estimate_motion_cross_correlation_patches(
     pre_exposure: float = 0.0,
     voltage: float = 300.0,
     _stats: torch.Tensor | None = None,
+    _whole_pixel_field: bool | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """Patch-wise Fourier cross-correlation -> ((2, t, gh, gw) Angstrom field, (t, gh, gw, 3) centres).
 
@@ -137,7 +138,13 @@ def estimate_motion_cross_correlation_patches(
     Reference: estimate_motion_xc.py:138-411, including the result-changing quirks Q1 (cached patches
     are masked in place, so earlier frames enter later references double-masked), Q2/Q3 (rigid
     pre-correction negates the caller's field in place and uses Angstrom as px; full pre-correction
-    uses the B-spline, resampling uses Catmull-Rom), Q4, Q6-Q9."""
+    uses the B-spline, resampling uses Catmull-Rom), Q4, Q6-Q9.
+
+    A rigid (2, t, 1, 1) field whose values are whole numbers (the integer estimate of ``estimate_global_motion``, quirk
+    Q5, handed over in pixels) needs no pre-correction pass: an integer Fourier shift is a circular roll, so every
+    frame's patch windows are simply read at origins moved by that frame's shift (wrapping around the frame edges).  The
+    check costs one host synchronisation; ``_whole_pixel_field`` (internal) vouches for it (True) or forces the
+    Fourier-shift pass (False)."""
     dev = resolve_device(image, device)
     movie = as_f32(image, dev)
     t, h, w = movie.shape
@@ -150,13 +157,26 @@ def estimate_motion_cross_correlation_patches(
     stats = _stats if _stats is not None else _ops.stack_stats(movie)  # _stats: the pipeline computes them once per movie
 
     source, source_stats = movie, stats  # patches are read from here, normalised on load
+    frame_shifts = None
     if deformation_field is not None:
         deformation_field = deformation_field.to(dev)
         if tuple(deformation_field.shape[-2:]) == (1, 1):
-            source = correct_motion_fast(movie, deformation_field, device=dev, _mean_std=stats)
+            if deformation_field.shape[1] != t:
+                raise ValueError(f"deformation_field has {deformation_field.shape[1]} frames, the movie {t}")
+            whole = _whole_pixel_field
+            if whole is not False:
+                shifts, not_whole = _fourier.integer_shifts(deformation_field)
+                if whole is None:
+                    whole = int(not_whole.item()) == 0  # the one host synchronisation of this function
+            if whole:
+                frame_shifts = shifts
+                deformation_field *= -1  # quirk Q2: correct_motion_fast negates the caller's field in place
+            else:
+                source = correct_motion_fast(movie, deformation_field, device=dev, _mean_std=stats)
+                source_stats = None
         else:
             source = correct_motion(movie, deformation_field, pixel_spacing, grid_type="bspline", device=dev, _mean_std=stats)
-        source_stats = None
+            source_stats = None
 
     p = int(patch_sidelength)
     centers = patch_grid_centers((t, h, w), (1, p, p), (1, p // 2, p // 2), distribute_patches=True)
@@ -178,7 +198,7 @@ def estimate_motion_cross_correlation_patches(
         jobs = cached_device_tensor(
             ("xc_jobs_mean", geometry),
             lambda: torch.tensor([[k, 1, k, 2, y0, x0] for k in range(t) for (y0, x0) in origins], dtype=torch.int32), dev)
-        spec = plan.forward(source, source_stats, mask, ylo, yhi, jobs, job_mode=1)
+        spec = plan.forward(source, source_stats, mask, ylo, yhi, jobs, job_mode=1, frame_shifts=frame_shifts)
         if dose_per_frame is not None:
             plan.dose_filter(spec, jobs, t, pixel_spacing, pre_exposure, dose_per_frame, voltage)
 
@@ -199,7 +219,7 @@ def estimate_motion_cross_correlation_patches(
             )
 
         jobs = cached_device_tensor(("xc_jobs_middle", (t, h, w, p), int(reference_frame)), middle_jobs, dev)
-        spec = plan.forward(source, source_stats, mask, ylo, yhi, jobs)
+        spec = plan.forward(source, source_stats, mask, ylo, yhi, jobs, frame_shifts=frame_shifts)
         if dose_per_frame is not None:
             plan.dose_filter(spec, jobs, t, pixel_spacing, pre_exposure, dose_per_frame, voltage)
         items = torch.arange(t * n_patches, dtype=torch.int32, device=dev)

@@ -12,16 +12,20 @@ from .correct_motion import correct_motion_sum
 from .estimate_motion_xc import estimate_global_motion, estimate_motion_cross_correlation_patches
 
 
-def cumulative_patch_field(global_field: torch.Tensor, pixel_spacing: float, patch_estimator):
+def cumulative_patch_field(global_field: torch.Tensor, pixel_spacing: float, patch_estimator, smoothing_window_size: int = 5):
     """Patch cross-correlation on top of a rigid (2, t, 1, 1) Angstrom field, composed so that the result is
-    ``global + patch residuals``.
+    ``smooth(global + patch residuals)``.
 
     The reference-compatible estimator takes the rigid field through ``correct_motion_fast``, which uses Angstrom values
     as pixels and negates the caller's tensor in place, and then accumulates the patch shifts onto the NEGATED field
     (quirk Q2; the reference's own example loop, ``examples/ttMotion.py:287-329``, only recovers from that in its later
     iterations).  Here the estimator is handed ``global / pixel_spacing`` -- so the pre-correction moves every frame by
-    exactly minus its shift in pixels -- and the base it accumulated on is swapped for the true global field afterwards.
-    ``patch_estimator(pre)`` must return ``(field (2, t, gh, gw), centres)`` and may negate ``pre`` in place or not."""
+    exactly minus its shift in pixels -- WITHOUT temporal smoothing; the base it accumulated on is swapped for the true
+    global field, and only then the Savitzky-Golay filter and the single joint mean subtraction (quirks Q9, Q4) are applied
+    to the composed field.  (Smoothing before the swap would leave the smoothing residual of the integer-quantised
+    global track, quirk Q5, in the result.)
+    ``patch_estimator(pre)`` must return ``(field (2, t, gh, gw), centres)`` computed with ``temporal_smoothing=False``
+    and may negate ``pre`` in place or not."""
     from ._lib import call, ptr, stream_ptr
     from .deformation_field_utils import resample_deformation_field
 
@@ -31,8 +35,12 @@ def cumulative_patch_field(global_field: torch.Tensor, pixel_spacing: float, pat
     t, gh, gw = xc_field.shape[1:]
     used_base = resample_deformation_field(-handed, (t, gh, gw))  # what the estimator accumulated the patch shifts on
     field = (xc_field - used_base + resample_deformation_field(global_field, (t, gh, gw))).contiguous()
+    zero_shifts = torch.zeros((t, gh * gw, 2), dtype=torch.float32, device=field.device)
+    scratch = torch.empty_like(field)
     with torch.cuda.device(field.device):
-        call("tmc_subtract_mean", ptr(field), field.numel(), stream_ptr(field.device))  # one joint mean, like quirk Q4
+        # smoothing + one joint mean (quirk Q4) of the composed field: the estimator's own tail with nothing to add
+        call("tmc_xc_postprocess", ptr(zero_shifts), t, gh * gw, float(pixel_spacing), -1, 0, 0.0, 1, int(smoothing_window_size),
+             1, ptr(field), ptr(scratch), stream_ptr(field.device))
     return field, centres
 
 
@@ -71,7 +79,8 @@ def estimate_motion(
         lambda pre: estimate_motion_cross_correlation_patches(
             image, pixel_spacing, b_factor=b_factor, frequency_range=frequency_range, patch_sidelength=patch_sidelength,
             deformation_field=pre, device=device, dose_per_frame=dose_per_frame, pre_exposure=pre_exposure, voltage=voltage,
-            _stats=stats,
+            temporal_smoothing=False, _stats=stats,
+            _whole_pixel_field=True,  # estimate_global_motion returns whole pixels (quirk Q5): no pre-correction pass, no sync
         ),
     )
     if n_iterations > 0:
@@ -111,7 +120,12 @@ def motion_correct_many(host_movies, pixel_spacing: float, device=None, out_host
 
     The H2D copy of movie i+1 runs on a side stream while movie i is being estimated and corrected
     (two device buffers), and each result is copied back asynchronously: dataset-scale processing
-    is bounded by max(PCIe, compute) instead of their sum."""
+    is bounded by max(PCIe, compute) instead of their sum.
+
+    The result of movie i is yielded only after movie i+1 has been enqueued and after the device-to-host copy of its sum
+    has completed (a CUDA event is waited for), so ``sum_host`` is always safe to read; the overlap is kept because the
+    GPU is already busy with movie i+1 while the host waits.  With ``out_host`` the same buffer is reused for every
+    movie: consume it before advancing the generator."""
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     movies = iter(host_movies)
     copy_stream = torch.cuda.Stream(device=dev)
@@ -136,6 +150,8 @@ def motion_correct_many(host_movies, pixel_spacing: float, device=None, out_host
     consumed[1].record(main)
     start_copy(0, nxt)
     slot = 0
+    pending = None  # (host sum, field, event after its D2H copy) of the previous movie
+    d2h_stream = torch.cuda.Stream(device=dev)
     while nxt is not None:
         try:
             upcoming = next(movies)
@@ -146,10 +162,22 @@ def motion_correct_many(host_movies, pixel_spacing: float, device=None, out_host
         main.wait_event(ready[slot])
         total, field = motion_correct(buffers[slot], pixel_spacing, device=dev, **kwargs)
         consumed[slot].record(main)
-        if out_host is not None:
-            host_sum = out_host
-        else:
-            host_sum = torch.empty(total.shape, dtype=torch.float32, pin_memory=True)
-        host_sum.copy_(total, non_blocking=True)
-        yield host_sum, field
+        if pending is not None and out_host is not None:
+            pending[2].synchronize()  # one shared host buffer: hand the previous result out before overwriting it
+            yield pending[0], pending[1]
+            pending = None
+        host_sum = out_host if out_host is not None else torch.empty(total.shape, dtype=torch.float32, pin_memory=True)
+        done = torch.cuda.Event()
+        d2h_stream.wait_stream(main)
+        with torch.cuda.stream(d2h_stream):
+            host_sum.copy_(total, non_blocking=True)
+            done.record(d2h_stream)
+        total.record_stream(d2h_stream)
+        if pending is not None:
+            pending[2].synchronize()
+            yield pending[0], pending[1]
+        pending = (host_sum, field, done)
         nxt, slot = upcoming, 1 - slot
+    if pending is not None:
+        pending[2].synchronize()
+        yield pending[0], pending[1]
