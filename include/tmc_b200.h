@@ -69,7 +69,7 @@ int tmc_spline_lattice(const float* coeffs, int c, int n0, int n1, int n2, int k
                        float* workspace, tmc_stream_t stream);
 
 /* ---- warp: correct_motion.py:81-185 (_correct_frame, get_pixel_shifts) + sample_image_2d -------- */
-long tmc_warp_workspace_floats(int t, int w, int lh);
+long tmc_warp_workspace_floats(int t, int w, int lh); /* t * 2 * (lh + 3) * w: x-interpolated lattice, reflection-padded rows */
 /* per pixel: bicubic(reflection) lookup of the frame's (2, lh, lw) Angstrom lattice -> / pixel_spacing ->
  * bicubic (border-clamped taps, zero outside) gather of the frame.  out_stack (t,h,w) and/or out_sum (h,w)
  * (fused sum over frames, never materialising the stack); accumulate_sum != 0 adds into out_sum (frame

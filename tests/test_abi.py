@@ -45,7 +45,7 @@ def test_library_loads_through_the_binding_and_answers_queries():
     assert _lib.query("tmc_fft_plan_elems", 96) == 2 * 256 + 96
     assert _lib.query("tmc_spline_workspace_floats", 2, 3, 5, 5) == 2 * 5 * 7 * 7
     assert _lib.query("tmc_spline_workspace_floats", 2, 40, 1, 1) == 2 * 42 * 4 * 4
-    assert _lib.query("tmc_warp_workspace_floats", 40, 4096, 50) == 40 * 2 * 50 * 4096
+    assert _lib.query("tmc_warp_workspace_floats", 40, 4096, 50) == 40 * 2 * (50 + 3) * 4096  # reflection-padded rows
     assert _lib.query("tmc_xc_peak_partials", 1024, 1024) == 32
 
 

@@ -137,17 +137,18 @@ def test_correct_motion_ragged_sizes_and_big_shifts(dev, shape):
     assert float((want == 0).float().mean()) > 0.01  # the case really exercises the zero fill
 
 
-@pytest.mark.parametrize("tiled", ["0", "1"])
+@pytest.mark.parametrize("tma", ["0", "1"])
 @pytest.mark.parametrize("amplitude", [2.0, 40.0])
-def test_correct_motion_shared_memory_tiles(dev, amplitude, tiled, monkeypatch):
-    """With TMC_WARP_TILED=1 images wider than 192 px with 16-byte aligned rows run the interior on the shared-memory
-    tile kernel and the 64-px border strips on the global-memory kernel (rectangle launches): smooth fields (taps
-    inside the staged boxes), and a wild field (boxes leave the image / taps leave the boxes: per-CTA and per-pixel
-    fall-backs), stack and fused sum.  TMC_WARP_TILED=0 (default) is the global-memory kernel alone."""
-    monkeypatch.setenv("TMC_WARP_TILED", tiled)
+@pytest.mark.parametrize("shape,grid", [((5, 300, 388), (3, 4, 5)), ((3, 331, 260), (3, 2, 2)), ((41, 64, 128), (41, 1, 1))])
+def test_correct_motion_tma_tiles(dev, shape, grid, amplitude, tma, monkeypatch):
+    """Images with 16-byte aligned rows run on the TMA-staged tile kernel (TMC_WARP_TMA=0: the global-memory kernel):
+    smooth fields (taps inside the staged boxes), a wild field (boxes hang over the frame edge, taps leave the boxes:
+    per-pixel fall-backs, zero fill outside the frame), ragged tile edges, more frames than pipeline stages, stack
+    output and fused sum, accumulation into an existing sum."""
+    monkeypatch.setenv("TMC_WARP_TMA", tma)
     g = torch.Generator().manual_seed(21)
-    img = torch.randn((5, 300, 388), generator=g)
-    field = torch.randn((2, 3, 4, 5), generator=g) * amplitude
+    img = torch.randn(shape, generator=g)
+    field = torch.randn((2, *grid), generator=g) * amplitude
     want = rp.correct_motion(img, field, 1.1, "bspline")
     got = tmc.correct_motion(img.to(dev), field.to(dev), 1.1, grid_type="bspline")
     assert rel_l2(got, want) <= REL_L2
@@ -157,6 +158,30 @@ def test_correct_motion_shared_memory_tiles(dev, amplitude, tiled, monkeypatch):
     again = total.clone()
     tmc.correct_motion_sum(img.to(dev), field.to(dev), 1.1, grid_type="bspline", out=again, accumulate=True)
     assert rel_l2(again, 2 * want.sum(dim=0)) <= REL_L2
+
+
+def test_tma_and_global_memory_kernels_agree(dev, monkeypatch):
+    """Same arithmetic up to the evaluation order of the Keys weights: 2048^2, shifts of a few pixels plus one corner
+    pushed far outside, normalised output."""
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn((7, 2048, 2048), generator=g).to(dev)
+    field = torch.randn((2, 3, 5, 5), generator=g) * 4.0
+    field[:, :, 0, 0] = 90.0
+    field = field.to(dev)
+    from torch_motion_correction_b200 import _ops
+    from torch_motion_correction_b200._common import grid_kind
+
+    stats = _ops.stack_stats(img)
+    lattice = _ops.spline_lattice(field, grid_kind("bspline"), 7, 50, 50)
+    outs = {}
+    for tma in ("0", "1"):
+        monkeypatch.setenv("TMC_WARP_TMA", tma)
+        stack, total = torch.empty_like(img), torch.empty_like(img[0])
+        _ops.warp_lattice(img, lattice, 0.83, mean_std=stats, out_stack=stack, out_sum=total)
+        outs[tma] = (stack, total)
+    assert rel_l2(outs["1"][0], outs["0"][0]) <= 2e-6
+    assert rel_l2(outs["1"][1], outs["0"][1]) <= 2e-6
+    assert rel_l2(outs["1"][1], outs["1"][0].sum(dim=0)) <= 1e-6
 
 
 def test_frame_split_sum_matches_whole(dev):

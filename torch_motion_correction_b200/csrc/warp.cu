@@ -142,13 +142,20 @@ constexpr int kRows = TMC_WARP_ROWS;         // vertically adjacent output pixel
 
 // Stage 1: interpolate every lattice row along x once per (frame, channel, lattice row, image
 // column): RX[f][ch][a][x] = sum_b wx_b(x) * L[f][ch][a][jx_b(x)].  Same x-then-y order as ATen.
-__global__ void lattice_xinterp_kernel(const float* __restrict__ lattice, int T, int lh, int lw, int W, float* __restrict__ rx) {
+// pad == 1: every (frame, channel) plane gets lh + 3 rows, row p holding lattice row reflect(p - 1) -- the reflection
+// padding of the y taps materialised, so that the 4 taps of a pixel are always 4 consecutive rows (i0 .. i0 + 3).
+constexpr int kRxPad = 3;
+__global__ void lattice_xinterp_kernel(const float* __restrict__ lattice, int T, int lh, int lw, int W, float* __restrict__ rx,
+                                       int pad) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= W) return;
   const LatticeAxis lx = lattice_axis(x, W, lw);
-  const long rows = (long)T * 2 * lh;
+  const int lhp = lh + kRxPad * pad;
+  const long rows = (long)T * 2 * lhp;
   for (long r = blockIdx.y; r < rows; r += gridDim.y) {
-    const float* p = lattice + r * lw;
+    const long plane = r / lhp;
+    const int a = reflect_index((int)(r - plane * lhp) - pad, lh);
+    const float* p = lattice + (plane * lh + a) * lw;
     rx[r * W + x] = lx.w[0] * __ldg(p + lx.j[0]) + lx.w[1] * __ldg(p + lx.j[1]) + lx.w[2] * __ldg(p + lx.j[2]) +
                     lx.w[3] * __ldg(p + lx.j[3]);
   }
@@ -183,10 +190,10 @@ __device__ __noinline__ float warp_pixel_generic(const float* __restrict__ image
                                                  int lh, float inv_px, float mean, float inv_std, float* __restrict__ out_stack,
                                                  int x, int y) {
   const LatticeAxis a = lattice_axis(y, H, lh);
-  const size_t rx_plane = (size_t)lh * W;
+  const size_t rx_plane = (size_t)(lh + kRxPad) * W;  // padded rows: lattice row j lives in row j + 1
   float acc = 0.f;
   for (int f = 0; f < T; ++f) {
-    const float* Ry = rx + (size_t)f * 2 * rx_plane + x;
+    const float* Ry = rx + (size_t)f * 2 * rx_plane + x + W;
     const float* Rx = Ry + rx_plane;
     float sy = a.w[0] * __ldg(Ry + (size_t)a.j[0] * W), sx = a.w[0] * __ldg(Rx + (size_t)a.j[0] * W);
 #pragma unroll
@@ -231,7 +238,7 @@ warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const 
   {
     const LatticeAxis a0 = lattice_axis(y_base, H, lh);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) jy[k] = a0.j[k] * W;
+    for (int k = 0; k < 4; ++k) jy[k] = (a0.j[k] + 1) * W;  // padded rows: lattice row j lives in row j + 1
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
       const LatticeAxis a = lattice_axis(min(y_base + r, y_last), H, lh);
@@ -272,7 +279,7 @@ warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const 
   const float2 inv_px = dup(1.0f / pixel_spacing);
   const float xf = (float)x;
   // all loads are (CTA-uniform 64-bit base) + (32-bit offset): no per-thread 64-bit pointer arithmetic
-  const unsigned rx_plane = (unsigned)lh * (unsigned)W;
+  const unsigned rx_plane = (unsigned)(lh + kRxPad) * (unsigned)W;
   unsigned jo[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) jo[k] = (unsigned)jy[k] + (unsigned)x;
@@ -399,193 +406,7 @@ warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const 
   }
 }
 
-// ---- interior tiles: frame tiles staged in shared memory ------------------------------------------------------------
-// One CTA = kTX x kTY output pixels (thread = one column x kRows rows, kTY / kRows thread rows).  Per frame the CTA
-// needs the frame region displaced by the local shift: the box origin follows the shift at the tile centre (rounded;
-// x aligned to 16 bytes) and a margin absorbs the variation of the shift across the tile.  Boxes are copied with 16-byte
-// cp.async one frame ahead (double buffer); taps are then 16 shared-memory loads at immediate offsets of one base
-// (one wavefront each, no tag lookup, no per-tap address arithmetic).  A pixel whose taps leave the box (cannot happen
-// for fields smoother than kMargin px per tile) is gathered from global memory instead.  The launch covers tiles whose
-// boxes lie inside the image for |shift| <= 56 px (64-px border strips); the image border is done by warp_lattice_kernel.
-constexpr int kTX = 64, kTY = 16, kMargin = 4;
-constexpr int kBoxW = kTX + 2 * kMargin + 8;  // 2 + 1 tap columns, up to 3 columns of alignment slack -> 80 loaded columns
-constexpr int kBoxS = 96;                     // row stride: a multiple of 32 words keeps lanes on different rows conflict-free
-constexpr int kBoxH = kTY + 2 * kMargin + 3;  // 27
-constexpr int kTiledThreads = kTX * (kTY / kRows);
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src));
-}
-
-template <bool WRITE_STACK, bool WRITE_SUM, bool NORMALISE>
-__global__ void __launch_bounds__(kTiledThreads, 3)
-warp_lattice_tiled_kernel(const float* __restrict__ image, int T, int H, int W, const float* __restrict__ rx, int lh,
-                          float pixel_spacing, const float* __restrict__ mean_std, float* __restrict__ out_stack,
-                          float* __restrict__ out_sum, int accumulate_sum, int x_begin, int y_begin) {
-  extern __shared__ __align__(16) float tsm[];
-  float* box = tsm;                                             // [2][kBoxH][kBoxS]
-  int* origin = reinterpret_cast<int*>(tsm + 2 * kBoxH * kBoxS);  // [T][2] = (oy, ox)
-  __shared__ int all_inside;
-  const int tid = threadIdx.y * kTX + threadIdx.x;
-  const int x0 = x_begin + blockIdx.x * kTX, y0 = y_begin + blockIdx.y * kTY;
-  const int x = x0 + threadIdx.x;
-  const int y_base = y0 + threadIdx.y * kRows;
-  const float inv_px_s = 1.0f / pixel_spacing;
-  if (tid == 0) all_inside = 1;
-  __syncthreads();
-  // box origin of every frame from the shift at the tile centre
-  for (int f = tid; f < T; f += kTiledThreads) {
-    const int yc = y0 + kTY / 2, xc = x0 + kTX / 2;
-    const LatticeAxis a = lattice_axis(yc, H, lh);
-    const size_t plane = (size_t)lh * W;
-    const float* Ry = rx + (size_t)f * 2 * plane + xc;
-    float sy = 0.f, sx = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      sy = fmaf(a.w[k], __ldg(Ry + (size_t)a.j[k] * W), sy);
-      sx = fmaf(a.w[k], __ldg(Ry + plane + (size_t)a.j[k] * W), sx);
-    }
-    const int oy = y0 + (int)floorf(sy * inv_px_s) - kMargin - 1;
-    const int ox = (x0 + (int)floorf(sx * inv_px_s) - kMargin - 1) & ~3;
-    origin[2 * f] = oy;
-    origin[2 * f + 1] = ox;
-    if (!(oy >= 0 && oy + kBoxH <= H && ox >= 0 && ox + kBoxW <= W)) all_inside = 0;  // also catches NaN shifts
-  }
-  __syncthreads();
-  float mean = 0.f, inv_std = 1.f;
-  if (NORMALISE) {
-    mean = __ldg(mean_std);
-    inv_std = 1.0f / __ldg(mean_std + 1);
-  }
-  // lattice taps along y
-  int jy[4];
-  float wy[kRows][4];
-  bool same_cell = true;
-  {
-    const LatticeAxis a0 = lattice_axis(y_base, H, lh);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) jy[k] = a0.j[k] * W;
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const LatticeAxis a = lattice_axis(y_base + r, H, lh);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        wy[r][k] = a.w[k];
-        same_cell = same_cell && (a.j[k] == a0.j[k]);
-      }
-    }
-  }
-  if (!all_inside) {
-    // a shift beyond kMaxShift somewhere in this tile: generic path for the whole CTA
-    for (int r = 0; r < kRows; ++r) {
-      const int y = y_base + r;
-      const float a = warp_pixel_generic<WRITE_STACK, NORMALISE>(image, T, H, W, rx, lh, inv_px_s, mean, inv_std, out_stack, x, y);
-      if (WRITE_SUM) {
-        float* o = out_sum + (long)y * W + x;
-        *o = accumulate_sum ? (*o + a) : a;
-      }
-    }
-    return;
-  }
-  if (!same_cell) {
-    // this thread's rows straddle a lattice cell (warp-uniform, ~kRows in every H / lh rows): generic path now, then it
-    // only helps loading the boxes
-    for (int r = 0; r < kRows; ++r) {
-      const int y = y_base + r;
-      const float a = warp_pixel_generic<WRITE_STACK, NORMALISE>(image, T, H, W, rx, lh, inv_px_s, mean, inv_std, out_stack, x, y);
-      if (WRITE_SUM) {
-        float* o = out_sum + (long)y * W + x;
-        *o = accumulate_sum ? (*o + a) : a;
-      }
-    }
-  }
-  auto issue_box = [&](int f) {
-    const int oy = origin[2 * f], ox = origin[2 * f + 1];
-    const float* src = image + (size_t)f * H * W + (size_t)oy * W + ox;
-    float* dst = box + (f & 1) * (kBoxH * kBoxS);
-    for (int i = tid; i < kBoxH * (kBoxW / 4); i += kTiledThreads) {
-      const int r = i / (kBoxW / 4), c4 = i - r * (kBoxW / 4);
-      cp_async16(dst + r * kBoxS + 4 * c4, src + (size_t)r * W + 4 * c4);
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-  };
-  issue_box(0);
-
-  float acc[kRows];
-#pragma unroll
-  for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
-  const float dy = __fsub_rn(__fmul_rn(0.5f, (float)H), 0.5f), dx = __fsub_rn(__fmul_rn(0.5f, (float)W), 0.5f);
-  const float2 nden = f2(-dy, -dx), rcp = f2(__frcp_rn(dy), __frcp_rn(dx));
-  const float2 scale = f2((float)(H - 1), (float)(W - 1));
-  const float2 inv_px = dup(inv_px_s);
-  const float xf = (float)x;
-  const unsigned rx_plane = (unsigned)lh * (unsigned)W;
-  const float* rx_frame = rx + x;
-  for (int f = 0; f < T; ++f) {
-    float2 R[4];
-    if (same_cell) {  // issued before the wait below: in flight while the box lands
-#pragma unroll
-      for (int k = 0; k < 4; ++k) R[k] = f2(__ldg(rx_frame + jy[k]), __ldg(rx_frame + rx_plane + jy[k]));
-      rx_frame += 2 * (size_t)rx_plane;
-    }
-    if (f + 1 < T) {
-      issue_box(f + 1);
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    }
-    __syncthreads();  // frame f's box is complete for every thread
-    const float* frame = image + (size_t)f * H * W;
-    const float* bx = box + (f & 1) * (kBoxH * kBoxS);
-    const int oy = origin[2 * f], ox = origin[2 * f + 1];
-    if (same_cell) {
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int y = y_base + r;
-      float2 s = __fmul2_rn(dup(wy[r][0]), R[0]);
-      s = __ffma2_rn(dup(wy[r][1]), R[1], s);
-      s = __ffma2_rn(dup(wy[r][2]), R[2], s);
-      s = __ffma2_rn(dup(wy[r][3]), R[3], s);
-      const float2 c = __fadd2_rn(f2((float)y, xf), __fmul2_rn(s, inv_px));
-      const float2 q0 = __fmul2_rn(c, rcp);
-      const float2 q = __ffma2_rn(__ffma2_rn(q0, nden, c), rcp, q0);
-      const float2 g = __fadd2_rn(q, dup(-1.0f));
-      const float2 u = __fmul2_rn(__fmul2_rn(__fadd2_rn(g, dup(1.0f)), dup(0.5f)), scale);
-      const float2 fl = f2(floorf(u.x), floorf(u.y));
-      const int by = (int)fl.x - 1 - oy, bxo = (int)fl.y - 1 - ox;  // first tap inside the box
-      float v;
-      if ((unsigned)by <= (unsigned)(kBoxH - 4) && (unsigned)bxo <= (unsigned)(kBoxW - 4)) {
-        float2 w[4];  // .x = weight along y, .y = weight along x
-        cubic_weights2(__ffma2_rn(fl, dup(-1.0f), u), w);
-        const float* p = bx + by * kBoxS + bxo;
-        float2 r01 = __fmul2_rn(dup(w[0].y), f2(p[0], p[kBoxS]));
-        float2 r23 = __fmul2_rn(dup(w[0].y), f2(p[2 * kBoxS], p[3 * kBoxS]));
-#pragma unroll
-        for (int b = 1; b < 4; ++b) {
-          r01 = __ffma2_rn(dup(w[b].y), f2(p[b], p[kBoxS + b]), r01);
-          r23 = __ffma2_rn(dup(w[b].y), f2(p[2 * kBoxS + b], p[3 * kBoxS + b]), r23);
-        }
-        const float2 t2 = __ffma2_rn(f2(w[2].x, w[3].x), r23, __fmul2_rn(f2(w[0].x, w[1].x), r01));
-        v = t2.x + t2.y;
-      } else {
-        v = gather_border(frame, H, W, c.x, c.y);
-      }
-      if (NORMALISE) v = (v - mean) * inv_std;
-      if (WRITE_STACK) out_stack[((size_t)f * H + y) * W + x] = v;
-      if (WRITE_SUM) acc[r] += v;
-    }
-    }
-    __syncthreads();  // everyone is done with this buffer before frame f + 2 lands in it
-  }
-  if (WRITE_SUM && same_cell) {
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      float* o = out_sum + (long)(y_base + r) * W + x;
-      *o = accumulate_sum ? (*o + acc[r]) : acc[r];
-    }
-  }
-}
+#include "warp_tma.cuh"
 
 // ---- backward of the warp w.r.t. the shift lattice (correct_motion_two_grids, grad=True) ------------------
 // d out / d shift = (1 / px) * sum_ab w'_a(t_y) w_b(t_x) tap_ab   (ATen grid_sampler_2d_backward, bicubic:
@@ -747,7 +568,7 @@ __global__ void pixel_tyx_kernel(int H, int W, int T, int frame_offset, int tota
 
 }  // namespace
 
-TMC_API long tmc_warp_workspace_floats(int t, int w, int lh) { return (long)t * 2 * lh * w; }
+TMC_API long tmc_warp_workspace_floats(int t, int w, int lh) { return (long)t * 2 * (lh + kRxPad) * w; }
 
 // image (t,h,w); lattice (t,2,lh,lw) in Angstrom; mean_std nullable device float[2] (input affine
 // (v - mean) / std applied to the warped value, zero outside); out_stack (t,h,w) nullable;
@@ -760,34 +581,66 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
   TMC_CHECK_ARG(out_stack || out_sum, "warp_lattice: need out_stack and/or out_sum");
   TMC_CHECK_ARG(t >= 1 && h >= 2 && w >= 2 && lh >= 1 && lw >= 1, "warp_lattice: bad shape t=%d h=%d w=%d lattice=%dx%d", t,
                 h, w, lh, lw);
-  TMC_CHECK_ARG((long)lh * w < (1l << 31), "warp_lattice: lattice rows x width overflows int");
   TMC_CHECK_ARG(pixel_spacing > 0.f, "warp_lattice: pixel_spacing must be > 0");
+  TMC_CHECK_ARG((long)(lh + kRxPad) * w < (1l << 31), "warp_lattice: lattice rows x width overflows int");
   {
-    long rows = (long)t * 2 * lh;
+    long rows = (long)t * 2 * (lh + kRxPad);
     dim3 g1(tmc_div_up(w, 128), (unsigned)(rows < 4096 ? rows : 4096));
-    lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, workspace); tmc_count_launch();
+    lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, workspace, 1); tmc_count_launch();
   }
   const bool s = out_stack != nullptr, a = out_sum != nullptr, n = mean_std != nullptr;
-  // interior tiles on the shared-memory kernel, the 64-px border strips (and everything when the rows are not
-  // 16-byte aligned or the image is small) on the global-memory kernel
-  int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0;  // interior rectangle, empty by default
-  // measured on B200 (C2): 5.9 ms against 4.3 ms for the global-memory kernel alone -- the per-frame barriers and the
-  // box copies cost more than the L1 tag lookups they save; kept (tested) behind TMC_WARP_TILED=1 for further work
-  const char* tiled_env = getenv("TMC_WARP_TILED");  // read per call: tests toggle it
-  const bool tiled_on = tiled_env && tiled_env[0] == '1';
-  if (tiled_on && w % 4 == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0 && w >= 128 + kTX && h >= 128 + kTY && kRows == 4) {
-    ix0 = 64;
-    ix1 = 64 + ((w - 128) / kTX) * kTX;
-    iy0 = 64;
-    iy1 = 64 + ((h - 128) / kTY) * kTY;
+  // TMC_WARP_TMA=0 keeps everything on the global-memory kernel (A/B testing; read per call: tests toggle it)
+  const char* tma_env = getenv("TMC_WARP_TMA");
+  const bool tma_on = !(tma_env && tma_env[0] == '0');
+  if (tma_on && tma::supported(image, workspace, t, h, w, lh)) {
+    // frame tiles staged by TMA, one persistent CTA per SM
+    CUtensorMap img_map, rx_map;
+    const bool ok = tma::make_map_3d(&img_map, image, (uint64_t)w, (uint64_t)h, (uint64_t)t, tma::kBoxW, tma::kBoxH, 1) &&
+                    tma::make_map_3d(&rx_map, workspace, (uint64_t)w, (uint64_t)(lh + kRxPad), (uint64_t)2 * t, tma::kTX,
+                                     tma::kRxRows, 2);
+    if (ok) {
+      tma::Params prm;
+      prm.image = image;
+      prm.T = t;
+      prm.H = h;
+      prm.W = w;
+      prm.rx = workspace;
+      prm.lh = lh;
+      prm.pixel_spacing = pixel_spacing;
+      prm.mean_std = mean_std;
+      prm.out_stack = out_stack;
+      prm.out_sum = out_sum;
+      prm.accumulate_sum = accumulate_sum;
+      prm.tiles_x = tmc_div_up(w, tma::kTX);
+      prm.n_tiles = prm.tiles_x * tmc_div_up(h, tma::kTY);
+      int dev_id = 0, sms = 148;
+      TMC_CUDA(cudaGetDevice(&dev_id));
+      TMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+      const int grid = prm.n_tiles < sms ? prm.n_tiles : sms;
+#define LAUNCH_TMA(S, A, N)                                                                                                  \
+  {                                                                                                                          \
+    TMC_CUDA(cudaFuncSetAttribute(tma::warp_tma_kernel<S, A, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
+                                  (int)tma::kSmemBytes));                                                                    \
+    tma::warp_tma_kernel<S, A, N><<<grid, tma::kThreads, tma::kSmemBytes, stream>>>(img_map, rx_map, prm);                    \
   }
-  auto launch_rect = [&](int xb, int xe, int yb, int ye) -> int {
-    if (xb >= xe || yb >= ye) return TMC_OK;
+      if (s && a && n) LAUNCH_TMA(true, true, true)
+      else if (s && a) LAUNCH_TMA(true, true, false)
+      else if (s && n) LAUNCH_TMA(true, false, true)
+      else if (s) LAUNCH_TMA(true, false, false)
+      else if (n) LAUNCH_TMA(false, true, true)
+      else LAUNCH_TMA(false, true, false)
+#undef LAUNCH_TMA
+      tmc_count_launch();
+      TMC_CHECK_LAUNCH("tmc_warp_lattice(tma)");
+      return TMC_OK;
+    }
+  }
+  {
     dim3 block(kTileX, kTileYGroups);
-    dim3 grid(tmc_div_up(xe - xb, kTileX), tmc_div_up(ye - yb, kTileYGroups * kRows));
+    dim3 grid(tmc_div_up(w, kTileX), tmc_div_up(h, kTileYGroups * kRows));
 #define LAUNCH(S, A, N)                                                                                          \
   warp_lattice_kernel<S, A, N><<<grid, block, 0, stream>>>(image, t, h, w, workspace, lh, pixel_spacing, mean_std, \
-                                                           out_stack, out_sum, accumulate_sum, xb, xe, yb, ye)
+                                                           out_stack, out_sum, accumulate_sum, 0, w, 0, h)
     if (s && a && n) LAUNCH(true, true, true);
     else if (s && a) LAUNCH(true, true, false);
     else if (s && n) LAUNCH(true, false, true);
@@ -796,38 +649,6 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
     else LAUNCH(false, true, false);
 #undef LAUNCH
     tmc_count_launch();
-    return TMC_OK;
-  };
-  if (ix1 > ix0 && iy1 > iy0) {
-    const size_t smem = (size_t)2 * kBoxH * kBoxS * sizeof(float) + (size_t)2 * t * sizeof(int);
-    dim3 block(kTX, kTY / kRows);
-    dim3 grid((ix1 - ix0) / kTX, (iy1 - iy0) / kTY);
-#define LAUNCH_T(S, A, N)                                                                                              \
-  {                                                                                                                    \
-    TMC_CUDA(cudaFuncSetAttribute(warp_lattice_tiled_kernel<S, A, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    warp_lattice_tiled_kernel<S, A, N><<<grid, block, smem, stream>>>(image, t, h, w, workspace, lh, pixel_spacing, mean_std, \
-                                                                     out_stack, out_sum, accumulate_sum, ix0, iy0);     \
-  }
-    if (smem <= 200 * 1024) {
-      if (s && a && n) LAUNCH_T(true, true, true)
-      else if (s && a) LAUNCH_T(true, true, false)
-      else if (s && n) LAUNCH_T(true, false, true)
-      else if (s) LAUNCH_T(true, false, false)
-      else if (n) LAUNCH_T(false, true, true)
-      else LAUNCH_T(false, true, false)
-      tmc_count_launch();
-    } else {
-      ix1 = ix0;  // too many frames for the origin table: everything on the global-memory kernel
-    }
-#undef LAUNCH_T
-  }
-  if (ix1 > ix0 && iy1 > iy0) {
-    launch_rect(0, w, 0, iy0);        // top strip
-    launch_rect(0, w, iy1, h);        // bottom strip
-    launch_rect(0, ix0, iy0, iy1);    // left strip
-    launch_rect(ix1, w, iy0, iy1);    // right strip
-  } else {
-    launch_rect(0, w, 0, h);
   }
   TMC_CHECK_LAUNCH("tmc_warp_lattice");
   return TMC_OK;
@@ -870,7 +691,7 @@ TMC_API int tmc_warp_lattice_backward(const float* image, int t, int h, int w, c
   float* rx = workspace;
   float* grad_rx = workspace + rows * w;
   dim3 g1(tmc_div_up(w, 128), (unsigned)(rows < 4096 ? rows : 4096));
-  lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, rx); tmc_count_launch();
+  lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, rx, 0); tmc_count_launch();
   TMC_CUDA(cudaMemsetAsync(grad_rx, 0, sizeof(float) * (size_t)rows * w, stream));
   TMC_CUDA(cudaMemsetAsync(grad_lattice, 0, sizeof(float) * (size_t)rows * lw, stream));
   dim3 g2(tmc_div_up(w, 128), h);

@@ -1,0 +1,411 @@
+// Fused resample-and-sum with frame tiles staged by TMA (included by warp.cu inside its anonymous namespace).
+//
+// Replaces the per-pixel global-memory gathers of warp_lattice_kernel for images whose rows are 16-byte aligned
+// (W % 4 == 0); same arithmetic, same results (correct_motion.py:81-185).
+//
+// One persistent CTA per SM walks over 64 x 28 output tiles; for every tile it visits the T frames in order:
+//   * a producer warp computes, per frame, where the tile lands in the frame (tile origin + the field's shift at the tile
+//     centre) and issues two tensor-map TMA loads (cp.async.bulk.tensor) into one slot of a ring of shared-memory stages:
+//     the 76 x 39 pixel box of the frame around that landing point (hardware zero-fill outside the frame) and the
+//     64 x 16 x 2 block of the x-interpolated shift lattice the tile's pixels need;
+//   * 14 consumer warps (thread = one column x 4 rows of the tile) wait on the stage's "full" mbarrier, evaluate the
+//     shift of their pixels from the staged lattice rows, run the reference's fp32 coordinate chain (packed fp32x2,
+//     both axes at once), read their 4 x 4 taps from the staged box at immediate offsets of one address (7 x 4 loads
+//     shared by the 4 vertically stacked pixels whenever their sampling points are stacked too) and release the stage
+//     through its "empty" mbarrier.  No block-wide barrier in the frame loop; frame sums live in registers.
+//   Pixels whose taps leave the box (shift varying by more than the 4-px margin inside one tile) or touch the image
+//   border (border-clamped taps / zero outside) take the generic global-memory path.
+#pragma once
+#include <cuda.h>
+
+namespace tma {
+
+constexpr int kTX = 64, kTY = 28;       // output tile: 14 consumer warps + the producer warp = 15 warps -> 128 registers
+constexpr int kMargin = 4;              // how far a pixel's shift may differ from the tile-centre shift
+constexpr int kBoxW = kTX + 2 * kMargin + 4;   // 76: + 3 tap columns, rounded up to 16 bytes
+constexpr int kBoxH = kTY + 2 * kMargin + 3;   // 39
+constexpr int kRxRows = 16;             // lattice rows staged per tile and channel
+constexpr int kImgBytes = kBoxW * kBoxH * 4;                      // 11856
+constexpr int kImgBytesPadded = (kImgBytes + 127) / 128 * 128;    // 11904
+constexpr int kRxBytes = kTX * kRxRows * 2 * 4;                   // 8192
+constexpr int kStageBytes = kImgBytesPadded + kRxBytes;
+constexpr int kStages = 8;
+constexpr int kConsumers = kTX * (kTY / kRows);  // 448 threads, 14 warps
+constexpr int kThreads = kConsumers + 32;        // + the producer warp
+constexpr int kConsumerWarps = kConsumers / 32;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 128;  // + alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 3-D tiled tensor-map load: box at (c0, c1, c2) (innermost first) -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Keys cubic-convolution weights (A = -0.75, ATen's bicubic) of two fractions at once (.x = y axis, .y = x axis) in
+// factored form: w0 = A t (1 - t)^2, w3 = A t^2 (1 - t), w1 = ((A + 2) t - (A + 3)) t^2 + 1, w2 = w1(1 - t).  Same
+// polynomials as get_cubic_upsample_coefficients (cubic_weights2), 11 instead of 15 packed instructions; the results
+// differ from ATen's evaluation order by rounding only (<= 2e-7 absolute, against a 1e-4 tolerance on the frame sum).
+__device__ __forceinline__ void keys_weights2(float2 t, float2 (&w)[4]) {
+  const float2 A = dup(kA), A2 = dup(kA + 2.0f), mA3 = dup(-(kA + 3.0f)), one = dup(1.0f);
+  const float2 u = __ffma2_rn(t, dup(-1.0f), one);
+  const float2 a = __fmul2_rn(A, __fmul2_rn(t, u));
+  w[0] = __fmul2_rn(a, u);
+  w[3] = __fmul2_rn(a, t);
+  w[1] = __ffma2_rn(__ffma2_rn(A2, t, mA3), __fmul2_rn(t, t), one);
+  w[2] = __ffma2_rn(__ffma2_rn(A2, u, mA3), __fmul2_rn(u, u), one);
+}
+
+struct Params {
+  const float* image;
+  int T, H, W;
+  const float* rx;  // (T, 2, lh + 3, W): x-interpolated lattice, rows padded by reflection (row p <-> lattice row p - 1)
+  int lh;
+  float pixel_spacing;
+  const float* mean_std;
+  float* out_stack;
+  float* out_sum;
+  int accumulate_sum;
+  int tiles_x, n_tiles;
+};
+
+template <bool WRITE_STACK, bool WRITE_SUM, bool NORMALISE>
+__global__ void __launch_bounds__(kThreads, 1)
+warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_constant__ CUtensorMap rx_map, const Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  // per stage: {oy + 1, ox + 1, by_lo, by_n, bx_lo, bx_n, -, -}: box origin (+1: the first tap is one before the floor) and
+  // the first-tap positions (by - by_lo <= by_n, unsigned) that keep 4 + 3 stacked tap rows / 4 tap columns inside the
+  // box AND inside the image (the zero-filled part of a box that hangs over the frame edge is never used)
+  __shared__ __align__(16) int stage_hdr[kStages][8];
+  unsigned char* stages = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const int tid = threadIdx.x;
+  const int T = p.T, H = p.H, W = p.W, lh = p.lh;
+  const int lhp = lh + 3;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const float inv_px_s = 1.0f / p.pixel_spacing;
+
+  if (tid >= kConsumers) {
+    // ---------------- producer warp ----------------
+    const int lane = tid - kConsumers;
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int x0 = (tile % p.tiles_x) * kTX, y0 = (tile / p.tiles_x) * kTY;
+      const int yc = min(y0 + kTY / 2, H - 1), xc = min(x0 + kTX / 2, W - 1);
+      const LatticeAxis ac = lattice_axis(yc, H, lh);
+      const int i0_tile = lattice_axis(y0, H, lh).i0;
+      for (int f0 = 0; f0 < T; f0 += 32) {
+        // lane l: landing point of the tile in frame f0 + l (shift of the tile centre, rounded down)
+        int oy = 0, ox = 0;
+        if (f0 + lane < T) {
+          const float* Ry = p.rx + ((size_t)(f0 + lane) * 2) * lhp * W + xc;
+          const float* Rx = Ry + (size_t)lhp * W;
+          float sy = 0.f, sx = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            sy = fmaf(ac.w[k], __ldg(Ry + (size_t)(ac.i0 + k) * W), sy);
+            sx = fmaf(ac.w[k], __ldg(Rx + (size_t)(ac.i0 + k) * W), sx);
+          }
+          // clamped: a wild (or NaN) shift must not overflow the int conversion; such tiles take the generic path
+          oy = y0 + (int)fminf(fmaxf(floorf(sy * inv_px_s), -1e6f), 1e6f) - kMargin - 1;
+          ox = x0 + (int)fminf(fmaxf(floorf(sx * inv_px_s), -1e6f), 1e6f) - kMargin - 1;
+        }
+        const int nf = min(32, T - f0);
+        for (int i = 0; i < nf; ++i) {
+          const int foy = __shfl_sync(0xffffffffu, oy, i), fox = __shfl_sync(0xffffffffu, ox, i);
+          if (lane == 0) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);  // the consumers have released this slot
+            {
+              const int by_lo = max(0, -foy), by_n = min(kBoxH - 4, H - 4 - foy) - by_lo - (kRows - 1);
+              const int bx_lo = max(0, -fox), bx_n = min(kBoxW - 4, W - 4 - fox) - bx_lo;
+              int* hdr = stage_hdr[stage];
+              hdr[0] = foy + 1;
+              hdr[1] = fox + 1;
+              hdr[2] = by_n >= 0 ? by_lo : 0x40000000;  // empty range: nothing passes
+              hdr[3] = by_n >= 0 ? by_n : 0;
+              hdr[4] = bx_n >= 0 ? bx_lo : 0x40000000;
+              hdr[5] = bx_n >= 0 ? bx_n : 0;
+            }
+            unsigned char* dst = stages + (size_t)stage * kStageBytes;
+            mbar_expect_tx(&full_bar[stage], kImgBytes + kRxBytes);
+            tma_load_3d(dst, &img_map, fox, foy, f0 + i, &full_bar[stage]);
+            tma_load_3d(dst + kImgBytesPadded, &rx_map, x0, i0_tile, 2 * (f0 + i), &full_bar[stage]);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps ----------------
+  const int tx = tid & (kTX - 1), tyg = tid >> 6;
+  const int lane = tid & 31;
+  float mean = 0.f, inv_std = 1.f;
+  if (NORMALISE) {
+    mean = __ldg(p.mean_std);
+    inv_std = 1.0f / __ldg(p.mean_std + 1);
+  }
+  // grid_sample round trip constants, .x = y axis (H), .y = x axis (W); see warp_lattice_kernel
+  const float dy = __fsub_rn(__fmul_rn(0.5f, (float)H), 0.5f), dx = __fsub_rn(__fmul_rn(0.5f, (float)W), 0.5f);
+  const float2 nden = f2(-dy, -dx), rcp = f2(__frcp_rn(dy), __frcp_rn(dx));
+  // ((g + 1) * 0.5) * (n - 1) == (g + 1) * (0.5 * (n - 1)) bit for bit: the halving is exact, so is 0.5 * (n - 1)
+  const float2 half_scale = f2(0.5f * (float)(H - 1), 0.5f * (float)(W - 1));
+  const float2 inv_px = dup(inv_px_s);
+  uint32_t stage = 0, phase = 0;
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int x0 = (tile % p.tiles_x) * kTX, y0 = (tile / p.tiles_x) * kTY;
+    const int x = x0 + tx, y_base = y0 + tyg * kRows;
+    const bool active = x < W && y_base < H;
+    const int y_last = H - 1;
+    const int i0_tile = lattice_axis(y0, H, lh).i0;
+    // lattice taps along y of the thread's rows: staged row (i0 - i0_tile + k) of the block, duplicated weights
+    float wy[kRows][4];
+    int lat[kRows];
+    float yf[kRows];
+    bool same_cell = true;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int y = min(y_base + r, y_last);
+      const LatticeAxis a = lattice_axis(y, H, lh);
+      yf[r] = (float)y;
+      lat[r] = min(max(a.i0 - i0_tile, 0), kRxRows - 4) * kTX + tx;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wy[r][k] = a.w[k];
+      same_cell = same_cell && (lat[r] == lat[0]);
+    }
+    const float xf = (float)min(x, W - 1);
+    float acc[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
+
+    for (int f = 0; f < T; ++f) {
+      mbar_wait(&full_bar[stage], phase);
+      if (active) {
+        const float* simg = reinterpret_cast<const float*>(stages + (size_t)stage * kStageBytes);
+        const float* srx = simg + kImgBytesPadded / 4;
+        const int4 org = *reinterpret_cast<const int4*>(stage_hdr[stage]);       // oy + 1, ox + 1, by_lo, by_n
+        const int2 xr = *reinterpret_cast<const int2*>(stage_hdr[stage] + 4);    // bx_lo, bx_n
+        float2 R[4];
+        if (same_cell) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) R[k] = f2(srx[lat[0] + k * kTX], srx[kRxRows * kTX + lat[0] + k * kTX]);
+        }
+        float2 c[kRows], fl[kRows], frac[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          if (!same_cell) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) R[k] = f2(srx[lat[r] + k * kTX], srx[kRxRows * kTX + lat[r] + k * kTX]);
+          }
+          float2 s = __fmul2_rn(dup(wy[r][0]), R[0]);
+          s = __ffma2_rn(dup(wy[r][1]), R[1], s);
+          s = __ffma2_rn(dup(wy[r][2]), R[2], s);
+          s = __ffma2_rn(dup(wy[r][3]), R[3], s);
+          // Angstrom -> px, then pixel_grid + pixel_shifts (two roundings, like the reference)
+          c[r] = __fadd2_rn(f2(yf[r], xf), __fmul2_rn(s, inv_px));
+          // grid_sample round trip: g = c / (0.5 n - 0.5) - 1 ; u = ((g + 1) / 2) (n - 1); the division as
+          // q0 = c * rcp and one Newton step on the residual (correctly rounded, see Divisor)
+          const float2 q0 = __fmul2_rn(c[r], rcp);
+          const float2 q = __ffma2_rn(__ffma2_rn(q0, nden, c[r]), rcp, q0);
+          const float2 g = __fadd2_rn(q, dup(-1.0f));
+          const float2 u = __fmul2_rn(__fadd2_rn(g, dup(1.0f)), half_scale);
+          fl[r] = f2(floorf(u.x), floorf(u.y));
+          frac[r] = __ffma2_rn(fl[r], dup(-1.0f), u);
+        }
+        // the 4 sampling points are vertically adjacent (same tap columns, consecutive tap rows: the shifts differ by
+        // ~1e-3 px per row, so almost always) and their 7 x 4 taps lie inside the box and inside the image
+        const int by0 = (int)fl[0].x - org.x, bx0 = (int)fl[0].y - org.y;
+        bool stacked = (unsigned)(by0 - org.z) <= (unsigned)org.w && (unsigned)(bx0 - xr.x) <= (unsigned)xr.y;
+#pragma unroll
+        for (int r = 1; r < kRows; ++r) stacked = stacked && fl[r].x == fl[0].x + (float)r && fl[r].y == fl[0].y;
+        float v[kRows];
+        if (stacked) {
+          // 7 rows of 4 taps serve all 4 pixels; rows (0,1), (2,3), (4,5) are kept as register pairs so that the x pass of
+          // two tap rows is one packed instruction (the x weight enters as a scalar operand)
+          const float* q = simg + by0 * kBoxW + bx0;
+          float2 p01[4], p23[4], p45[4];
+          float r6[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            p01[b] = f2(q[b], q[kBoxW + b]);
+            p23[b] = f2(q[2 * kBoxW + b], q[3 * kBoxW + b]);
+            p45[b] = f2(q[4 * kBoxW + b], q[5 * kBoxW + b]);
+            r6[b] = q[6 * kBoxW + b];
+          }
+          float2 w[4];  // .x = weight along y, .y = weight along x
+          // pixel 0: tap rows 0..3
+          keys_weights2(frac[0], w);
+          {
+            float2 h01 = __fmul2_rn(dup(w[0].y), p01[0]), h23 = __fmul2_rn(dup(w[0].y), p23[0]);
+#pragma unroll
+            for (int b = 1; b < 4; ++b) {
+              h01 = __ffma2_rn(dup(w[b].y), p01[b], h01);
+              h23 = __ffma2_rn(dup(w[b].y), p23[b], h23);
+            }
+            v[0] = fmaf(w[3].x, h23.y, fmaf(w[2].x, h23.x, fmaf(w[1].x, h01.y, w[0].x * h01.x)));
+          }
+          // pixel 1: tap rows 1..4
+          keys_weights2(frac[1], w);
+          {
+            float h1 = w[0].y * p01[0].y, h4 = w[0].y * p45[0].x;
+            float2 h23 = __fmul2_rn(dup(w[0].y), p23[0]);
+#pragma unroll
+            for (int b = 1; b < 4; ++b) {
+              h1 = fmaf(w[b].y, p01[b].y, h1);
+              h4 = fmaf(w[b].y, p45[b].x, h4);
+              h23 = __ffma2_rn(dup(w[b].y), p23[b], h23);
+            }
+            v[1] = fmaf(w[3].x, h4, fmaf(w[2].x, h23.y, fmaf(w[1].x, h23.x, w[0].x * h1)));
+          }
+          // pixel 2: tap rows 2..5
+          keys_weights2(frac[2], w);
+          {
+            float2 h23 = __fmul2_rn(dup(w[0].y), p23[0]), h45 = __fmul2_rn(dup(w[0].y), p45[0]);
+#pragma unroll
+            for (int b = 1; b < 4; ++b) {
+              h23 = __ffma2_rn(dup(w[b].y), p23[b], h23);
+              h45 = __ffma2_rn(dup(w[b].y), p45[b], h45);
+            }
+            v[2] = fmaf(w[3].x, h45.y, fmaf(w[2].x, h45.x, fmaf(w[1].x, h23.y, w[0].x * h23.x)));
+          }
+          // pixel 3: tap rows 3..6
+          keys_weights2(frac[3], w);
+          {
+            float h3 = w[0].y * p23[0].y, h6 = w[0].y * r6[0];
+            float2 h45 = __fmul2_rn(dup(w[0].y), p45[0]);
+#pragma unroll
+            for (int b = 1; b < 4; ++b) {
+              h3 = fmaf(w[b].y, p23[b].y, h3);
+              h6 = fmaf(w[b].y, r6[b], h6);
+              h45 = __ffma2_rn(dup(w[b].y), p45[b], h45);
+            }
+            v[3] = fmaf(w[3].x, h6, fmaf(w[2].x, h45.y, fmaf(w[1].x, h45.x, w[0].x * h3)));
+          }
+        } else {
+          // rare: sampling points not stacked, taps outside the box (shift varying by more than the margin inside the
+          // tile) or at the image border (border-clamped taps / zero outside): per pixel, from the box or from global memory
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) {
+            const int by = (int)fl[r].x - org.x, bx = (int)fl[r].y - org.y;
+            if ((unsigned)(by - org.z) <= (unsigned)(org.w + kRows - 1) && (unsigned)(bx - xr.x) <= (unsigned)xr.y) {
+              const float* q = simg + by * kBoxW + bx;
+              float2 w[4];
+              keys_weights2(frac[r], w);
+              float h[4];
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+                h[a] = fmaf(w[3].y, q[a * kBoxW + 3], fmaf(w[2].y, q[a * kBoxW + 2], fmaf(w[1].y, q[a * kBoxW + 1], w[0].y * q[a * kBoxW])));
+              v[r] = fmaf(w[3].x, h[3], fmaf(w[2].x, h[2], fmaf(w[1].x, h[1], w[0].x * h[0])));
+            } else {
+              v[r] = gather_border(p.image + (size_t)f * H * W, H, W, c[r].x, c[r].y);
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          float o = v[r];
+          if (NORMALISE) o = (o - mean) * inv_std;
+          if (WRITE_STACK && y_base + r < H) p.out_stack[((size_t)f * H + y_base + r) * W + x] = o;
+          if (WRITE_SUM) acc[r] += o;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == kStages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    if (WRITE_SUM && active) {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        if (y_base + r < H) {
+          float* o = p.out_sum + (size_t)(y_base + r) * W + x;
+          *o = p.accumulate_sum ? (*o + acc[r]) : acc[r];
+        }
+      }
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// the driver's tensor-map encoder, looked up through the runtime (no link-time dependency on libcuda)
+inline EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult status;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &status) != cudaSuccess ||
+        status != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return (EncodeTiledFn)ptr;
+  }();
+  return fn;
+}
+
+// fp32 tensor (d2, d1, d0) contiguous, innermost d0; box (b2, b1, b0); out-of-bounds elements read as zero
+inline bool make_map_3d(CUtensorMap* map, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                        uint32_t b2) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {d0 * sizeof(float), d0 * d1 * sizeof(float)};
+  const cuuint32_t box[3] = {b0, b1, b2};
+  const cuuint32_t elem[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, elem,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// the kernel serves this problem: 16-byte aligned rows and lattice cells tall enough for the staged lattice block
+inline bool supported(const float* image, const float* rx, int t, int h, int w, int lh) {
+  if (w % 4 != 0 || (reinterpret_cast<uintptr_t>(image) & 15) != 0 || (reinterpret_cast<uintptr_t>(rx) & 15) != 0) return false;
+  if (h < kTY || w < kTX) return false;
+  // a tile's rows must not span more lattice cells than the staged block holds (16 rows = 12 cells + 4 taps)
+  if (lh >= 2 && (double)(h - 1) / (double)(lh - 1) * (kRxRows - 5) < (double)kTY) return false;
+  if ((long)t * 2 > 0x7fffffffl) return false;
+  return encode_tiled() != nullptr;
+}
+
+}  // namespace tma
