@@ -87,6 +87,7 @@ def evaluate_cubic_grid_3d(data: torch.Tensor, u: torch.Tensor, matrix: torch.Te
     """Evaluate a (c, n0, n1, n2) uniform cubic grid at ``u (..., 3)`` -> ``(..., c)``."""
     lead = u.shape[:-1]
     u = u.reshape(-1, 3).to(data.dtype)
+    matrix = matrix.to(u.device)  # the characteristic matrices are module constants (CPU)
     g = data
     for dim in (1, 2, 3):
         g = _pad_axis_linear(g, dim)
@@ -241,15 +242,18 @@ def circle(radius: float, image_shape, center=None, smoothing_radius: float = 0,
     image_shape = tuple(int(s) for s in image_shape)
     if center is None:
         center = tuple(s // 2 for s in image_shape)
-    distances = coordinate_grid(image_shape, center=center, norm=True, device=None)
-    mask = distances < radius
-    if smoothing_radius == 0:
-        return mask.float().to(device)
-    edt = ndi.distance_transform_edt(torch.logical_not(mask).numpy())
-    edt = torch.as_tensor(edt).float()
-    idx = torch.logical_and(edt > 0, edt <= smoothing_radius)
-    out = mask.float()
-    out[idx] = torch.cos((torch.pi / 2) * (edt[idx] / smoothing_radius))
+    if device is None:
+        device = torch.get_default_device()  # bench.py's ATen-on-CUDA baseline runs this module under torch.device("cuda")
+    with torch.device("cpu"):  # the distance transform is scipy's, on the host
+        distances = coordinate_grid(image_shape, center=center, norm=True, device=None)
+        mask = distances < radius
+        if smoothing_radius == 0:
+            return mask.float().to(device)
+        edt = ndi.distance_transform_edt(torch.logical_not(mask).numpy())
+        edt = torch.as_tensor(edt).float()
+        idx = torch.logical_and(edt > 0, edt <= smoothing_radius)
+        out = mask.float()
+        out[idx] = torch.cos((torch.pi / 2) * (edt[idx] / smoothing_radius))
     return out.to(device)
 
 

@@ -366,8 +366,8 @@ def temporal_smoothing(field: torch.Tensor, window: int):
     for gy in range(field.shape[2]):
         for gx in range(field.shape[3]):
             for c in range(2):
-                series = field[c, :, gy, gx].numpy()
-                out[c, :, gy, gx] = torch.from_numpy(savgol_filter(series, window, 1))
+                series = field[c, :, gy, gx].cpu().numpy()
+                out[c, :, gy, gx] = torch.from_numpy(savgol_filter(series, window, 1)).to(field.device)
     return out
 
 

@@ -179,8 +179,9 @@ def test_tma_and_global_memory_kernels_agree(dev, monkeypatch):
         stack, total = torch.empty_like(img), torch.empty_like(img[0])
         _ops.warp_lattice(img, lattice, 0.83, mean_std=stats, out_stack=stack, out_sum=total)
         outs[tma] = (stack, total)
-    assert rel_l2(outs["1"][0], outs["0"][0]) <= 2e-6
-    assert rel_l2(outs["1"][1], outs["0"][1]) <= 2e-6
+    # the kernels evaluate the Keys weights in different (equivalent) orders: ~1e-7 per weight, 16 taps
+    assert rel_l2(outs["1"][0], outs["0"][0]) <= 5e-6
+    assert rel_l2(outs["1"][1], outs["0"][1]) <= 5e-6
     assert rel_l2(outs["1"][1], outs["1"][0].sum(dim=0)) <= 1e-6
 
 

@@ -613,6 +613,10 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
       prm.accumulate_sum = accumulate_sum;
       prm.tiles_x = tmc_div_up(w, tma::kTX);
       prm.n_tiles = prm.tiles_x * tmc_div_up(h, tma::kTY);
+      {
+        const char* dbg = getenv("TMC_WARP_TMA_DEBUG");
+        prm.debug = dbg ? atoi(dbg) : 0;
+      }
       int dev_id = 0, sms = 148;
       TMC_CUDA(cudaGetDevice(&dev_id));
       TMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));

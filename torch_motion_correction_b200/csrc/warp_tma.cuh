@@ -6,7 +6,7 @@
 // One persistent CTA per SM walks over 64 x 28 output tiles; for every tile it visits the T frames in order:
 //   * a producer warp computes, per frame, where the tile lands in the frame (tile origin + the field's shift at the tile
 //     centre) and issues two tensor-map TMA loads (cp.async.bulk.tensor) into one slot of a ring of shared-memory stages:
-//     the 76 x 39 pixel box of the frame around that landing point (hardware zero-fill outside the frame) and the
+//     the 80 x 39 pixel box of the frame around that landing point (hardware zero-fill outside the frame) and the
 //     64 x 16 x 2 block of the x-interpolated shift lattice the tile's pixels need;
 //   * 14 consumer warps (thread = one column x 4 rows of the tile) wait on the stage's "full" mbarrier, evaluate the
 //     shift of their pixels from the staged lattice rows, run the reference's fp32 coordinate chain (packed fp32x2,
@@ -22,11 +22,11 @@ namespace tma {
 
 constexpr int kTX = 64, kTY = 28;       // output tile: 14 consumer warps + the producer warp = 15 warps -> 128 registers
 constexpr int kMargin = 4;              // how far a pixel's shift may differ from the tile-centre shift
-constexpr int kBoxW = kTX + 2 * kMargin + 4;   // 76: + 3 tap columns, rounded up to 16 bytes
+constexpr int kBoxW = kTX + 2 * kMargin + 8;   // 80: + 3 tap columns + up to 3 columns of alignment slack (see below), 16-byte rows
 constexpr int kBoxH = kTY + 2 * kMargin + 3;   // 39
 constexpr int kRxRows = 16;             // lattice rows staged per tile and channel
-constexpr int kImgBytes = kBoxW * kBoxH * 4;                      // 11856
-constexpr int kImgBytesPadded = (kImgBytes + 127) / 128 * 128;    // 11904
+constexpr int kImgBytes = kBoxW * kBoxH * 4;                      // 12480
+constexpr int kImgBytesPadded = (kImgBytes + 127) / 128 * 128;    // 12544
 constexpr int kRxBytes = kTX * kRxRows * 2 * 4;                   // 8192
 constexpr int kStageBytes = kImgBytesPadded + kRxBytes;
 constexpr int kStages = 8;
@@ -92,6 +92,7 @@ struct Params {
   float* out_sum;
   int accumulate_sum;
   int tiles_x, n_tiles;
+  int debug;  // TMC_WARP_TMA_DEBUG bits: 1 no image loads, 2 no lattice loads, 4 consumers skip the arithmetic
 };
 
 template <bool WRITE_STACK, bool WRITE_SUM, bool NORMALISE>
@@ -142,7 +143,9 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
           }
           // clamped: a wild (or NaN) shift must not overflow the int conversion; such tiles take the generic path
           oy = y0 + (int)fminf(fmaxf(floorf(sy * inv_px_s), -1e6f), 1e6f) - kMargin - 1;
-          ox = x0 + (int)fminf(fmaxf(floorf(sx * inv_px_s), -1e6f), 1e6f) - kMargin - 1;
+          // TMA wants the innermost box coordinate on a 16-byte boundary (measured: any other x raises "illegal
+          // instruction"; tools/tma_probe.cu): rounded down to 4 pixels, the box is 3 columns wider for it
+          ox = (x0 + (int)fminf(fmaxf(floorf(sx * inv_px_s), -1e6f), 1e6f) - kMargin - 1) & ~3;
         }
         const int nf = min(32, T - f0);
         for (int i = 0; i < nf; ++i) {
@@ -161,9 +164,9 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
               hdr[5] = bx_n >= 0 ? bx_n : 0;
             }
             unsigned char* dst = stages + (size_t)stage * kStageBytes;
-            mbar_expect_tx(&full_bar[stage], kImgBytes + kRxBytes);
-            tma_load_3d(dst, &img_map, fox, foy, f0 + i, &full_bar[stage]);
-            tma_load_3d(dst + kImgBytesPadded, &rx_map, x0, i0_tile, 2 * (f0 + i), &full_bar[stage]);
+            mbar_expect_tx(&full_bar[stage], ((p.debug & 1) ? 0 : kImgBytes) + ((p.debug & 2) ? 0 : kRxBytes));
+            if (!(p.debug & 1)) tma_load_3d(dst, &img_map, fox, foy, f0 + i, &full_bar[stage]);
+            if (!(p.debug & 2)) tma_load_3d(dst + kImgBytesPadded, &rx_map, x0, i0_tile, 2 * (f0 + i), &full_bar[stage]);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -219,7 +222,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
 
     for (int f = 0; f < T; ++f) {
       mbar_wait(&full_bar[stage], phase);
-      if (active) {
+      if (active && !(p.debug & 4)) {
         const float* simg = reinterpret_cast<const float*>(stages + (size_t)stage * kStageBytes);
         const float* srx = simg + kImgBytesPadded / 4;
         const int4 org = *reinterpret_cast<const int4*>(stage_hdr[stage]);       // oy + 1, ox + 1, by_lo, by_n
