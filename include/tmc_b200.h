@@ -34,6 +34,11 @@ int tmc_version(void);            /* 100 = 0.1.0 */
 const char* tmc_last_error(void); /* thread-local message of the last failing call (host pointer) */
 int tmc_sm_count(void);           /* SM count of the current device, -1 on error */
 long tmc_launch_count(void);      /* kernels launched by this library since load (bench bookkeeping) */
+/* per-kernel device timing for the roofline report: while enabled, the hot kernels' launches are bracketed by CUDA events on
+ * their stream (enable != 0 drops earlier records); the report is "kernel,launches,total_ms\n" lines (NUL-terminated,
+ * truncated to size; waits for the recorded events) and returns the bytes the full report needs */
+int tmc_kernel_timing(int enable);
+long tmc_kernel_timing_report(char* buf, long size);
 /* copy nbytes (multiple of 4) from PAGE-LOCKED host memory to device memory with a kernel reading the host mapping:
  * unlike cudaMemcpyAsync it does not queue behind a large host-to-device copy of a pipelined run */
 int tmc_upload_pinned(const void* host_pinned, void* dst, long nbytes, tmc_stream_t stream);

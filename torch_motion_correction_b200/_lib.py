@@ -29,6 +29,8 @@ _SIGNATURES = {
     "tmc_last_error": (c_char_p, []),
     "tmc_sm_count": (I, []),
     "tmc_launch_count": (L, []),
+    "tmc_kernel_timing": (I, [I]),
+    "tmc_kernel_timing_report": (L, [ctypes.c_char_p, L]),
     "tmc_upload_pinned": (I, [P, P, L, P]),
     "tmc_stack_stats_workspace_doubles": (I, []),
     "tmc_stack_stats": (I, [P, I, I, I, I, I, I, I, P, P, P]),
@@ -152,6 +154,24 @@ def call(name: str, *args):
         if status == 3:
             raise NotImplementedError(f"{name}: {msg}")
         raise RuntimeError(f"{name} failed (status {status}): {msg}")
+
+
+def kernel_timing(enable: bool) -> None:
+    """Switch the library's per-kernel CUDA-event timing on (dropping earlier records) or off (bench.py)."""
+    load().tmc_kernel_timing(1 if enable else 0)
+
+
+def kernel_timing_report() -> dict:
+    """{kernel: (launches, total device ms)} of the launches recorded since ``kernel_timing(True)``."""
+    lib = load()
+    need = lib.tmc_kernel_timing_report(None, 0)
+    buf = ctypes.create_string_buffer(int(need) + 16)
+    lib.tmc_kernel_timing_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.rsplit(",", 2)
+        out[name] = (int(n), float(ms))
+    return out
 
 
 def query(name: str, *args):

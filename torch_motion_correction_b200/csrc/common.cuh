@@ -15,6 +15,18 @@
 void tmc_set_error(const char* fmt, ...);
 // bookkeeping for bench.py: every kernel launch of this library is counted
 void tmc_count_launch();
+// optional per-kernel device timing (tmc_kernel_timing): CUDA events recorded on the launching stream right before and
+// right after a launch; no-ops unless switched on
+void tmc_timing_begin(cudaStream_t stream);
+void tmc_timing_end(const char* kernel, cudaStream_t stream);
+// launch statement bracketed by the timing events and counted
+#define TMC_TIMED(name, stream, ...) \
+  do {                               \
+    tmc_timing_begin(stream);        \
+    __VA_ARGS__;                     \
+    tmc_timing_end(name, stream);    \
+    tmc_count_launch();              \
+  } while (0)
 
 #define TMC_CHECK_ARG(cond, ...)          \
   do {                                    \

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -20,6 +21,86 @@ void tmc_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 TMC_API long tmc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 TMC_API const char* tmc_last_error(void) { return g_last_error; }
+
+// ---- per-kernel device timing (bench.py's roofline: CUDA-event duration of individual launches) ----------------------
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+namespace {
+struct TimedLaunch {
+  const char* kernel;
+  cudaEvent_t start, stop;
+};
+std::atomic<int> g_timing_on{0};
+std::mutex g_timing_mutex;
+std::vector<TimedLaunch> g_timed;
+thread_local cudaEvent_t tl_start = nullptr;
+bool capturing(cudaStream_t stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone;
+}
+}  // namespace
+
+void tmc_timing_begin(cudaStream_t stream) {
+  tl_start = nullptr;
+  if (!g_timing_on.load(std::memory_order_relaxed) || capturing(stream)) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, stream);
+  tl_start = e;
+}
+
+void tmc_timing_end(const char* kernel, cudaStream_t stream) {
+  if (tl_start == nullptr) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, stream);
+  std::lock_guard<std::mutex> lock(g_timing_mutex);
+  g_timed.push_back({kernel, tl_start, e});
+  tl_start = nullptr;
+}
+
+// enable != 0: start recording (drops earlier records); 0: stop recording (records are kept for the report)
+TMC_API int tmc_kernel_timing(int enable) {
+  std::lock_guard<std::mutex> lock(g_timing_mutex);
+  if (enable) {
+    for (auto& t : g_timed) {
+      cudaEventDestroy(t.start);
+      cudaEventDestroy(t.stop);
+    }
+    g_timed.clear();
+  }
+  g_timing_on.store(enable ? 1 : 0);
+  return TMC_OK;
+}
+
+// "kernel,launches,total_ms\n" per timed kernel into buf (NUL-terminated, truncated to size); waits for the recorded
+// events; returns the number of bytes the full report needs
+TMC_API long tmc_kernel_timing_report(char* buf, long size) {
+  std::lock_guard<std::mutex> lock(g_timing_mutex);
+  std::map<std::string, std::pair<long, double>> agg;
+  for (auto& t : g_timed) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(t.stop) == cudaSuccess && cudaEventElapsedTime(&ms, t.start, t.stop) == cudaSuccess) {
+      auto& a = agg[t.kernel];
+      a.first += 1;
+      a.second += ms;
+    }
+  }
+  std::string out;
+  char line[256];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s,%ld,%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && size > 0) {
+    const long n = (long)out.size() < size - 1 ? (long)out.size() : size - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (long)out.size() + 1;
+}
 
 TMC_API int tmc_version(void) { return 100; }  // 0.1.0
 

@@ -613,6 +613,12 @@ __global__ void fourier_shift_kernel(float2* __restrict__ spec, int T, int NY, i
 
 #define TMC_FOR_EACH_M(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
 
+// timing label of a size-templated kernel (the two sizes of the benchmark get their own rows)
+template <int MM>
+constexpr const char* sized_label(const char* l4096, const char* l1024, const char* other) {
+  return MM == 4096 ? l4096 : (MM == 1024 ? l1024 : other);
+}
+
 template <int V>
 struct IntC {
   static constexpr int value = V;
@@ -674,11 +680,11 @@ TMC_API int tmc_fft_plan_init(int n, void* plan, cudaStream_t stream) {
     return TMC_ERR_UNSUPPORTED;
   }
   float2* tw = (float2*)plan;
-  twiddle_kernel<<<tmc_div_up(m, 128), 128, 0, stream>>>(m, tw); tmc_count_launch();
+  TMC_TIMED("twiddle_kernel", stream, twiddle_kernel<<<tmc_div_up(m, 128), 128, 0, stream>>>(m, tw));
   if (m != n) {
     float2* chirp = tw + m;
     float2* bhat = chirp + n;
-    chirp_kernel<<<tmc_div_up(m, 128), 128, 0, stream>>>(n, m, chirp, bhat); tmc_count_launch();
+    TMC_TIMED("chirp_kernel", stream, chirp_kernel<<<tmc_div_up(m, 128), 128, 0, stream>>>(n, m, chirp, bhat));
     // bhat <- FFT_m(bhat) in place (one row, plain power-of-two transform)
     AxisPlan p;
     p.tw = tw;
@@ -688,7 +694,7 @@ TMC_API int tmc_fft_plan_init(int n, void* plan, cudaStream_t stream) {
     int rc = dispatch_fft(m, "fft_plan_init", [&](auto M, auto) {
       constexpr int MM = decltype(M)::value;
       if (int e = enable_smem(c2c_rows_kernel<MM, false>, fft_smem_bytes<MM>())) return e;
-      c2c_rows_kernel<MM, false><<<1, kThreads, fft_smem_bytes<MM>(), stream>>>(bhat, 1, p, bhat); tmc_count_launch();
+      TMC_TIMED("c2c_rows_kernel", stream, c2c_rows_kernel<MM, false><<<1, kThreads, fft_smem_bytes<MM>(), stream>>>(bhat, 1, p, bhat));
       return TMC_OK;
     });
     if (rc) return rc;
@@ -705,8 +711,8 @@ TMC_API int tmc_fft_c2c_rows(const void* in, int rows, int n, const void* plan, 
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
     if (int e = enable_smem(c2c_rows_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
-    c2c_rows_kernel<MM, BB><<<tmc_div_up(rows, batch_for(MM)), kThreads, fft_smem_bytes<MM>(), stream>>>(
-        (const float2*)in, rows, p, (float2*)out); tmc_count_launch();
+    TMC_TIMED("c2c_rows_kernel", stream, c2c_rows_kernel<MM, BB><<<tmc_div_up(rows, batch_for(MM)), kThreads, fft_smem_bytes<MM>(), stream>>>(
+        (const float2*)in, rows, p, (float2*)out));
     return TMC_OK;
   });
   if (rc) return rc;
@@ -748,14 +754,17 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
         dim3 grid(tmc_div_up(yhi - ylo, rows_per_cta), njobs);
         if (job_mode == 1) {
           if (int e = enable_smem(poly::rows_forward_poly<1>, poly::smem_bytes)) return e;
-          poly::rows_forward_poly<1><<<grid, poly::kThreads, poly::smem_bytes, stream>>>(image, h, w, mean_std, mask, jobs, frame_shifts, x_margin, ylo, yhi, ny,
-                                                                                     kx_count, px.tw, (float2*)tmp, rows_per_cta);
+          TMC_TIMED("rows_forward_poly<1>", stream,
+                    poly::rows_forward_poly<1><<<grid, poly::kThreads, poly::smem_bytes, stream>>>(
+                        image, h, w, mean_std, mask, jobs, frame_shifts, x_margin, ylo, yhi, ny, kx_count, px.tw, (float2*)tmp,
+                        rows_per_cta));
         } else {
           if (int e = enable_smem(poly::rows_forward_poly<2>, poly::smem_bytes)) return e;
-          poly::rows_forward_poly<2><<<grid, poly::kThreads, poly::smem_bytes, stream>>>(image, h, w, mean_std, mask, jobs, frame_shifts, x_margin, ylo, yhi, ny,
-                                                                                     kx_count, px.tw, (float2*)tmp, rows_per_cta);
+          TMC_TIMED("rows_forward_poly<2>", stream,
+                    poly::rows_forward_poly<2><<<grid, poly::kThreads, poly::smem_bytes, stream>>>(
+                        image, h, w, mean_std, mask, jobs, frame_shifts, x_margin, ylo, yhi, ny, kx_count, px.tw, (float2*)tmp,
+                        rows_per_cta));
         }
-        tmc_count_launch();
         return TMC_OK;
       }
     }
@@ -770,9 +779,11 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
 #define TMC_ROWS_FWD(MODE)                                                                                      \
   {                                                                                                             \
     if (int e = enable_smem(rows_forward_p2<MM, MODE>, smem)) return e;                                         \
+    tmc_timing_begin(stream);                                                                                   \
     rows_forward_p2<MM, MODE><<<grid, fft2::kThreads, smem, stream>>>(image, h, w, mean_std, mask, jobs, frame_shifts, \
                                                                      x_margin, ylo, yhi, ny, kx_count, px.tw,          \
                                                                      (float2*)tmp, rows_per_cta);                      \
+    tmc_timing_end(MM == 4096 ? "rows_forward_p2<4096>" : "rows_forward_p2", stream);                            \
   }
         if (job_mode == 1) TMC_ROWS_FWD(1) else if (job_mode == 2) TMC_ROWS_FWD(2) else TMC_ROWS_FWD(0)
 #undef TMC_ROWS_FWD
@@ -783,8 +794,8 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
     if (int e = enable_smem(rows_forward_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(tmc_div_up(yhi - ylo, batch_for(MM)), njobs);
     if (yhi > ylo) {
-      rows_forward_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>(
-          image, h, w, mean_std, mask, jobs, frame_shifts, x_margin, ylo, yhi, ny, kx_count, px, (float2*)tmp); tmc_count_launch();
+      TMC_TIMED("rows_forward_kernel", stream, rows_forward_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>(
+          image, h, w, mean_std, mask, jobs, frame_shifts, x_margin, ylo, yhi, ny, kx_count, px, (float2*)tmp));
     }
     return TMC_OK;
   });
@@ -796,14 +807,14 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
     if constexpr (use_fast_path<MM, BB>()) {
       if (int e = enable_smem(cols_forward_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
       dim3 grid(tmc_div_up(kx_count, fft2::Cfg<MM>::B), 2 * njobs);
-      cols_forward_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
-          (const float2*)tmp, ylo, yhi, kx_count, ky_count, ky_start, weight, py.tw, (float2*)out); tmc_count_launch();
+      TMC_TIMED(sized_label<MM>("cols_forward_p2<4096>", "cols_forward_p2<1024>", "cols_forward_p2"), stream, cols_forward_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
+          (const float2*)tmp, ylo, yhi, kx_count, ky_count, ky_start, weight, py.tw, (float2*)out));
       return TMC_OK;
     }
     if (int e = enable_smem(cols_forward_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(tmc_div_up(kx_count, batch_for(MM)), 2 * njobs);
-    cols_forward_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ylo, yhi, kx_count, ky_count,
-                                                                                 ky_start, weight, py, (float2*)out); tmc_count_launch();
+    TMC_TIMED("cols_forward_kernel", stream, cols_forward_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ylo, yhi, kx_count, ky_count,
+                                                                                 ky_start, weight, py, (float2*)out));
     return TMC_OK;
   });
   if (rc) return rc;
@@ -830,7 +841,7 @@ __global__ void integer_shifts_kernel(const float* __restrict__ field, int t, fl
 TMC_API int tmc_integer_shifts(const float* field, int t, float scale, int* shifts, int* not_integer, cudaStream_t stream) {
   TMC_CHECK_ARG(field && shifts && not_integer && t >= 1, "integer_shifts: bad arguments");
   TMC_CUDA(cudaMemsetAsync(not_integer, 0, sizeof(int), stream));
-  integer_shifts_kernel<<<tmc_div_up(t, 128), 128, 0, stream>>>(field, t, scale, shifts, not_integer); tmc_count_launch();
+  TMC_TIMED("integer_shifts_kernel", stream, integer_shifts_kernel<<<tmc_div_up(t, 128), 128, 0, stream>>>(field, t, scale, shifts, not_integer));
   TMC_CHECK_LAUNCH("tmc_integer_shifts");
   return TMC_OK;
 }
@@ -841,7 +852,7 @@ TMC_API int tmc_xc_pair_products(const void* spec, const int* ref_plane, const i
   TMC_CHECK_ARG(spec && ref_plane && cur_plane && out && nitems >= 0 && plane_elems >= 1, "xc_pair_products: bad arguments");
   if (nitems == 0) return TMC_OK;
   dim3 grid((unsigned)(tmc_div_up(plane_elems, 256) < 64 ? tmc_div_up(plane_elems, 256) : 64), nitems);
-  xc_pair_product_kernel<<<grid, 256, 0, stream>>>((const float2*)spec, ref_plane, cur_plane, plane_elems, (float2*)out); tmc_count_launch();
+  TMC_TIMED("xc_pair_product_kernel", stream, xc_pair_product_kernel<<<grid, 256, 0, stream>>>((const float2*)spec, ref_plane, cur_plane, plane_elems, (float2*)out));
   TMC_CHECK_LAUNCH("tmc_xc_pair_products");
   return TMC_OK;
 }
@@ -855,8 +866,8 @@ TMC_API int tmc_xc_leave_one_out_products(const void* spec, int t, int g, long p
   TMC_CHECK_ARG(k_begin >= 0 && k_count >= 0 && k_begin + k_count <= t, "xc_leave_one_out_products: bad frame range");
   if (k_count == 0) return TMC_OK;
   dim3 grid(tmc_div_up(plane_elems, 128), g);
-  xc_leave_one_out_kernel<<<grid, 128, 0, stream>>>((const float2*)spec, t, g, plane_elems, delta_offsets, deltas,
-                                                    k_begin, k_count, (float2*)out); tmc_count_launch();
+  TMC_TIMED("xc_leave_one_out_kernel", stream, xc_leave_one_out_kernel<<<grid, 128, 0, stream>>>((const float2*)spec, t, g, plane_elems, delta_offsets, deltas,
+                                                    k_begin, k_count, (float2*)out));
   TMC_CHECK_LAUNCH("tmc_xc_leave_one_out_products");
   return TMC_OK;
 }
@@ -887,14 +898,14 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
     if constexpr (use_fast_path<MM, BB>()) {
       if (int e = enable_smem(cols_inverse_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
       dim3 grid(tmc_div_up(kx_count, fft2::Cfg<MM>::B), nitems);
-      cols_inverse_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
-          (const float2*)prod, kx_count, ky_count, ky_start, py.tw, (float2*)tmp); tmc_count_launch();
+      TMC_TIMED(sized_label<MM>("cols_inverse_p2<4096>", "cols_inverse_p2<1024>", "cols_inverse_p2"), stream, cols_inverse_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
+          (const float2*)prod, kx_count, ky_count, ky_start, py.tw, (float2*)tmp));
       return TMC_OK;
     }
     if (int e = enable_smem(cols_inverse_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(tmc_div_up(kx_count, batch_for(MM)), nitems);
-    cols_inverse_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)prod, kx_count, ky_count, ky_start,
-                                                                                 py, (float2*)tmp); tmc_count_launch();
+    TMC_TIMED("cols_inverse_kernel", stream, cols_inverse_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)prod, kx_count, ky_count, ky_start,
+                                                                                 py, (float2*)tmp));
     return TMC_OK;
   });
   if (rc) return rc;
@@ -907,28 +918,28 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
       if (kx_count <= 128 && use_poly()) {
         if (int e = enable_smem(poly::rows_inverse_argmax_poly, poly::smem_bytes)) return e;
         dim3 grid(nparts, nitems);
-        poly::rows_inverse_argmax_poly<<<grid, poly::kThreads, poly::smem_bytes, stream>>>((const float2*)tmp, ny, kx_count, px.tw,
-                                                                                         (PeakCandidate*)partial); tmc_count_launch();
+        TMC_TIMED("rows_inverse_argmax_poly", stream, poly::rows_inverse_argmax_poly<<<grid, poly::kThreads, poly::smem_bytes, stream>>>((const float2*)tmp, ny, kx_count, px.tw,
+                                                                                         (PeakCandidate*)partial));
         return TMC_OK;
       }
     }
     if constexpr (use_fast_path<MM, BB>()) {
       if (int e = enable_smem(rows_inverse_argmax_p2<MM>, rows_inverse_smem_bytes<MM>())) return e;
       dim3 grid(nparts, nitems);
-      rows_inverse_argmax_p2<MM><<<grid, fft2::kThreads, rows_inverse_smem_bytes<MM>(), stream>>>(
-          (const float2*)tmp, ny, kx_count, px.tw, (PeakCandidate*)partial); tmc_count_launch();
+      TMC_TIMED(sized_label<MM>("rows_inverse_argmax_p2<4096>", "rows_inverse_argmax_p2<1024>", "rows_inverse_argmax_p2"), stream, rows_inverse_argmax_p2<MM><<<grid, fft2::kThreads, rows_inverse_smem_bytes<MM>(), stream>>>(
+          (const float2*)tmp, ny, kx_count, px.tw, (PeakCandidate*)partial));
       return TMC_OK;
     }
     if (int e = enable_smem(rows_inverse_argmax_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(nparts, nitems);
-    rows_inverse_argmax_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ny, kx_count, px,
-                                                                                        (PeakCandidate*)partial); tmc_count_launch();
+    TMC_TIMED("rows_inverse_argmax_kernel", stream, rows_inverse_argmax_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ny, kx_count, px,
+                                                                                        (PeakCandidate*)partial));
     return TMC_OK;
   });
   if (rc) return rc;
   TMC_CHECK_LAUNCH("tmc_xc_peaks(rows)");
-  peak_finalize_kernel<<<nitems, 128, 0, stream>>>((const float2*)tmp, (const PeakCandidate*)partial, nparts, ny, nx,
-                                                   kx_count, sub_pixel, shifts); tmc_count_launch();
+  TMC_TIMED("peak_finalize_kernel", stream, peak_finalize_kernel<<<nitems, 128, 0, stream>>>((const float2*)tmp, (const PeakCandidate*)partial, nparts, ny, nx,
+                                                   kx_count, sub_pixel, shifts));
   TMC_CHECK_LAUNCH("tmc_xc_peaks(finalize)");
   return TMC_OK;
 }
@@ -946,13 +957,13 @@ TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const 
     if constexpr (use_fast_path<MM, BB>()) {
       if (int e = enable_smem(cols_inverse_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
       dim3 grid(tmc_div_up(kx, fft2::Cfg<MM>::B), nitems);
-      cols_inverse_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>((const float2*)spec, kx, ny, 0, py.tw,
-                                                                                      (float2*)tmp); tmc_count_launch();
+      TMC_TIMED(sized_label<MM>("cols_inverse_p2<4096>", "cols_inverse_p2<1024>", "cols_inverse_p2"), stream, cols_inverse_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>((const float2*)spec, kx, ny, 0, py.tw,
+                                                                                      (float2*)tmp));
       return TMC_OK;
     }
     if (int e = enable_smem(cols_inverse_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(tmc_div_up(kx, batch_for(MM)), nitems);
-    cols_inverse_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)spec, kx, ny, 0, py, (float2*)tmp); tmc_count_launch();
+    TMC_TIMED("cols_inverse_kernel", stream, cols_inverse_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)spec, kx, ny, 0, py, (float2*)tmp));
     return TMC_OK;
   });
   if (rc) return rc;
@@ -962,14 +973,14 @@ TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const 
     if constexpr (use_fast_path<MM, BB>()) {
       if (int e = enable_smem(rows_inverse_store_p2<MM>, rows_inverse_smem_bytes<MM>())) return e;
       dim3 grid(tmc_div_up(ny, rows_per_cta_inverse<MM>()), nitems);
-      rows_inverse_store_p2<MM><<<grid, fft2::kThreads, rows_inverse_smem_bytes<MM>(), stream>>>(
-          (const float2*)tmp, ny, kx, px.tw, 1.0f / ((float)nx * (float)ny), out); tmc_count_launch();
+      TMC_TIMED(sized_label<MM>("rows_inverse_store_p2<4096>", "rows_inverse_store_p2<1024>", "rows_inverse_store_p2"), stream, rows_inverse_store_p2<MM><<<grid, fft2::kThreads, rows_inverse_smem_bytes<MM>(), stream>>>(
+          (const float2*)tmp, ny, kx, px.tw, 1.0f / ((float)nx * (float)ny), out));
       return TMC_OK;
     }
     if (int e = enable_smem(rows_inverse_store_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
     dim3 grid(tmc_div_up(ny, 2 * batch_for(MM)), nitems);
-    rows_inverse_store_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ny, kx, px,
-                                                                                       1.0f / ((float)nx * (float)ny), out); tmc_count_launch();
+    TMC_TIMED("rows_inverse_store_kernel", stream, rows_inverse_store_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ny, kx, px,
+                                                                                       1.0f / ((float)nx * (float)ny), out));
     return TMC_OK;
   });
   if (rc) return rc;
@@ -982,7 +993,7 @@ TMC_API int tmc_fourier_shift(void* spec, int t, int ny, int nx, const float* fi
   TMC_CHECK_ARG(spec && field && t >= 1 && ny >= 1 && nx >= 2, "fourier_shift: bad arguments");
   const int kx = nx / 2 + 1;
   dim3 grid(tmc_div_up(kx, 128), ny, t);
-  fourier_shift_kernel<<<grid, 128, 0, stream>>>((float2*)spec, t, ny, nx, kx, field, sign); tmc_count_launch();
+  TMC_TIMED("fourier_shift_kernel", stream, fourier_shift_kernel<<<grid, 128, 0, stream>>>((float2*)spec, t, ny, nx, kx, field, sign));
   TMC_CHECK_LAUNCH("tmc_fourier_shift");
   return TMC_OK;
 }
@@ -1016,15 +1027,15 @@ TMC_API int tmc_fourier_shift_frames(const float* image, int t, int ny, int nx, 
       constexpr size_t smem = rows_forward_smem_bytes<MM>();
       if (int e = enable_smem(rows_forward_p2<MM, 2>, smem)) return e;
       dim3 grid(tmc_div_up(ny, rows_per_cta), njobs);
-      rows_forward_p2<MM, 2><<<grid, fft2::kThreads, smem, stream>>>(image, ny, nx, mean_std, nullptr, jobs, nullptr, 0, 0, ny, ny,
-                                                                    kx, px.tw, (float2*)tmp, rows_per_cta); tmc_count_launch();
+      TMC_TIMED("rows_forward_p2", stream, rows_forward_p2<MM, 2><<<grid, fft2::kThreads, smem, stream>>>(image, ny, nx, mean_std, nullptr, jobs, nullptr, 0, 0, ny, ny,
+                                                                    kx, px.tw, (float2*)tmp, rows_per_cta));
     }
     return TMC_OK;
   });
   if (rc) return rc;
   {
     dim3 grid(tmc_div_up(ny, 128), t);
-    shift_phase_y_kernel<<<grid, 128, 0, stream>>>(field, t, ny, sign, (float2*)phase); tmc_count_launch();
+    TMC_TIMED("shift_phase_y_kernel", stream, shift_phase_y_kernel<<<grid, 128, 0, stream>>>(field, t, ny, sign, (float2*)phase));
   }
   rc = dispatch_fft(ny, "fourier_shift_frames", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
@@ -1033,16 +1044,16 @@ TMC_API int tmc_fourier_shift_frames(const float* image, int t, int ny, int nx, 
         constexpr size_t smem = (size_t)(4 * fft2::Cfg<MM>::STRIDE + 64 + fft2::Cfg<MM>::TW_HI) * sizeof(float2);
         if (int e = enable_smem(cols_shift_quad_p2<MM>, smem)) return e;
         dim3 grid(tmc_div_up(kx, 4), t);
-        cols_shift_quad_p2<MM><<<grid, 512, smem, stream>>>((float2*)tmp, kx, nx, (const float2*)phase, field, t, sign, py.tw);
-        tmc_count_launch();
+        TMC_TIMED("cols_shift_quad_p2", stream,
+                  cols_shift_quad_p2<MM><<<grid, 512, smem, stream>>>((float2*)tmp, kx, nx, (const float2*)phase, field, t, sign, py.tw));
         return TMC_OK;
       }
     }
     if constexpr (use_fast_path<MM, decltype(BLU)::value>()) {
       if (int e = enable_smem(cols_shift_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
       dim3 grid(tmc_div_up(kx, fft2::Cfg<MM>::B), t);
-      cols_shift_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>((float2*)tmp, kx, nx, (const float2*)phase,
-                                                                                    field, t, sign, py.tw); tmc_count_launch();
+      TMC_TIMED(sized_label<MM>("cols_shift_p2<4096>", "cols_shift_p2<1024>", "cols_shift_p2"), stream, cols_shift_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>((float2*)tmp, kx, nx, (const float2*)phase,
+                                                                                    field, t, sign, py.tw));
     }
     return TMC_OK;
   });
@@ -1052,8 +1063,8 @@ TMC_API int tmc_fourier_shift_frames(const float* image, int t, int ny, int nx, 
     if constexpr (use_fast_path<MM, decltype(BLU)::value>()) {
       if (int e = enable_smem(rows_inverse_store_p2<MM>, rows_inverse_smem_bytes<MM>())) return e;
       dim3 grid(tmc_div_up(ny, rows_per_cta_inverse<MM>()), t);
-      rows_inverse_store_p2<MM><<<grid, fft2::kThreads, rows_inverse_smem_bytes<MM>(), stream>>>(
-          (const float2*)tmp, ny, kx, px.tw, 1.0f / ((float)nx * (float)ny), out); tmc_count_launch();
+      TMC_TIMED(sized_label<MM>("rows_inverse_store_p2<4096>", "rows_inverse_store_p2<1024>", "rows_inverse_store_p2"), stream, rows_inverse_store_p2<MM><<<grid, fft2::kThreads, rows_inverse_smem_bytes<MM>(), stream>>>(
+          (const float2*)tmp, ny, kx, px.tw, 1.0f / ((float)nx * (float)ny), out));
     }
     return TMC_OK;
   });

@@ -107,8 +107,8 @@ TMC_API int tmc_stack_stats(const float* image, int t, int h, int w, int y0, int
   TMC_CHECK_ARG(0 <= y0 && y0 < y1 && y1 <= h && 0 <= x0 && x0 < x1 && x1 <= w, "stack_stats: empty or out-of-range box");
   const long rows = (long)t * (y1 - y0);
   int nblocks = (int)(rows < 148 * 8 ? rows : 148 * 8);
-  stats_partial_kernel<<<nblocks, kStatsThreads, 0, stream>>>(image, t, h, w, y0, y1, x0, x1, workspace); tmc_count_launch();
-  stats_final_kernel<<<1, 32, 0, stream>>>(workspace, nblocks, (double)rows * (x1 - x0), mean_std); tmc_count_launch();
+  TMC_TIMED("stats_partial_kernel", stream, stats_partial_kernel<<<nblocks, kStatsThreads, 0, stream>>>(image, t, h, w, y0, y1, x0, x1, workspace));
+  TMC_TIMED("stats_final_kernel", stream, stats_final_kernel<<<1, 32, 0, stream>>>(workspace, nblocks, (double)rows * (x1 - x0), mean_std));
   TMC_CHECK_LAUNCH("tmc_stack_stats");
   return TMC_OK;
 }
@@ -122,15 +122,15 @@ TMC_API int tmc_stack_moments(const float* image, int t, int h, int w, int y0, i
   TMC_CHECK_ARG(0 <= y0 && y0 < y1 && y1 <= h && 0 <= x0 && x0 < x1 && x1 <= w, "stack_moments: empty or out-of-range box");
   const long rows = (long)t * (y1 - y0);
   int nblocks = (int)(rows < 148 * 8 ? rows : 148 * 8);
-  stats_partial_kernel<<<nblocks, kStatsThreads, 0, stream>>>(image, t, h, w, y0, y1, x0, x1, workspace); tmc_count_launch();
-  stats_moments_kernel<<<1, 32, 0, stream>>>(workspace, nblocks, (double)rows * (x1 - x0), moments); tmc_count_launch();
+  TMC_TIMED("stats_partial_kernel", stream, stats_partial_kernel<<<nblocks, kStatsThreads, 0, stream>>>(image, t, h, w, y0, y1, x0, x1, workspace));
+  TMC_TIMED("stats_moments_kernel", stream, stats_moments_kernel<<<1, 32, 0, stream>>>(workspace, nblocks, (double)rows * (x1 - x0), moments));
   TMC_CHECK_LAUNCH("tmc_stack_moments");
   return TMC_OK;
 }
 
 TMC_API int tmc_moments_to_mean_std(const double* moments, float* mean_std, cudaStream_t stream) {
   TMC_CHECK_ARG(moments && mean_std, "moments_to_mean_std: null pointer");
-  moments_to_mean_std_kernel<<<1, 1, 0, stream>>>(moments, mean_std); tmc_count_launch();
+  TMC_TIMED("moments_to_mean_std_kernel", stream, moments_to_mean_std_kernel<<<1, 1, 0, stream>>>(moments, mean_std));
   TMC_CHECK_LAUNCH("tmc_moments_to_mean_std");
   return TMC_OK;
 }

@@ -142,8 +142,9 @@ constexpr int kRows = TMC_WARP_ROWS;         // vertically adjacent output pixel
 
 // Stage 1: interpolate every lattice row along x once per (frame, channel, lattice row, image
 // column): RX[f][ch][a][x] = sum_b wx_b(x) * L[f][ch][a][jx_b(x)].  Same x-then-y order as ATen.
-// pad == 1: every (frame, channel) plane gets lh + 3 rows, row p holding lattice row reflect(p - 1) -- the reflection
-// padding of the y taps materialised, so that the 4 taps of a pixel are always 4 consecutive rows (i0 .. i0 + 3).
+// pad == 1: every frame gets lh + 3 rows of (channel y, channel x) row pairs, row p holding lattice row reflect(p - 1) --
+// the reflection padding of the y taps materialised, so that the 4 taps of a pixel are always 4 consecutive rows
+// (i0 .. i0 + 3): layout (T, lh + 3, 2, W).
 constexpr int kRxPad = 3;
 __global__ void lattice_xinterp_kernel(const float* __restrict__ lattice, int T, int lh, int lw, int W, float* __restrict__ rx,
                                        int pad) {
@@ -153,8 +154,18 @@ __global__ void lattice_xinterp_kernel(const float* __restrict__ lattice, int T,
   const int lhp = lh + kRxPad * pad;
   const long rows = (long)T * 2 * lhp;
   for (long r = blockIdx.y; r < rows; r += gridDim.y) {
-    const long plane = r / lhp;
-    const int a = reflect_index((int)(r - plane * lhp) - pad, lh);
+    // pad == 0: rows ordered (frame, channel, lattice row); pad == 1: (frame, padded lattice row, channel)
+    long plane;
+    int a;
+    if (pad) {
+      const long fr = r / (2 * lhp);
+      const int rem = (int)(r - fr * 2 * lhp);
+      plane = fr * 2 + (rem & 1);
+      a = reflect_index((rem >> 1) - 1, lh);
+    } else {
+      plane = r / lhp;
+      a = (int)(r - plane * lhp);
+    }
     const float* p = lattice + (plane * lh + a) * lw;
     rx[r * W + x] = lx.w[0] * __ldg(p + lx.j[0]) + lx.w[1] * __ldg(p + lx.j[1]) + lx.w[2] * __ldg(p + lx.j[2]) +
                     lx.w[3] * __ldg(p + lx.j[3]);
@@ -190,16 +201,16 @@ __device__ __noinline__ float warp_pixel_generic(const float* __restrict__ image
                                                  int lh, float inv_px, float mean, float inv_std, float* __restrict__ out_stack,
                                                  int x, int y) {
   const LatticeAxis a = lattice_axis(y, H, lh);
-  const size_t rx_plane = (size_t)(lh + kRxPad) * W;  // padded rows: lattice row j lives in row j + 1
+  const size_t rx_plane = (size_t)(lh + kRxPad) * W;  // (T, lh + 3, 2, W): lattice row j lives in padded row j + 1
   float acc = 0.f;
   for (int f = 0; f < T; ++f) {
-    const float* Ry = rx + (size_t)f * 2 * rx_plane + x + W;
-    const float* Rx = Ry + rx_plane;
-    float sy = a.w[0] * __ldg(Ry + (size_t)a.j[0] * W), sx = a.w[0] * __ldg(Rx + (size_t)a.j[0] * W);
+    const float* Ry = rx + (size_t)f * 2 * rx_plane + x + 2 * W;
+    const float* Rx = Ry + W;
+    float sy = a.w[0] * __ldg(Ry + (size_t)a.j[0] * 2 * W), sx = a.w[0] * __ldg(Rx + (size_t)a.j[0] * 2 * W);
 #pragma unroll
     for (int k = 1; k < 4; ++k) {
-      sy = fmaf(a.w[k], __ldg(Ry + (size_t)a.j[k] * W), sy);
-      sx = fmaf(a.w[k], __ldg(Rx + (size_t)a.j[k] * W), sx);
+      sy = fmaf(a.w[k], __ldg(Ry + (size_t)a.j[k] * 2 * W), sy);
+      sx = fmaf(a.w[k], __ldg(Rx + (size_t)a.j[k] * 2 * W), sx);
     }
     const float cy = __fadd_rn((float)y, __fmul_rn(sy, inv_px));
     const float cx = __fadd_rn((float)x, __fmul_rn(sx, inv_px));
@@ -238,7 +249,7 @@ warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const 
   {
     const LatticeAxis a0 = lattice_axis(y_base, H, lh);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) jy[k] = (a0.j[k] + 1) * W;  // padded rows: lattice row j lives in row j + 1
+    for (int k = 0; k < 4; ++k) jy[k] = (a0.j[k] + 1) * 2 * W;  // (T, lh + 3, 2, W): lattice row j lives in padded row j + 1
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
       const LatticeAxis a = lattice_axis(min(y_base + r, y_last), H, lh);
@@ -287,7 +298,7 @@ warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const 
   const float* frame = image;
   float2 Rn[4];  // (y shift, x shift) lattice rows at this column, loaded one frame ahead
 #pragma unroll
-  for (int k = 0; k < 4; ++k) Rn[k] = f2(__ldg(rx_frame + jo[k]), __ldg(rx_frame + rx_plane + jo[k]));
+  for (int k = 0; k < 4; ++k) Rn[k] = f2(__ldg(rx_frame + jo[k]), __ldg(rx_frame + W + jo[k]));
   for (int f = 0; f < T; ++f, frame += (size_t)H * W) {
     float2 R[4];
 #pragma unroll
@@ -295,7 +306,7 @@ warp_lattice_kernel(const float* __restrict__ image, int T, int H, int W, const 
     if (f + 1 < T) {
       rx_frame += 2 * (size_t)rx_plane;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) Rn[k] = f2(__ldg(rx_frame + jo[k]), __ldg(rx_frame + rx_plane + jo[k]));
+      for (int k = 0; k < 4; ++k) Rn[k] = f2(__ldg(rx_frame + jo[k]), __ldg(rx_frame + W + jo[k]));
     }
     // stage A: sampling coordinates of the thread's pixels -> tap pointers and fractions
     float2 c[kRows], frac[kRows];
@@ -586,7 +597,7 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
   {
     long rows = (long)t * 2 * (lh + kRxPad);
     dim3 g1(tmc_div_up(w, 128), (unsigned)(rows < 4096 ? rows : 4096));
-    lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, workspace, 1); tmc_count_launch();
+    TMC_TIMED("lattice_xinterp_kernel", stream, lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, workspace, 1));
   }
   const bool s = out_stack != nullptr, a = out_sum != nullptr, n = mean_std != nullptr;
   // TMC_WARP_TMA=0 keeps everything on the global-memory kernel (A/B testing; read per call: tests toggle it)
@@ -596,8 +607,8 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
     // frame tiles staged by TMA, one persistent CTA per SM
     CUtensorMap img_map, rx_map;
     const bool ok = tma::make_map_3d(&img_map, image, (uint64_t)w, (uint64_t)h, (uint64_t)t, tma::kBoxW, tma::kBoxH, 1) &&
-                    tma::make_map_3d(&rx_map, workspace, (uint64_t)w, (uint64_t)(lh + kRxPad), (uint64_t)2 * t, tma::kTX,
-                                     tma::kRxRows, 2);
+                    tma::make_map_3d(&rx_map, workspace, (uint64_t)w, 2, (uint64_t)t * (lh + kRxPad), tma::kTX, 2,
+                                     (uint32_t)tma::staged_lattice_rows(h, lh));
     if (ok) {
       tma::Params prm;
       prm.image = image;
@@ -606,6 +617,7 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
       prm.W = w;
       prm.rx = workspace;
       prm.lh = lh;
+      prm.rx_rows = tma::staged_lattice_rows(h, lh);
       prm.pixel_spacing = pixel_spacing;
       prm.mean_std = mean_std;
       prm.out_stack = out_stack;
@@ -625,7 +637,9 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
   {                                                                                                                          \
     TMC_CUDA(cudaFuncSetAttribute(tma::warp_tma_kernel<S, A, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
                                   (int)tma::kSmemBytes));                                                                    \
+    tmc_timing_begin(stream);                                                                                                \
     tma::warp_tma_kernel<S, A, N><<<grid, tma::kThreads, tma::kSmemBytes, stream>>>(img_map, rx_map, prm);                    \
+    tmc_timing_end("warp_tma_kernel", stream);                                                                               \
   }
       if (s && a && n) LAUNCH_TMA(true, true, true)
       else if (s && a) LAUNCH_TMA(true, true, false)
@@ -642,6 +656,7 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
   {
     dim3 block(kTileX, kTileYGroups);
     dim3 grid(tmc_div_up(w, kTileX), tmc_div_up(h, kTileYGroups * kRows));
+    tmc_timing_begin(stream);
 #define LAUNCH(S, A, N)                                                                                          \
   warp_lattice_kernel<S, A, N><<<grid, block, 0, stream>>>(image, t, h, w, workspace, lh, pixel_spacing, mean_std, \
                                                            out_stack, out_sum, accumulate_sum, 0, w, 0, h)
@@ -652,6 +667,7 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
     else if (n) LAUNCH(false, true, true);
     else LAUNCH(false, true, false);
 #undef LAUNCH
+    tmc_timing_end("warp_lattice_kernel", stream);
     tmc_count_launch();
   }
   TMC_CHECK_LAUNCH("tmc_warp_lattice");
@@ -662,7 +678,7 @@ TMC_API int tmc_pixel_shifts(const float* lattice, int lh, int lw, int h, int w,
                              cudaStream_t stream) {
   TMC_CHECK_ARG(lattice && out && lh >= 1 && lw >= 1 && h >= 2 && w >= 2 && pixel_spacing > 0.f, "pixel_shifts: bad arguments");
   dim3 grid(tmc_div_up(w, 128), h);
-  pixel_shifts_kernel<<<grid, 128, 0, stream>>>(lattice, lh, lw, h, w, pixel_spacing, out); tmc_count_launch();
+  TMC_TIMED("pixel_shifts_kernel", stream, pixel_shifts_kernel<<<grid, 128, 0, stream>>>(lattice, lh, lw, h, w, pixel_spacing, out));
   TMC_CHECK_LAUNCH("tmc_pixel_shifts");
   return TMC_OK;
 }
@@ -671,7 +687,7 @@ TMC_API int tmc_warp_dense_shifts(const float* image, int t, int h, int w, const
                                   cudaStream_t stream) {
   TMC_CHECK_ARG(image && shifts && out_stack && t >= 1 && h >= 2 && w >= 2, "warp_dense_shifts: bad arguments");
   dim3 grid(tmc_div_up(w, 128), h, t);
-  warp_dense_shifts_kernel<<<grid, 128, 0, stream>>>(image, t, h, w, shifts, out_stack); tmc_count_launch();
+  TMC_TIMED("warp_dense_shifts_kernel", stream, warp_dense_shifts_kernel<<<grid, 128, 0, stream>>>(image, t, h, w, shifts, out_stack));
   TMC_CHECK_LAUNCH("tmc_warp_dense_shifts");
   return TMC_OK;
 }
@@ -679,7 +695,7 @@ TMC_API int tmc_warp_dense_shifts(const float* image, int t, int h, int w, const
 TMC_API int tmc_pixel_tyx(int h, int w, int t, int frame_offset, int total_frames, float* tyx, cudaStream_t stream) {
   TMC_CHECK_ARG(tyx && t >= 1 && h >= 2 && w >= 2 && total_frames >= t + frame_offset, "pixel_tyx: bad arguments");
   dim3 grid(tmc_div_up(w, 128), h, t);
-  pixel_tyx_kernel<<<grid, 128, 0, stream>>>(h, w, t, frame_offset, total_frames, tyx); tmc_count_launch();
+  TMC_TIMED("pixel_tyx_kernel", stream, pixel_tyx_kernel<<<grid, 128, 0, stream>>>(h, w, t, frame_offset, total_frames, tyx));
   TMC_CHECK_LAUNCH("tmc_pixel_tyx");
   return TMC_OK;
 }
@@ -695,12 +711,12 @@ TMC_API int tmc_warp_lattice_backward(const float* image, int t, int h, int w, c
   float* rx = workspace;
   float* grad_rx = workspace + rows * w;
   dim3 g1(tmc_div_up(w, 128), (unsigned)(rows < 4096 ? rows : 4096));
-  lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, rx, 0); tmc_count_launch();
+  TMC_TIMED("lattice_xinterp_kernel", stream, lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, rx, 0));
   TMC_CUDA(cudaMemsetAsync(grad_rx, 0, sizeof(float) * (size_t)rows * w, stream));
   TMC_CUDA(cudaMemsetAsync(grad_lattice, 0, sizeof(float) * (size_t)rows * lw, stream));
   dim3 g2(tmc_div_up(w, 128), h);
-  warp_lattice_backward_kernel<<<g2, 128, 0, stream>>>(image, t, h, w, rx, lh, pixel_spacing, grad_out, grad_rx); tmc_count_launch();
-  lattice_xinterp_backward_kernel<<<g1, 128, 0, stream>>>(grad_rx, rows, lw, w, grad_lattice); tmc_count_launch();
+  TMC_TIMED("warp_lattice_backward_kernel", stream, warp_lattice_backward_kernel<<<g2, 128, 0, stream>>>(image, t, h, w, rx, lh, pixel_spacing, grad_out, grad_rx));
+  TMC_TIMED("lattice_xinterp_backward_kernel", stream, lattice_xinterp_backward_kernel<<<g1, 128, 0, stream>>>(grad_rx, rows, lw, w, grad_lattice));
   TMC_CHECK_LAUNCH("tmc_warp_lattice_backward");
   return TMC_OK;
 }
@@ -710,7 +726,7 @@ TMC_API int tmc_lattice_tyx(int t, int frame_offset, int total_frames, int lh, i
   TMC_CHECK_ARG(tyx && t >= 1 && lh >= 1 && lw >= 1 && frame_offset >= 0 && frame_offset + t <= total_frames,
                 "lattice_tyx: bad arguments");
   const long n = (long)t * lh * lw;
-  lattice_tyx_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(t, frame_offset, total_frames, lh, lw, tyx); tmc_count_launch();
+  TMC_TIMED("lattice_tyx_kernel", stream, lattice_tyx_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(t, frame_offset, total_frames, lh, lw, tyx));
   TMC_CHECK_LAUNCH("tmc_lattice_tyx");
   return TMC_OK;
 }

@@ -81,10 +81,21 @@ __device__ __forceinline__ void keys_weights2(float2 t, float2 (&w)[4]) {
   w[2] = __ffma2_rn(__ffma2_rn(A2, u, mA3), __fmul2_rn(u, u), one);
 }
 
+// the same with an L2 eviction-priority hint (createpolicy)
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, "
+      "%4}], [%5], %6;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 struct Params {
   const float* image;
   int T, H, W;
-  const float* rx;  // (T, 2, lh + 3, W): x-interpolated lattice, rows padded by reflection (row p <-> lattice row p - 1)
+  const float* rx;  // (T, lh + 3, 2, W): x-interpolated lattice, rows padded by reflection (row p <-> lattice row p - 1)
+  int rx_rows;      // lattice rows staged per tile (5 .. kRxRows)
   int lh;
   float pixel_spacing;
   const float* mean_std;
@@ -124,57 +135,78 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
     // ---------------- producer warp ----------------
     const int lane = tid - kConsumers;
     uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int x0 = (tile % p.tiles_x) * kTX, y0 = (tile / p.tiles_x) * kTY;
+    uint64_t keep_policy;  // the lattice rows are re-read by every tile of the same lattice cells: keep them in L2
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
+    const uint32_t stage_tx = kImgBytes + (uint32_t)p.rx_rows * kTX * 2 * 4;
+    // work = chunks of up to 32 frames of one tile; lane l owns frame f0 + l of the chunk: where the tile lands in that
+    // frame (tile origin + the shift of the tile centre, rounded down).  The next chunk's landing points are computed
+    // (global loads in flight) while the current chunk's loads are being issued.
+    auto landing = [&](int tile, int f0, int& oy, int& ox, int& x0, int& i0_tile) {
+      x0 = (tile % p.tiles_x) * kTX;
+      const int y0 = (tile / p.tiles_x) * kTY;
       const int yc = min(y0 + kTY / 2, H - 1), xc = min(x0 + kTX / 2, W - 1);
       const LatticeAxis ac = lattice_axis(yc, H, lh);
-      const int i0_tile = lattice_axis(y0, H, lh).i0;
-      for (int f0 = 0; f0 < T; f0 += 32) {
-        // lane l: landing point of the tile in frame f0 + l (shift of the tile centre, rounded down)
-        int oy = 0, ox = 0;
-        if (f0 + lane < T) {
-          const float* Ry = p.rx + ((size_t)(f0 + lane) * 2) * lhp * W + xc;
-          const float* Rx = Ry + (size_t)lhp * W;
-          float sy = 0.f, sx = 0.f;
+      i0_tile = lattice_axis(y0, H, lh).i0;
+      oy = ox = 0;
+      if (f0 + lane < T) {
+        const float* Ry = p.rx + ((size_t)(f0 + lane) * lhp + ac.i0) * 2 * W + xc;
+        float sy = 0.f, sx = 0.f;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            sy = fmaf(ac.w[k], __ldg(Ry + (size_t)(ac.i0 + k) * W), sy);
-            sx = fmaf(ac.w[k], __ldg(Rx + (size_t)(ac.i0 + k) * W), sx);
-          }
-          // clamped: a wild (or NaN) shift must not overflow the int conversion; such tiles take the generic path
-          oy = y0 + (int)fminf(fmaxf(floorf(sy * inv_px_s), -1e6f), 1e6f) - kMargin - 1;
-          // TMA wants the innermost box coordinate on a 16-byte boundary (measured: any other x raises "illegal
-          // instruction"; tools/tma_probe.cu): rounded down to 4 pixels, the box is 3 columns wider for it
-          ox = (x0 + (int)fminf(fmaxf(floorf(sx * inv_px_s), -1e6f), 1e6f) - kMargin - 1) & ~3;
+        for (int k = 0; k < 4; ++k) {
+          sy = fmaf(ac.w[k], __ldg(Ry + (size_t)k * 2 * W), sy);
+          sx = fmaf(ac.w[k], __ldg(Ry + (size_t)(k * 2 + 1) * W), sx);
         }
-        const int nf = min(32, T - f0);
-        for (int i = 0; i < nf; ++i) {
-          const int foy = __shfl_sync(0xffffffffu, oy, i), fox = __shfl_sync(0xffffffffu, ox, i);
-          if (lane == 0) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);  // the consumers have released this slot
-            {
-              const int by_lo = max(0, -foy), by_n = min(kBoxH - 4, H - 4 - foy) - by_lo - (kRows - 1);
-              const int bx_lo = max(0, -fox), bx_n = min(kBoxW - 4, W - 4 - fox) - bx_lo;
-              int* hdr = stage_hdr[stage];
-              hdr[0] = foy + 1;
-              hdr[1] = fox + 1;
-              hdr[2] = by_n >= 0 ? by_lo : 0x40000000;  // empty range: nothing passes
-              hdr[3] = by_n >= 0 ? by_n : 0;
-              hdr[4] = bx_n >= 0 ? bx_lo : 0x40000000;
-              hdr[5] = bx_n >= 0 ? bx_n : 0;
-            }
-            unsigned char* dst = stages + (size_t)stage * kStageBytes;
-            mbar_expect_tx(&full_bar[stage], ((p.debug & 1) ? 0 : kImgBytes) + ((p.debug & 2) ? 0 : kRxBytes));
-            if (!(p.debug & 1)) tma_load_3d(dst, &img_map, fox, foy, f0 + i, &full_bar[stage]);
-            if (!(p.debug & 2)) tma_load_3d(dst + kImgBytesPadded, &rx_map, x0, i0_tile, 2 * (f0 + i), &full_bar[stage]);
-          }
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-        __syncwarp();
+        // clamped: a wild (or NaN) shift must not overflow the int conversion; such tiles take the generic path
+        oy = y0 + (int)fminf(fmaxf(floorf(sy * inv_px_s), -1e6f), 1e6f) - kMargin - 1;
+        // TMA wants the innermost box coordinate on a 16-byte boundary (measured: any other x raises "illegal
+        // instruction"; tools/tma_probe.cu): rounded down to 4 pixels, the box is 3 columns wider for it
+        ox = (x0 + (int)fminf(fmaxf(floorf(sx * inv_px_s), -1e6f), 1e6f) - kMargin - 1) & ~3;
       }
+    };
+    int tile = blockIdx.x, f0 = 0;
+    int oy, ox, x0, i0_tile;
+    if (tile < p.n_tiles) landing(tile, f0, oy, ox, x0, i0_tile);
+    while (tile < p.n_tiles) {
+      int ntile = tile, nf0 = f0 + 32;
+      if (nf0 >= T) {
+        nf0 = 0;
+        ntile += gridDim.x;
+      }
+      int noy = 0, nox = 0, nx0 = 0, ni0 = 0;
+      if (ntile < p.n_tiles) landing(ntile, nf0, noy, nox, nx0, ni0);
+      const int nf = min(32, T - f0);
+      for (int i = 0; i < nf; ++i) {
+        const int foy = __shfl_sync(0xffffffffu, oy, i), fox = __shfl_sync(0xffffffffu, ox, i);
+        if (lane == 0) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);  // the consumers have released this slot
+          {
+            const int by_lo = max(0, -foy), by_n = min(kBoxH - 4, H - 4 - foy) - by_lo - (kRows - 1);
+            const int bx_lo = max(0, -fox), bx_n = min(kBoxW - 4, W - 4 - fox) - bx_lo;
+            int* hdr = stage_hdr[stage];
+            hdr[0] = foy + 1;
+            hdr[1] = fox + 1;
+            hdr[2] = by_n >= 0 ? by_lo : 0x40000000;  // empty range: nothing passes
+            hdr[3] = by_n >= 0 ? by_n : 0;
+            hdr[4] = bx_n >= 0 ? bx_lo : 0x40000000;
+            hdr[5] = bx_n >= 0 ? bx_n : 0;
+          }
+          unsigned char* dst = stages + (size_t)stage * kStageBytes;
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          tma_load_3d(dst, &img_map, fox, foy, f0 + i, &full_bar[stage]);
+          tma_load_3d_hint(dst + kImgBytesPadded, &rx_map, x0, 0, (f0 + i) * lhp + i0_tile, &full_bar[stage], keep_policy);
+        }
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      __syncwarp();
+      tile = ntile;
+      f0 = nf0;
+      oy = noy;
+      ox = nox;
+      x0 = nx0;
+      i0_tile = ni0;
     }
     return;
   }
@@ -199,21 +231,24 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
     const int x = x0 + tx, y_base = y0 + tyg * kRows;
     const bool active = x < W && y_base < H;
     const int y_last = H - 1;
-    const int i0_tile = lattice_axis(y0, H, lh).i0;
-    // lattice taps along y of the thread's rows: staged row (i0 - i0_tile + k) of the block, duplicated weights
+    // lattice taps along y of the thread's rows: staged row (i0 - i0_tile + k) of the block.  One lattice_axis per lane
+    // (lanes 0..3: the thread's rows -- every lane of a warp has the same rows; lane 4: the tile's first row), shuffled
     float wy[kRows][4];
     int lat[kRows];
     float yf[kRows];
     bool same_cell = true;
+    {
+      const LatticeAxis mine = lattice_axis(lane < kRows ? min(y_base + lane, y_last) : y0, H, lh);
+      const int i0_tile = __shfl_sync(0xffffffffu, mine.i0, kRows);
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int y = min(y_base + r, y_last);
-      const LatticeAxis a = lattice_axis(y, H, lh);
-      yf[r] = (float)y;
-      lat[r] = min(max(a.i0 - i0_tile, 0), kRxRows - 4) * kTX + tx;
+      for (int r = 0; r < kRows; ++r) {
+        yf[r] = (float)min(y_base + r, y_last);
+        const int i0 = __shfl_sync(0xffffffffu, mine.i0, r);
+        lat[r] = min(max(i0 - i0_tile, 0), p.rx_rows - 4) * (2 * kTX) + tx;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) wy[r][k] = a.w[k];
-      same_cell = same_cell && (lat[r] == lat[0]);
+        for (int k = 0; k < 4; ++k) wy[r][k] = __shfl_sync(0xffffffffu, mine.w[k], r);
+        same_cell = same_cell && (lat[r] == lat[0]);
+      }
     }
     const float xf = (float)min(x, W - 1);
     float acc[kRows];
@@ -230,14 +265,14 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
         float2 R[4];
         if (same_cell) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) R[k] = f2(srx[lat[0] + k * kTX], srx[kRxRows * kTX + lat[0] + k * kTX]);
+          for (int k = 0; k < 4; ++k) R[k] = f2(srx[lat[0] + k * 2 * kTX], srx[lat[0] + (k * 2 + 1) * kTX]);
         }
         float2 c[kRows], fl[kRows], frac[kRows];
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
           if (!same_cell) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) R[k] = f2(srx[lat[r] + k * kTX], srx[kRxRows * kTX + lat[r] + k * kTX]);
+            for (int k = 0; k < 4; ++k) R[k] = f2(srx[lat[r] + k * 2 * kTX], srx[lat[r] + (k * 2 + 1) * kTX]);
           }
           float2 s = __fmul2_rn(dup(wy[r][0]), R[0]);
           s = __ffma2_rn(dup(wy[r][1]), R[1], s);
@@ -401,12 +436,18 @@ inline bool make_map_3d(CUtensorMap* map, const float* base, uint64_t d0, uint64
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// lattice rows a tile needs: its kTY image rows span at most floor((kTY - 1) / cell) + 2 lattice cells (+ 3 taps)
+inline int staged_lattice_rows(int h, int lh) {
+  if (lh < 2) return 5;
+  const double cell = (double)(h - 1) / (double)(lh - 1);  // image rows per lattice row
+  return (int)((kTY - 1) / cell) + 6;  // one spare row against the fp32 rounding of the lattice coordinate
+}
+
 // the kernel serves this problem: 16-byte aligned rows and lattice cells tall enough for the staged lattice block
 inline bool supported(const float* image, const float* rx, int t, int h, int w, int lh) {
   if (w % 4 != 0 || (reinterpret_cast<uintptr_t>(image) & 15) != 0 || (reinterpret_cast<uintptr_t>(rx) & 15) != 0) return false;
   if (h < kTY || w < kTX) return false;
-  // a tile's rows must not span more lattice cells than the staged block holds (16 rows = 12 cells + 4 taps)
-  if (lh >= 2 && (double)(h - 1) / (double)(lh - 1) * (kRxRows - 5) < (double)kTY) return false;
+  if (staged_lattice_rows(h, lh) > kRxRows) return false;
   if ((long)t * 2 > 0x7fffffffl) return false;
   return encode_tiled() != nullptr;
 }
