@@ -45,6 +45,19 @@ def _worker(rank, world, port, out_dir):
         assert float((field - want_field).abs().max()) <= 1e-4, float((field - want_field).abs().max())
         rel = float(torch.linalg.norm(total - want_total) / torch.linalg.norm(want_total))
         assert rel <= 1e-5, rel
+        # with the spline optimiser: Sigma and the coefficient gradient all-reduced every iteration
+        import random
+
+        kw = dict(patch_sidelength=64, frequency_range=(80, 5), n_iterations=6, deformation_field_resolution=(3, 3, 3))
+        random.seed(11)  # rank 0 draws the mini-batches and broadcasts them
+        total, field = motion_correct_frame_split(movie[f0:f1].to(dev), 1.1, f0, t, **kw)
+        random.seed(11)
+        want_total, want_field = tmc.motion_correct(movie.to(dev), 1.1, **kw)
+        assert field.shape == (2, 3, 3, 3)
+        assert float((field - want_field).abs().max()) <= 1e-4, float((field - want_field).abs().max())
+        assert float(want_field.abs().max()) > 1e-3
+        rel = float(torch.linalg.norm(total - want_total) / torch.linalg.norm(want_total))
+        assert rel <= 1e-5, rel
         with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
@@ -66,6 +79,21 @@ def test_frame_split_world1_degenerates_to_single_gpu():
     want_total, want_field = tmc.motion_correct(movie, 1.1, patch_sidelength=64, frequency_range=(80, 5))
     assert float((field - want_field).abs().max()) <= 1e-5
     assert float(torch.linalg.norm(total - want_total) / torch.linalg.norm(want_total)) <= 1e-6
+    # the split optimiser (two halves around the all-reduce) against the one-launch-per-iteration kernels
+    import random
+
+    from torch_motion_correction_b200 import _ops
+    from torch_motion_correction_b200.distributed import estimate_local_motion_frame_split
+
+    init = want_field
+    random.seed(4)
+    want = tmc.estimate_local_motion(movie, 1.1, (64, 64), (3, 3, 3), init, n_iterations=8, frequency_range=(80, 5),
+                                     grid_type="bspline")
+    random.seed(4)
+    got, losses = estimate_local_motion_frame_split(movie, 1.1, (64, 64), (3, 3, 3), init, 0, movie.shape[0], _ops.stack_stats(movie),
+                                                    n_iterations=8, frequency_range=(80, 5), grid_type="bspline", return_losses=True)
+    assert float((got - want).abs().max()) <= 1e-4, float((got - want).abs().max())
+    assert len(losses) == 8 and all(l > 0 for l in losses)
 
 
 def test_motion_correct_many_matches_single_calls():

@@ -13,7 +13,8 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_long, c_void_p
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libtmc_b200.so")
+# TMC_B200_LIB: an alternative build of the same library (A/B experiments: tools/build_variant.sh)
+LIB_PATH = os.environ.get("TMC_B200_LIB") or os.path.join(_PKG_DIR, "libtmc_b200.so")
 
 _lib = None
 
@@ -71,6 +72,8 @@ _SIGNATURES = {
     "tmc_local_spectra_norms": (I, [P, I, I, I, I, I, I, I, I, I, P, P]),
     "tmc_local_loss_workspace_bytes": (L, [I, I, I, I]),
     "tmc_local_loss_grad": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, I, P, P, P, P]),
+    "tmc_local_split_sigma": (I, [P, P, P, I, I, I, I, I, I, I, I, F, P, P, P]),
+    "tmc_local_split_grad": (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, I, F, I, P, P, P, P]),
     "tmc_advance_counter": (I, [P, P]),
     "tmc_adam_step": (I, [P, P, P, P, I, D, D, D, D, D, P, P]),
     "tmc_local_steps_supported": (I, [I, I, I, I]),

@@ -3,12 +3,12 @@
 // Replaces the per-pixel global-memory gathers of warp_lattice_kernel for images whose rows are 16-byte aligned
 // (W % 4 == 0); same arithmetic, same results (correct_motion.py:81-185).
 //
-// One persistent CTA per SM walks over 64 x 28 output tiles; for every tile it visits the T frames in order:
+// One persistent CTA per SM walks over 32 x 60 output tiles; for every tile it visits the T frames in order:
 //   * a producer warp computes, per frame, where the tile lands in the frame (tile origin + the field's shift at the tile
 //     centre) and issues two tensor-map TMA loads (cp.async.bulk.tensor) into one slot of a ring of shared-memory stages:
-//     the 80 x 39 pixel box of the frame around that landing point (hardware zero-fill outside the frame) and the
+//     the 48 x 71 pixel box of the frame around that landing point (hardware zero-fill outside the frame) and the
 //     64 x 16 x 2 block of the x-interpolated shift lattice the tile's pixels need;
-//   * 14 consumer warps (thread = one column x 4 rows of the tile) wait on the stage's "full" mbarrier, evaluate the
+//   * 15 consumer warps (thread = one column x 4 rows of the tile) wait on the stage's "full" mbarrier, evaluate the
 //     shift of their pixels from the staged lattice rows, run the reference's fp32 coordinate chain (packed fp32x2,
 //     both axes at once), read their 4 x 4 taps from the staged box at immediate offsets of one address (7 x 4 loads
 //     shared by the 4 vertically stacked pixels whenever their sampling points are stacked too) and release the stage
@@ -20,17 +20,24 @@
 
 namespace tma {
 
-constexpr int kTX = 64, kTY = 28;       // output tile: 14 consumer warps + the producer warp = 15 warps -> 128 registers
+#ifndef TMC_TMA_TX
+#define TMC_TMA_TX 32
+#define TMC_TMA_TY 60
+#endif
+// output tile: one consumer warp per 4 image rows.  32 x 60 = 15 consumer warps + the producer warp = 16 warps of 128
+// registers, 4 per scheduler (with 14 warps two schedulers would idle a quarter of the time)
+constexpr int kTX = TMC_TMA_TX, kTY = TMC_TMA_TY;
 constexpr int kMargin = 4;              // how far a pixel's shift may differ from the tile-centre shift
-constexpr int kBoxW = kTX + 2 * kMargin + 8;   // 80: + 3 tap columns + up to 3 columns of alignment slack (see below), 16-byte rows
-constexpr int kBoxH = kTY + 2 * kMargin + 3;   // 39
+constexpr int kBoxW = kTX + 2 * kMargin + 8;   // 48: + 3 tap columns + up to 3 columns of alignment slack (see below), 16-byte rows
+constexpr int kBoxH = kTY + 2 * kMargin + 3;   // 71
 constexpr int kRxRows = 16;             // lattice rows staged per tile and channel
-constexpr int kImgBytes = kBoxW * kBoxH * 4;                      // 12480
-constexpr int kImgBytesPadded = (kImgBytes + 127) / 128 * 128;    // 12544
-constexpr int kRxBytes = kTX * kRxRows * 2 * 4;                   // 8192
+constexpr int kImgBytes = kBoxW * kBoxH * 4;                      // 13632
+constexpr int kImgBytesPadded = (kImgBytes + 127) / 128 * 128;    // 13696
+constexpr int kRxBytes = kTX * kRxRows * 2 * 4;                   // 4096
 constexpr int kStageBytes = kImgBytesPadded + kRxBytes;
 constexpr int kStages = 8;
-constexpr int kConsumers = kTX * (kTY / kRows);  // 448 threads, 14 warps
+constexpr int kConsumers = kTX * (kTY / kRows);  // 480 threads, 15 warps
+static_assert(kTX % 32 == 0 && kTY % kRows == 0 && (kTX & (kTX - 1)) == 0, "tile shape");
 constexpr int kThreads = kConsumers + 32;        // + the producer warp
 constexpr int kConsumerWarps = kConsumers / 32;
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 128;  // + alignment slack
@@ -212,7 +219,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
   }
 
   // ---------------- consumer warps ----------------
-  const int tx = tid & (kTX - 1), tyg = tid >> 6;
+  const int tx = tid & (kTX - 1), tyg = tid / kTX;
   const int lane = tid & 31;
   float mean = 0.f, inv_std = 1.f;
   if (NORMALISE) {

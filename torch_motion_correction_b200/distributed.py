@@ -172,11 +172,152 @@ def estimate_patch_motion_frame_split(local_frames, pixel_spacing, frame_offset,
     return field, centers.to(dev)
 
 
+def estimate_local_motion_frame_split(local_frames, pixel_spacing, patch_shape, deformation_field_resolution,
+                                      initial_deformation_field, frame_offset, total_frames, mean_std, n_iterations=100,
+                                      b_factor=500, frequency_range=(300, 10), grid_type="catmull_rom", loss_type="mse",
+                                      optimizer_kwargs=None, group=None, return_losses=False):
+    """``estimate_local_motion`` (Adam; "mse" / "cc" losses) for a frame-split movie.
+
+    Every rank transforms the patches of its own frames once.  Per iteration the frames are coupled only through
+    ``Sigma = sum_t S_t`` (estimate_motion_optimizer.py:391-399): each rank sums its frames
+    (``tmc_local_split_sigma``), the (patches x pass-band box) complex partial sums are all-reduced, the gradient of the
+    local frames' shifts follows from the reduced sums (``tmc_local_split_grad``), is scattered onto the spline
+    coefficients and all-reduced again (2 nt nh nw floats); the Adam update is replicated on every rank.  The shuffled
+    mini-batch weighting (quirks Q10 / Q11) is drawn on rank 0 and broadcast, so the result equals the single-GPU run with
+    the same ``random`` state.  Returns the (2, nt, nh, nw) field (identical on all ranks)."""
+    from .estimate_motion_optimizer import LOSS_TYPES, _shuffled_batches
+    from ._lib import query
+
+    rank, world = _world(group)
+    dev = local_frames.device
+    frames = as_f32(local_frames, dev)
+    t_local, h, w = frames.shape
+    t = int(total_frames)
+    ph, pw = patch_shape
+    if loss_type not in ("mse", "cc"):
+        raise NotImplementedError("the frame-split optimiser covers the 'mse' and 'cc' losses")
+    lt = LOSS_TYPES[loss_type]
+    kind = grid_kind(grid_type)
+    resolution = tuple(int(r) for r in deformation_field_resolution)
+    px = float(pixel_spacing)
+    kw = dict(optimizer_kwargs) if optimizer_kwargs is not None else {}
+
+    centers = patch_grid_centers((t, h, w), (1, ph, pw), (1, ph // 2, pw // 2), distribute_patches=True)
+    gh, gw = centers.shape[1:3]
+    g = gh * gw
+    flat = centers[0].reshape(-1, 3)
+    y0 = (flat[:, 1] - ph // 2).tolist()
+    x0 = (flat[:, 2] - pw // 2).tolist()
+    if min(y0) < 0 or min(x0) < 0 or max(y0) + ph > h or max(x0) + pw > w:
+        raise AssertionError(f"Patch size {tuple(patch_shape)} too large for control points in image of shape {(t, h, w)}")
+
+    if initial_deformation_field is None:
+        base = torch.zeros((2, *resolution), dtype=torch.float32, device=dev)
+    else:
+        base = resample_deformation_field(as_f32(initial_deformation_field, dev), resolution)
+        with torch.cuda.device(dev):
+            call("tmc_subtract_mean", ptr(base), base.numel(), stream_ptr(dev))
+
+    # spectra of the local frames, patch-major (G, tp, KY, KX)
+    plan = _fourier.BandPlan(ph, pw, dev, px, b_factor, frequency_range)
+    mask, ylo, yhi = _fourier.soft_disc_mask((ph, pw), pw / 4, pw / 4, dev)  # quirk Q18
+    tp = 2 * ((t_local + 1) // 2)
+    bins = plan.plane_elems
+    if t_local > 0:
+        jobs = torch.tensor([[i, 1, i + 1 if i + 1 < t_local else -1, 1, y0[gi], x0[gi]] for gi in range(g)
+                             for i in range(0, t_local, 2)], dtype=torch.int32).to(dev)
+        spec = plan.forward(frames, mean_std, mask, ylo, yhi, jobs, job_mode=2)
+        norms = torch.empty((g, t_local, 2), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            call("tmc_local_spectra_norms", ptr(spec), g, t_local, tp, ph, pw, plan.ky, plan.kx, plan.ky_start, 0, ptr(norms),
+                 stream_ptr(dev))
+        sum_norms = norms[:, :, 0 if lt == 0 else 1].sum(dim=1).contiguous()
+    else:
+        spec = torch.zeros((1,), dtype=torch.float32, device=dev)
+        sum_norms = torch.zeros((g,), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sum_norms, op=dist.ReduceOp.SUM, group=group)
+
+    # normalised (t, y, x) centres of the local frames, time-major (t_local, G, 3)
+    norm = centers[frame_offset : frame_offset + t_local].clone().float()
+    norm[..., 0] /= float(t - 1) if t > 1 else float("nan")
+    norm[..., 1] /= float(h - 1)
+    norm[..., 2] /= float(w - 1)
+    centres_norm = norm.reshape(t_local, g, 3).contiguous().to(dev)
+    eval_base = _ops.spline_eval(base, kind, centres_norm) if t_local > 0 else torch.zeros((0, g, 2), device=dev)
+
+    # the mini-batch weighting of every iteration: drawn once (rank 0) and broadcast
+    def patch_scales(batches):
+        scale = [0.0] * g
+        for batch in batches:
+            b = len(batch)
+            sc = 1.0 / (b * t * ph * (pw // 2 + 1)) / (ph * pw) if lt == 0 else 1.0 / (b * t)
+            for gi in batch:
+                scale[gi] = sc
+        return scale
+
+    n_iterations = int(n_iterations)
+    scales = torch.zeros((max(n_iterations, 1), g), dtype=torch.float32)
+    if rank == 0:
+        for i in range(n_iterations):
+            scales[i] = torch.tensor(patch_scales(_shuffled_batches(g, 8)), dtype=torch.float32)
+    scales = scales.to(dev)
+    if world > 1:
+        dist.broadcast(scales, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+
+    new = torch.zeros((2, *resolution), dtype=torch.float32, device=dev)
+    exp_avg, exp_avg_sq = torch.zeros_like(new), torch.zeros_like(new)
+    lr, (b1, b2) = float(kw.get("lr", 0.01)), kw.get("betas", (0.9, 0.999))
+    eps, wd = float(kw.get("eps", 1e-08)), float(kw.get("weight_decay", 0))
+    counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+    sigma = torch.empty((g, bins, 2), dtype=torch.float32, device=dev)
+    ws = torch.empty(((query("tmc_local_loss_workspace_bytes", g, max(t_local, 1), plan.ky, plan.kx) + 7) // 8,),
+                     dtype=torch.float64, device=dev)
+    grad = torch.zeros_like(new)  # partial gradient of the local frames, all-reduced (the loss is already global)
+    loss = torch.zeros((1,), dtype=torch.float64, device=dev)
+    grad_eval = torch.empty((max(t_local, 1), g, 2), dtype=torch.float32, device=dev)
+    losses = []
+    n_ws = query("tmc_spline_workspace_floats", 2, *resolution)
+    ws_eval = torch.empty((n_ws,), dtype=torch.float32, device=dev)
+    ws_back = torch.empty((n_ws,), dtype=torch.float32, device=dev)
+    eval_new = torch.empty((max(t_local, 1), g, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        stream = stream_ptr(dev)
+        for _ in range(n_iterations):
+            if t_local > 0:
+                _ops.spline_eval(new, kind, centres_norm, out=eval_new.view(-1, 2), ws=ws_eval)
+            call("tmc_local_split_sigma", ptr(spec), ptr(eval_new), ptr(eval_base), g, t_local, tp, ph, pw, plan.ky, plan.kx,
+                 plan.ky_start, px, ptr(sigma), ptr(ws), stream)
+            if world > 1:
+                dist.all_reduce(sigma, op=dist.ReduceOp.SUM, group=group)
+            call("tmc_local_split_grad", ptr(spec), ptr(sigma), ptr(sum_norms), ptr(scales), ptr(counter), g, t_local, tp, t, ph, pw,
+                 plan.ky, plan.kx, plan.ky_start, px, lt, ptr(loss), ptr(grad_eval), ptr(ws), stream)
+            if t_local > 0:
+                _ops.spline_eval_backward((2, *resolution), kind, centres_norm, grad_eval, out=grad, ws=ws_back)
+            else:
+                grad.zero_()
+            if world > 1:
+                dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+            if return_losses:
+                losses.append(loss.clone())
+            call("tmc_adam_step", ptr(new), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), new.numel(), lr, float(b1), float(b2), eps, wd,
+                 ptr(counter), stream)
+            call("tmc_advance_counter", ptr(counter), stream)
+    final = (new + base).contiguous()
+    with torch.cuda.device(dev):
+        call("tmc_subtract_mean", ptr(final), final.numel(), stream_ptr(dev))
+    if return_losses:
+        return final, [float(l) for l in losses]
+    return final
+
+
 def motion_correct_frame_split(local_frames: torch.Tensor, pixel_spacing: float, frame_offset: int, total_frames: int,
                                patch_sidelength: int = 1024, b_factor: float = 500, frequency_range=(300, 10),
-                               grid_type: str = "bspline", group=None, device=None):
-    """Estimate (global + patch XC) and correct ONE movie whose frames are split across the ranks
-    of ``group``.  Returns ``(frame sum (h, w) on every rank, field (2, t, gh, gw))``."""
+                               grid_type: str = "bspline", group=None, device=None, n_iterations: int = 0,
+                               deformation_field_resolution=None, optimizer_kwargs=None):
+    """Estimate (global + patch XC [+ ``n_iterations`` of the spline optimiser]) and correct ONE movie whose frames are
+    split across the ranks of ``group``.  Returns ``(frame sum (h, w) on every rank, field)``; the field is
+    (2, t, gh, gw) without the optimiser and (2, nt, nh, nw) with it."""
     dev = resolve_device(local_frames, device)
     frames = as_f32(local_frames, dev)
     grid_kind(grid_type)
@@ -194,5 +335,11 @@ def motion_correct_frame_split(local_frames: torch.Tensor, pixel_spacing: float,
             whole_pixel_field=True,
         ),
     )
+    if n_iterations > 0:
+        field = estimate_local_motion_frame_split(
+            frames, pixel_spacing, (patch_sidelength, patch_sidelength), deformation_field_resolution or (3, 5, 5), field,
+            frame_offset, total_frames, stats, n_iterations=n_iterations, b_factor=b_factor, frequency_range=frequency_range,
+            grid_type=grid_type, optimizer_kwargs=optimizer_kwargs, group=group,
+        )
     total = correct_motion_sum_frame_split(frames, field, pixel_spacing, frame_offset, total_frames, grid_type, group)
     return total, field
