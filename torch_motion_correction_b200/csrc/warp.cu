@@ -595,8 +595,12 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
   TMC_CHECK_ARG(pixel_spacing > 0.f, "warp_lattice: pixel_spacing must be > 0");
   TMC_CHECK_ARG((long)(lh + kRxPad) * w < (1l << 31), "warp_lattice: lattice rows x width overflows int");
   {
+    // every thread sets up its column's taps once (two divisions) and then walks over rows: few, long-lived CTAs
     long rows = (long)t * 2 * (lh + kRxPad);
-    dim3 g1(tmc_div_up(w, 128), (unsigned)(rows < 4096 ? rows : 4096));
+    const int col_blocks = tmc_div_up(w, 128);
+    long row_blocks = (148l * 8 + col_blocks - 1) / col_blocks;
+    if (row_blocks > rows) row_blocks = rows;
+    dim3 g1(col_blocks, (unsigned)row_blocks);
     TMC_TIMED("lattice_xinterp_kernel", stream, lattice_xinterp_kernel<<<g1, 128, 0, stream>>>(lattice, t, lh, lw, w, workspace, 1));
   }
   const bool s = out_stack != nullptr, a = out_sum != nullptr, n = mean_std != nullptr;

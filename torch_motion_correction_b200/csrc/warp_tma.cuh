@@ -74,18 +74,29 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
+// packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2) or, with -DTMC_TMA_SCALAR, the same as pairs of scalar instructions
+#ifdef TMC_TMA_SCALAR
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) { return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+#else
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+#endif
+
 // Keys cubic-convolution weights (A = -0.75, ATen's bicubic) of two fractions at once (.x = y axis, .y = x axis) in
 // factored form: w0 = A t (1 - t)^2, w3 = A t^2 (1 - t), w1 = ((A + 2) t - (A + 3)) t^2 + 1, w2 = w1(1 - t).  Same
 // polynomials as get_cubic_upsample_coefficients (cubic_weights2), 11 instead of 15 packed instructions; the results
 // differ from ATen's evaluation order by rounding only (<= 2e-7 absolute, against a 1e-4 tolerance on the frame sum).
 __device__ __forceinline__ void keys_weights2(float2 t, float2 (&w)[4]) {
   const float2 A = dup(kA), A2 = dup(kA + 2.0f), mA3 = dup(-(kA + 3.0f)), one = dup(1.0f);
-  const float2 u = __ffma2_rn(t, dup(-1.0f), one);
-  const float2 a = __fmul2_rn(A, __fmul2_rn(t, u));
-  w[0] = __fmul2_rn(a, u);
-  w[3] = __fmul2_rn(a, t);
-  w[1] = __ffma2_rn(__ffma2_rn(A2, t, mA3), __fmul2_rn(t, t), one);
-  w[2] = __ffma2_rn(__ffma2_rn(A2, u, mA3), __fmul2_rn(u, u), one);
+  const float2 u = pk_fma(t, dup(-1.0f), one);
+  const float2 a = pk_mul(A, pk_mul(t, u));
+  w[0] = pk_mul(a, u);
+  w[3] = pk_mul(a, t);
+  w[1] = pk_fma(pk_fma(A2, t, mA3), pk_mul(t, t), one);
+  w[2] = pk_fma(pk_fma(A2, u, mA3), pk_mul(u, u), one);
 }
 
 // the same with an L2 eviction-priority hint (createpolicy)
@@ -281,20 +292,20 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
 #pragma unroll
             for (int k = 0; k < 4; ++k) R[k] = f2(srx[lat[r] + k * 2 * kTX], srx[lat[r] + (k * 2 + 1) * kTX]);
           }
-          float2 s = __fmul2_rn(dup(wy[r][0]), R[0]);
-          s = __ffma2_rn(dup(wy[r][1]), R[1], s);
-          s = __ffma2_rn(dup(wy[r][2]), R[2], s);
-          s = __ffma2_rn(dup(wy[r][3]), R[3], s);
+          float2 s = pk_mul(dup(wy[r][0]), R[0]);
+          s = pk_fma(dup(wy[r][1]), R[1], s);
+          s = pk_fma(dup(wy[r][2]), R[2], s);
+          s = pk_fma(dup(wy[r][3]), R[3], s);
           // Angstrom -> px, then pixel_grid + pixel_shifts (two roundings, like the reference)
-          c[r] = __fadd2_rn(f2(yf[r], xf), __fmul2_rn(s, inv_px));
+          c[r] = pk_add(f2(yf[r], xf), pk_mul(s, inv_px));
           // grid_sample round trip: g = c / (0.5 n - 0.5) - 1 ; u = ((g + 1) / 2) (n - 1); the division as
           // q0 = c * rcp and one Newton step on the residual (correctly rounded, see Divisor)
-          const float2 q0 = __fmul2_rn(c[r], rcp);
-          const float2 q = __ffma2_rn(__ffma2_rn(q0, nden, c[r]), rcp, q0);
-          const float2 g = __fadd2_rn(q, dup(-1.0f));
-          const float2 u = __fmul2_rn(__fadd2_rn(g, dup(1.0f)), half_scale);
+          const float2 q0 = pk_mul(c[r], rcp);
+          const float2 q = pk_fma(pk_fma(q0, nden, c[r]), rcp, q0);
+          const float2 g = pk_add(q, dup(-1.0f));
+          const float2 u = pk_mul(pk_add(g, dup(1.0f)), half_scale);
           fl[r] = f2(floorf(u.x), floorf(u.y));
-          frac[r] = __ffma2_rn(fl[r], dup(-1.0f), u);
+          frac[r] = pk_fma(fl[r], dup(-1.0f), u);
         }
         // the 4 sampling points are vertically adjacent (same tap columns, consecutive tap rows: the shifts differ by
         // ~1e-3 px per row, so almost always) and their 7 x 4 taps lie inside the box and inside the image
@@ -320,11 +331,11 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
           // pixel 0: tap rows 0..3
           keys_weights2(frac[0], w);
           {
-            float2 h01 = __fmul2_rn(dup(w[0].y), p01[0]), h23 = __fmul2_rn(dup(w[0].y), p23[0]);
+            float2 h01 = pk_mul(dup(w[0].y), p01[0]), h23 = pk_mul(dup(w[0].y), p23[0]);
 #pragma unroll
             for (int b = 1; b < 4; ++b) {
-              h01 = __ffma2_rn(dup(w[b].y), p01[b], h01);
-              h23 = __ffma2_rn(dup(w[b].y), p23[b], h23);
+              h01 = pk_fma(dup(w[b].y), p01[b], h01);
+              h23 = pk_fma(dup(w[b].y), p23[b], h23);
             }
             v[0] = fmaf(w[3].x, h23.y, fmaf(w[2].x, h23.x, fmaf(w[1].x, h01.y, w[0].x * h01.x)));
           }
@@ -332,23 +343,23 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
           keys_weights2(frac[1], w);
           {
             float h1 = w[0].y * p01[0].y, h4 = w[0].y * p45[0].x;
-            float2 h23 = __fmul2_rn(dup(w[0].y), p23[0]);
+            float2 h23 = pk_mul(dup(w[0].y), p23[0]);
 #pragma unroll
             for (int b = 1; b < 4; ++b) {
               h1 = fmaf(w[b].y, p01[b].y, h1);
               h4 = fmaf(w[b].y, p45[b].x, h4);
-              h23 = __ffma2_rn(dup(w[b].y), p23[b], h23);
+              h23 = pk_fma(dup(w[b].y), p23[b], h23);
             }
             v[1] = fmaf(w[3].x, h4, fmaf(w[2].x, h23.y, fmaf(w[1].x, h23.x, w[0].x * h1)));
           }
           // pixel 2: tap rows 2..5
           keys_weights2(frac[2], w);
           {
-            float2 h23 = __fmul2_rn(dup(w[0].y), p23[0]), h45 = __fmul2_rn(dup(w[0].y), p45[0]);
+            float2 h23 = pk_mul(dup(w[0].y), p23[0]), h45 = pk_mul(dup(w[0].y), p45[0]);
 #pragma unroll
             for (int b = 1; b < 4; ++b) {
-              h23 = __ffma2_rn(dup(w[b].y), p23[b], h23);
-              h45 = __ffma2_rn(dup(w[b].y), p45[b], h45);
+              h23 = pk_fma(dup(w[b].y), p23[b], h23);
+              h45 = pk_fma(dup(w[b].y), p45[b], h45);
             }
             v[2] = fmaf(w[3].x, h45.y, fmaf(w[2].x, h45.x, fmaf(w[1].x, h23.y, w[0].x * h23.x)));
           }
@@ -356,12 +367,12 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
           keys_weights2(frac[3], w);
           {
             float h3 = w[0].y * p23[0].y, h6 = w[0].y * r6[0];
-            float2 h45 = __fmul2_rn(dup(w[0].y), p45[0]);
+            float2 h45 = pk_mul(dup(w[0].y), p45[0]);
 #pragma unroll
             for (int b = 1; b < 4; ++b) {
               h3 = fmaf(w[b].y, p23[b].y, h3);
               h6 = fmaf(w[b].y, r6[b], h6);
-              h45 = __ffma2_rn(dup(w[b].y), p45[b], h45);
+              h45 = pk_fma(dup(w[b].y), p45[b], h45);
             }
             v[3] = fmaf(w[3].x, h6, fmaf(w[2].x, h45.y, fmaf(w[1].x, h45.x, w[0].x * h3)));
           }
