@@ -34,6 +34,8 @@ WORKLOADS = {
     # reduced shapes for quick functional runs (NOT the headline; selected only with --workload)
     "c1": dict(t=10, h=512, w=512, pixel_spacing=1.0, patch=128, resolution=(3, 5, 5)),
     "mid": dict(t=16, h=2048, w=2048, pixel_spacing=0.83, patch=512, resolution=(3, 5, 5)),
+    # BASELINE.json configs[3]: super-resolution 40 x 8192^2 movie, ONE movie split by frames over the ranks (--gpus N > 1)
+    "c4": dict(t=40, h=8192, w=8192, pixel_spacing=0.415, patch=1024, resolution=(3, 5, 5)),
 }
 
 
@@ -48,6 +50,7 @@ def parse_args():
                     help="spline-optimiser iterations per movie (-1: default of the build)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aten-baseline", action="store_true")
+    ap.add_argument("--no-frame-split", action="store_true", help="skip the frame-split (one movie over N GPUs) sub-record at N > 1")
     return ap.parse_args()
 
 
@@ -78,6 +81,123 @@ def synthetic_movie_gpu(t, h, w, seed, device):
         movie[k] = specimen[pad - sy : pad - sy + h, pad - sx : pad - sx + w]
         movie[k] += torch.randn((h, w), generator=g, device=device)
     return movie, walk
+
+
+def synthetic_frames_gpu(t, h, w, seed, device, f0=0, f1=None):
+    """Frames [f0, f1) of a movie like synthetic_movie_gpu's whose frames can be generated independently (one noise seed
+    per frame): every rank of a frame-split run makes its own block of the SAME movie."""
+    f1 = t if f1 is None else f1
+    g = torch.Generator(device=device).manual_seed(seed)
+    pad = 16
+    H, W = h + 2 * pad, w + 2 * pad
+    white = torch.randn((H, W), generator=g, device=device)
+    fy = torch.fft.fftfreq(H, device=device)[:, None]
+    fx = torch.fft.rfftfreq(W, device=device)[None, :]
+    spec = torch.fft.rfftn(white) * torch.exp(-(fy**2 + fx**2) / (2 * 0.08**2))
+    del white
+    specimen = torch.fft.irfftn(spec, s=(H, W))
+    del spec
+    specimen = specimen / specimen.std()
+    cpu_g = torch.Generator().manual_seed(seed)
+    walk = torch.cumsum(torch.randn((t, 2), generator=cpu_g), dim=0)
+    walk = walk - walk[t // 2]
+    walk = torch.round(walk / max(float(walk.abs().max()), 1e-6) * 6.0).long()
+    frames = torch.empty((f1 - f0, h, w), dtype=torch.float32, device=device)
+    for k in range(f0, f1):
+        sy, sx = int(walk[k, 0]), int(walk[k, 1])
+        gk = torch.Generator(device=device).manual_seed(seed * 1000 + k)
+        frames[k - f0] = specimen[pad - sy : pad - sy + h, pad - sx : pad - sx + w]
+        frames[k - f0] += torch.randn((h, w), generator=gk, device=device)
+    return frames, walk
+
+
+def frame_split_record(dev, rank, world, steps, iterations, dist):
+    """BASELINE config 4 through distributed.motion_correct_frame_split: ONE 40 x 8192^2 movie split by frames over the
+    ranks, spline optimiser included (Sigma + coefficient-gradient all-reduce per iteration, frame-sum all-reduce at the
+    end, NCCL).  Returns the sub-record of the benchmark line (rank 0) or None."""
+    import random
+
+    import torch_motion_correction_b200 as tmc
+    from torch_motion_correction_b200 import _fourier
+    from torch_motion_correction_b200.distributed import frame_range, motion_correct_frame_split
+
+    cfg = WORKLOADS["c4"]
+    t, h, w, px, p = cfg["t"], cfg["h"], cfg["w"], cfg["pixel_spacing"], cfg["patch"]
+    f0, f1 = frame_range(t, rank, world)
+    local, _ = synthetic_frames_gpu(t, h, w, 4040, dev, f0, f1)
+    kw = dict(patch_sidelength=p, n_iterations=iterations, deformation_field_resolution=cfg["resolution"])
+
+    def step():
+        random.seed(99)  # rank 0 draws the optimiser's mini-batches and broadcasts them
+        return motion_correct_frame_split(local, px, f0, t, **kw)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    total, field = step()
+    step()
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        total, field = step()
+    e.record()
+    barrier()
+    ms = torch.tensor([s.elapsed_time(e) / steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # the one bandwidth-relevant collective alone: all-reduce of the (h, w) fp32 partial frame sums
+    buf = torch.zeros((h, w), dtype=torch.float32, device=dev)
+    for _ in range(2):
+        dist.all_reduce(buf)
+    barrier()
+    s.record()
+    for _ in range(5):
+        dist.all_reduce(buf)
+    e.record()
+    barrier()
+    ar_ms = torch.tensor([s.elapsed_time(e) / 5], device=dev)
+    dist.all_reduce(ar_ms, op=dist.ReduceOp.MAX)
+    del buf
+    # single-GPU run of the same movie on rank 0 (speed-up and agreement)
+    record = None
+    if rank == 0:
+        del local
+        torch.cuda.empty_cache()
+        movie, _ = synthetic_frames_gpu(t, h, w, 4040, dev)
+
+        def single():
+            random.seed(99)
+            return tmc.motion_correct(movie, px, **kw)
+
+        want_total, want_field = single()
+        single()
+        torch.cuda.synchronize(dev)
+        s.record()
+        for _ in range(steps):
+            single()
+        e.record()
+        torch.cuda.synchronize(dev)
+        single_ms = s.elapsed_time(e) / steps
+        band = _fourier.BandPlan(p, p, dev, px, 500, (300, 10))
+        from torch_motion_correction_b200.patch_grid import patch_grid_centers
+
+        centres = patch_grid_centers((t, h, w), (1, p, p), (1, p // 2, p // 2))
+        g = centres.shape[1] * centres.shape[2]
+        record = {
+            "workload": f"c4: ONE {t}x{h}x{w} fp32 movie split by frames over {world} GPUs: whole-frame XC + patch XC ({p} px, {g} "
+                        f"patches) + {iterations}-iteration {cfg['resolution']} spline optimiser + warp-and-sum + NCCL frame-sum all-reduce",
+            "ms_per_movie": float(ms), "single_gpu_ms_per_movie": single_ms, "speedup_vs_1_gpu": single_ms / float(ms),
+            "frame_sum_allreduce_ms": float(ar_ms), "frame_sum_allreduce_bytes": h * w * 4,
+            "frame_sum_allreduce_busbw_gbs": h * w * 4 * 2 * (world - 1) / world / (float(ar_ms) * 1e-3) / 1e9,
+            "optimiser_allreduce_bytes_per_iteration": g * band.plane_elems * 8 + 2 * 3 * 5 * 5 * 4,
+            "max_abs_field_diff_angstrom": float((field - want_field).abs().max()),
+            "rel_l2_sum_diff": float(torch.linalg.norm(total - want_total) / torch.linalg.norm(want_total)),
+        }
+        del movie
+    barrier()
+    torch.cuda.empty_cache()
+    return record
 
 
 # --------------------------------------------------------------------------------------------
@@ -407,6 +527,11 @@ def main():
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e_ms)
 
+    torch.cuda.empty_cache()
+    split = None
+    if world > 1 and not args.no_frame_split:
+        split = frame_split_record(dev, rank, world, max(2, min(args.steps, 3)), iterations, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -536,6 +661,7 @@ def main():
         "entry_point_ms_per_movie": breakdown,
         "cpu_baseline": cpu_base,
         "aten_cuda_baseline": aten_base,
+        "frame_split": split,
         "clocks": clocks,
     }
     print(json.dumps(line))
