@@ -15,6 +15,8 @@ single-GPU path (world size 1), which is how the ``-m gpu`` tests exercise the b
 
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -281,9 +283,11 @@ def estimate_local_motion_frame_split(local_frames, pixel_spacing, patch_shape, 
     ws_eval = torch.empty((n_ws,), dtype=torch.float32, device=dev)
     ws_back = torch.empty((n_ws,), dtype=torch.float32, device=dev)
     eval_new = torch.empty((max(t_local, 1), g, 2), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        stream = stream_ptr(dev)
-        for _ in range(n_iterations):
+    def one_iteration():
+        """Everything of one optimiser iteration is device-side (the mini-batch row and the Adam step number come from the
+        device counter), so it can be captured once -- the two all-reduces included -- and replayed."""
+        with torch.cuda.device(dev):
+            stream = stream_ptr(dev)
             if t_local > 0:
                 _ops.spline_eval(new, kind, centres_norm, out=eval_new.view(-1, 2), ws=ws_eval)
             call("tmc_local_split_sigma", ptr(spec), ptr(eval_new), ptr(eval_base), g, t_local, tp, ph, pw, plan.ky, plan.kx,
@@ -298,11 +302,49 @@ def estimate_local_motion_frame_split(local_frames, pixel_spacing, patch_shape, 
                 grad.zero_()
             if world > 1:
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
-            if return_losses:
-                losses.append(loss.clone())
             call("tmc_adam_step", ptr(new), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), new.numel(), lr, float(b1), float(b2), eps, wd,
                  ptr(counter), stream)
             call("tmc_advance_counter", ptr(counter), stream)
+
+    done = 0
+    capturable = world == 1 or dist.get_backend(group) == "nccl"  # gloo stages through the host: cannot be captured
+    use_graph = (os.environ.get("TMC_SPLIT_GRAPH", "1") != "0" and n_iterations >= 4 and not return_losses and capturable
+                 and not torch.cuda.is_current_stream_capturing())
+    if use_graph:
+        # launch-bound loop (~10 small kernels + 2 collectives per iteration): one eager iteration, one captured, the rest
+        # replayed.  Whether to capture is decided identically on every rank (a rank replaying while another runs eagerly
+        # would still issue the same collectives in the same order, but keep it simple).
+        main = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(main)
+        graph = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.stream(side):
+                one_iteration()
+                done = 1
+                graph.capture_begin()
+                try:
+                    one_iteration()
+                finally:
+                    graph.capture_end()
+                done = 2
+                for _ in range(n_iterations - 2):
+                    graph.replay()
+                done = n_iterations
+            main.wait_stream(side)
+        except Exception as exc:  # capture refused (e.g. a process-group backend that cannot be captured): finish eagerly
+            import warnings
+
+            if os.environ.get("TMC_DEBUG"):
+                raise
+            warnings.warn(f"CUDA-graph capture of the frame-split optimiser iteration failed ({exc}); running eagerly", stacklevel=2)
+            main.wait_stream(side)
+            if done == 1:
+                pass  # the eager iteration has run; the failed capture executed nothing
+    for _ in range(done, n_iterations):
+        one_iteration()
+        if return_losses:
+            losses.append(loss.clone())
     final = (new + base).contiguous()
     with torch.cuda.device(dev):
         call("tmc_subtract_mean", ptr(final), final.numel(), stream_ptr(dev))
