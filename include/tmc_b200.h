@@ -56,6 +56,22 @@ int tmc_stack_moments(const float* image, int t, int h, int w, int y0, int y1, i
                       double* workspace, tmc_stream_t stream);
 int tmc_moments_to_mean_std(const double* moments, float* mean_std, tmc_stream_t stream);
 
+/* ---- movie preparation: examples/ttMotion.py:90-202,357 (gain_correct, remove_hot_pixels, set_frames_mean_zero, the
+ *      cast to float32) for movies that arrive in their detector-native type ------------------------------------------- */
+/* src (t, n) of dtype 0 uint8 / 1 uint16 / 2 int16 / 3 float16 / 4 float32 -> dst (t, n) fp32, times gain (n, nullable);
+ * moments (t, 2) double (nullable) = per-frame {sum, sum of squares} of the result */
+int tmc_convert_stack(const void* src, int dtype, int t, long n, const float* gain, float* dst, double* moments,
+                      tmc_stream_t stream);
+/* pixels further than `threshold` population standard deviations from their frame's mean are replaced by one of their (up to
+ * 8) neighbours, picked by a hash of the position (the reference draws it with np.random.choice); moments are updated;
+ * hot_count (device int, nullable) receives the number found, at most `capacity` are replaced.
+ * workspace: tmc_hot_pixel_workspace_bytes(capacity) bytes */
+long tmc_hot_pixel_workspace_bytes(int capacity);
+int tmc_remove_hot_pixels(float* stack, int t, int h, int w, double* moments, float threshold, int capacity, void* workspace,
+                          int* hot_count, tmc_stream_t stream);
+/* every frame minus its own mean (moments[f][0] / n), in place */
+int tmc_subtract_frame_means(float* stack, int t, long n, const double* moments, tmc_stream_t stream);
+
 /* ---- cubic spline grids: torch_cubic_spline_grids.Cubic{CatmullRom,BSpline}Grid3d as used at
  *      deformation_field_utils.py:9-93, estimate_motion_optimizer.py:487-490, correct_motion.py:288-305 */
 long tmc_spline_workspace_floats(int c, int n0, int n1, int n2);

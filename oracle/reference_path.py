@@ -755,3 +755,59 @@ def synthetic_movie_large(t: int, h: int, w: int, seed: int = 0, noise: float = 
         fr = F.grid_sample(specimen[None, None], grid, mode="bicubic", padding_mode="border", align_corners=True)[0, 0]
         frames[k] = fr + noise * torch.randn((h, w), generator=g)
     return frames.contiguous(), walk
+
+
+# --------------------------------------------------------------------------------------
+# movie preparation   (examples/ttMotion.py:90-202 -- example code, not part of the package)
+# --------------------------------------------------------------------------------------
+
+
+def _hash3(a, b, c):
+    """Position hash of csrc/prepare.cu (uint32 arithmetic)."""
+    a, b, c = (np.asarray(v, dtype=np.uint64) for v in (a, b, c))
+    m = np.uint64(0xFFFFFFFF)
+    h = ((a * np.uint64(0x9E3779B1)) & m) ^ (((b + np.uint64(0x7F4A7C15)) & m) * np.uint64(0x85EBCA77) & m) ^ (
+        ((c + np.uint64(0x165667B1)) & m) * np.uint64(0xC2B2AE3D) & m)
+    h ^= h >> np.uint64(15)
+    h = (h * np.uint64(0x2C1B3C6D)) & m
+    h ^= h >> np.uint64(12)
+    h = (h * np.uint64(0x297A2D39)) & m
+    h ^= h >> np.uint64(15)
+    return h
+
+
+def prepare_movie(movie: np.ndarray, gain: np.ndarray | None = None, hot_pixel_threshold: float | None = None,
+                  zero_frame_means: bool = False):
+    """``gain_correct`` (:85-123, the multiply), ``remove_hot_pixels`` (:125-178) and ``set_frames_mean_zero`` (:180-202)
+    in the order of the example's ``main`` (:372-381), on a float32 copy of the movie.
+
+    One documented deviation: the reference replaces a hot pixel by ``np.random.choice`` of its neighbours, sequentially
+    and in place; here (and in csrc/prepare.cu) the neighbour is picked by a hash of (frame, y, x) and read from the frame
+    as it was before any replacement -- the same distribution, reproducible, order independent.  Returns
+    ``(movie float32, number of hot pixels)``."""
+    out = movie.astype(np.float32)
+    if gain is not None:
+        out = out * gain.astype(np.float32)
+    n_hot = 0
+    if hot_pixel_threshold is not None:
+        t, h, w = out.shape
+        fixed = out.copy()
+        for f in range(t):
+            frame = out[f]
+            mean, std = np.mean(frame, dtype=np.float64), np.std(frame, dtype=np.float64)
+            lim = np.float32(hot_pixel_threshold) * np.float32(std)
+            hot = (frame > np.float32(mean) + lim) | (frame < np.float32(mean) - lim)
+            for y, x in zip(*np.where(hot)):
+                y0, y1, x0, x1 = max(0, y - 1), min(h - 1, y + 1), max(0, x - 1), min(w - 1, x + 1)
+                cols, cells = x1 - x0 + 1, (y1 - y0 + 1) * (x1 - x0 + 1)
+                if cells <= 1:
+                    continue
+                pick = int(_hash3(f, y, x) % np.uint64(cells - 1))
+                if pick >= (y - y0) * cols + (x - x0):
+                    pick += 1
+                fixed[f, y, x] = frame[y0 + pick // cols, x0 + pick % cols]
+                n_hot += 1
+        out = fixed
+    if zero_frame_means:
+        out = out - np.mean(out, axis=(1, 2), keepdims=True, dtype=np.float64).astype(np.float32)
+    return out, n_hot

@@ -28,6 +28,7 @@ from .optimization_state import OptimizationState, OptimizationTracker
 from .patch_grid import patch_grid_centers
 from .spline_grids import CubicBSplineGrid3d, CubicCatmullRomGrid3d
 from .pipeline import estimate_motion, motion_correct, motion_correct_many
+from .prepare import prepare_movie
 from .utils import normalize_image
 
 __version__ = "0.1.0"
@@ -49,4 +50,5 @@ __all__ = [
     "motion_correct",
     "motion_correct_many",
     "dose_weight",
+    "prepare_movie",
 ]

@@ -37,6 +37,10 @@ _SIGNATURES = {
     "tmc_stack_stats": (I, [P, I, I, I, I, I, I, I, P, P, P]),
     "tmc_stack_moments": (I, [P, I, I, I, I, I, I, I, P, P, P]),
     "tmc_moments_to_mean_std": (I, [P, P, P]),
+    "tmc_convert_stack": (I, [P, I, I, L, P, P, P, P]),
+    "tmc_hot_pixel_workspace_bytes": (L, [I]),
+    "tmc_remove_hot_pixels": (I, [P, I, I, I, P, F, I, P, P, P]),
+    "tmc_subtract_frame_means": (I, [P, I, L, P, P]),
     "tmc_spline_workspace_floats": (L, [I, I, I, I]),
     "tmc_spline_eval": (I, [P, I, I, I, I, I, P, L, P, P, P]),
     "tmc_spline_eval_backward": (I, [I, I, I, I, I, P, L, P, F, P, P, P]),

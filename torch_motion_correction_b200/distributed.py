@@ -327,8 +327,7 @@ def estimate_local_motion_frame_split(local_frames, pixel_spacing, patch_shape, 
                     one_iteration()
                 finally:
                     graph.capture_end()
-                done = 2
-                for _ in range(n_iterations - 2):
+                for _ in range(n_iterations - 1):  # the capture itself executed nothing
                     graph.replay()
                 done = n_iterations
             main.wait_stream(side)

@@ -115,8 +115,13 @@ def motion_correct(image: torch.Tensor, pixel_spacing: float, grid_type: str = "
     return total, field
 
 
-def motion_correct_many(host_movies, pixel_spacing: float, device=None, out_host=None, **kwargs):
+def motion_correct_many(host_movies, pixel_spacing: float, device=None, out_host=None, gain=None, hot_pixel_threshold=None,
+                        zero_frame_means=False, **kwargs):
     """Align a sequence of movies held in (ideally pinned) HOST memory; yields ``(sum_host, field)``.
+
+    Movies may arrive in their detector-native type (uint8 / uint16 / int16 / float16, or float32): they cross PCIe as
+    they are (1-2 bytes per pixel instead of 4) and are converted on the device, together with the optional preparation of
+    ``prepare_movie`` (``gain`` multiply, hot-pixel replacement, per-frame mean removal; examples/ttMotion.py:90-202).
 
     The H2D copy of movie i+1 runs on a side stream while movie i is being estimated and corrected
     (two device buffers), and each result is copied back asynchronously: dataset-scale processing
@@ -134,9 +139,12 @@ def motion_correct_many(host_movies, pixel_spacing: float, device=None, out_host
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
+    prepared = [None]  # one fp32 buffer: movie i is prepared into it while movie i + 1 is still in flight over PCIe
+    gain_dev = gain.to(device=dev, dtype=torch.float32).contiguous() if gain is not None else None
+
     def start_copy(slot, host):
-        if buffers[slot] is None or buffers[slot].shape != host.shape:
-            buffers[slot] = torch.empty(host.shape, dtype=torch.float32, device=dev)
+        if buffers[slot] is None or buffers[slot].shape != host.shape or buffers[slot].dtype != host.dtype:
+            buffers[slot] = torch.empty(host.shape, dtype=host.dtype, device=dev)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])  # the previous occupant of this buffer has been processed
             buffers[slot].copy_(host, non_blocking=True)
@@ -160,8 +168,19 @@ def motion_correct_many(host_movies, pixel_spacing: float, device=None, out_host
         if upcoming is not None:
             start_copy(1 - slot, upcoming)
         main.wait_event(ready[slot])
-        total, field = motion_correct(buffers[slot], pixel_spacing, device=dev, **kwargs)
-        consumed[slot].record(main)
+        movie = buffers[slot]
+        if movie.dtype != torch.float32 or gain_dev is not None or hot_pixel_threshold is not None or zero_frame_means:
+            from .prepare import prepare_movie
+
+            if prepared[0] is None or prepared[0].shape != movie.shape:
+                prepared[0] = torch.empty(movie.shape, dtype=torch.float32, device=dev)
+            movie = prepare_movie(movie, gain=gain_dev, hot_pixel_threshold=hot_pixel_threshold,
+                                  zero_frame_means=zero_frame_means, device=dev, out=prepared[0])
+            consumed[slot].record(main)  # the staging buffer is free as soon as it has been converted
+            total, field = motion_correct(movie, pixel_spacing, device=dev, **kwargs)
+        else:
+            total, field = motion_correct(movie, pixel_spacing, device=dev, **kwargs)
+            consumed[slot].record(main)
         if pending is not None and out_host is not None:
             pending[2].synchronize()  # one shared host buffer: hand the previous result out before overwriting it
             yield pending[0], pending[1]
