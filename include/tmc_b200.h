@@ -231,20 +231,6 @@ int tmc_local_loss_grad(const void* spec, const double* norms, const float* eval
                         const float* patch_scale, const int* iteration, int g, int t, int tp, int ny, int nx, int ky_count,
                         int kx_count, int ky_start, float pixel_spacing, int loss_type, double* loss, float* grad_eval,
                         void* workspace, tmc_stream_t stream);
-/* frame-split movies (one movie over several GPUs): the loss/gradient evaluation in two halves around the
- * all-reduce of Sigma = sum over ALL frames of the shifted spectra -- the quantity that couples the frames at
- * estimate_motion_optimizer.py:391-399.  spec (g, tp, ky_count, kx_count): spectra of the LOCAL frames; eval_new / eval_base
- * (t_local, g, 2).  tmc_local_split_sigma -> sigma (g, ky_count*kx_count) complex64 partial sums (all-reduce, SUM);
- * tmc_local_split_grad(sigma = reduced, sum_norms (g) double = norms summed over ALL frames) -> loss (full, identical on
- * every rank) + grad_eval (t_local, g, 2).  loss_type 0 mse / 1 cc.  workspace: tmc_local_loss_workspace_bytes(g, t_local, ..),
- * shared by the two calls of one evaluation. */
-int tmc_local_split_sigma(const void* spec, const float* eval_new, const float* eval_base, int g, int t_local, int tp, int ny,
-                          int nx, int ky_count, int kx_count, int ky_start, float pixel_spacing, void* sigma, void* workspace,
-                          tmc_stream_t stream);
-int tmc_local_split_grad(const void* spec, const void* sigma, const double* sum_norms, const float* patch_scale,
-                         const int* iteration, int g, int t_local, int tp, int t_total, int ny, int nx, int ky_count,
-                         int kx_count, int ky_start, float pixel_spacing, int loss_type, double* loss, float* grad_eval,
-                         void* workspace, tmc_stream_t stream);
 /* *counter += 1 on the stream: device-side iteration index so a captured optimiser step can be replayed
  * (patch_scale may then be (n_iterations, g) with `iteration` = counter; mse / cc only) */
 int tmc_advance_counter(int* counter, tmc_stream_t stream);

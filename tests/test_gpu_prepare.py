@@ -38,7 +38,7 @@ def test_prepare_movie_matches_the_example_pre_processing(dev, name, shape):
     rng = np.random.default_rng(1)
     gain = (1.0 + 0.05 * rng.standard_normal((h, w))).astype(np.float32)
     want, n_hot = rp.prepare_movie(movie, gain=gain, hot_pixel_threshold=10.0, zero_frame_means=True)
-    assert n_hot >= 4
+    assert n_hot >= 3
     host = torch.from_numpy(movie.view(np.uint16) if name == "uint16" else movie)
     if name == "uint16":
         host = host.view(torch.uint16)

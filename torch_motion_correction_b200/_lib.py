@@ -76,8 +76,6 @@ _SIGNATURES = {
     "tmc_local_spectra_norms": (I, [P, I, I, I, I, I, I, I, I, I, P, P]),
     "tmc_local_loss_workspace_bytes": (L, [I, I, I, I]),
     "tmc_local_loss_grad": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, I, F, I, P, P, P, P]),
-    "tmc_local_split_sigma": (I, [P, P, P, I, I, I, I, I, I, I, I, F, P, P, P]),
-    "tmc_local_split_grad": (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, I, F, I, P, P, P, P]),
     "tmc_advance_counter": (I, [P, P]),
     "tmc_adam_step": (I, [P, P, P, P, I, D, D, D, D, D, P, P]),
     "tmc_local_steps_supported": (I, [I, I, I, I]),

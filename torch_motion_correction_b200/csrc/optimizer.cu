@@ -346,144 +346,6 @@ __global__ void loss_fused_finish_kernel(const double* __restrict__ norms, const
   }
 }
 
-// ---- frame-split movies: the same fused "mse" / "cc" evaluation in two halves around an all-reduce ----------------
-// A rank holds the spectra of its own frames only.  Sigma = sum over ALL frames is the one quantity that couples the
-// frames (estimate_motion_optimizer.py:391-399): every rank sums its frames (split_sigma_kernel), the (G, bins)
-// partial sums are all-reduced, and the gradient of the local frames' shifts follows from the global Sigma
-// (split_grad_kernel; T below is the local frame count, T_total enters the loss constants only).
-
-template <int kFusedBins, int UNROLL>
-__global__ void __launch_bounds__(kOptThreads)
-split_sigma_kernel(const float2* __restrict__ spec, const float2* __restrict__ E, int T, int Tp, BandGeom geom,
-                   float2* __restrict__ sigma) {
-  const int g = blockIdx.y;
-  const int bins = geom.KY * geom.KX;
-  int bin[kFusedBins], kyb[kFusedBins], kx[kFusedBins];
-  float2 sum[kFusedBins];
-#pragma unroll
-  for (int i = 0; i < kFusedBins; ++i) {
-    bin[i] = (blockIdx.x * kFusedBins + i) * kOptThreads + threadIdx.x;
-    const int bb = bin[i] < bins ? bin[i] : 0;
-    kyb[i] = bb / geom.KX;
-    kx[i] = bb % geom.KX;
-    sum[i] = make_float2(0.f, 0.f);
-  }
-  const float2* sp = spec + (long)g * Tp * bins;
-  const float2* Eg = E + (long)g * T * (geom.KY + geom.KX);
-#pragma unroll UNROLL
-  for (int t = 0; t < T; ++t) {
-    const float2* Et = Eg + (long)t * (geom.KY + geom.KX);
-#pragma unroll
-    for (int i = 0; i < kFusedBins; ++i) {
-      if (bin[i] < bins) {
-        const float2 e = cmul(__ldg(Et + kyb[i]), __ldg(Et + geom.KY + kx[i]));
-        sum[i] = cadd(sum[i], cmul(__ldg(sp + (long)t * bins + bin[i]), e));
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < kFusedBins; ++i)
-    if (bin[i] < bins) sigma[(long)g * bins + bin[i]] = sum[i];
-}
-
-// q[g] += sum_f w |Sigma|^2 (Sigma: the all-reduced sum) ; grad[g][t][:] += -2 b sum_f w (c f) Im(S_t conj Sigma), t local
-template <int kFusedBins, int UNROLL>
-__global__ void __launch_bounds__(kOptThreads)
-split_grad_kernel(const float2* __restrict__ spec, const float2* __restrict__ E, const float2* __restrict__ sigma,
-                  const float* __restrict__ patch_scale, const int* __restrict__ iter_ptr, int G, int T, int Tp, int T_total,
-                  BandGeom geom, int loss_type, int ph, int pw, double* __restrict__ q, float* __restrict__ grad) {
-  extern __shared__ float acc[];  // [T][2]
-  const int g = blockIdx.y;
-  const int bins = geom.KY * geom.KX;
-  for (int i = threadIdx.x; i < 2 * T; i += kOptThreads) acc[i] = 0.f;
-  const float sc = patch_scale[(long)(iter_ptr ? *iter_ptr : 0) * G + g];
-  if (sc == 0.f || T_total < 2) return;
-  float b;
-  if (loss_type == 0) {
-    const float a = (float)T_total / (float)(T_total - 1);
-    b = -sc * a * a / (float)T_total;
-  } else {
-    b = -sc / ((float)ph * (float)pw * (float)(T_total - 1));
-  }
-  int bin[kFusedBins], kyb[kFusedBins], kx[kFusedBins];
-  float cfy[kFusedBins], cfx[kFusedBins], w[kFusedBins];
-  float2 sum[kFusedBins];
-#pragma unroll
-  for (int i = 0; i < kFusedBins; ++i) {
-    bin[i] = (blockIdx.x * kFusedBins + i) * kOptThreads + threadIdx.x;
-    const bool live = bin[i] < bins;
-    const int bb = live ? bin[i] : 0;
-    float herm;
-    bin_freqs(geom, bb, cfy[i], cfx[i], herm);
-    w[i] = live ? (loss_type == 0 ? 1.0f : herm) : 0.0f;
-    kyb[i] = bb / geom.KX;
-    kx[i] = bb % geom.KX;
-    bin[i] = bb;
-    sum[i] = sigma[(long)g * bins + bb];
-  }
-  {
-    double v = 0.0;
-#pragma unroll
-    for (int i = 0; i < kFusedBins; ++i) v += (double)w[i] * ((double)sum[i].x * sum[i].x + (double)sum[i].y * sum[i].y);
-    v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) atomicAdd(q + g, v);
-  }
-  const float2* sp = spec + (long)g * Tp * bins;
-  const float2* Eg = E + (long)g * T * (geom.KY + geom.KX);
-  __syncthreads();  // acc zeroed
-#pragma unroll UNROLL
-  for (int t = 0; t < T; ++t) {
-    const float2* Et = Eg + (long)t * (geom.KY + geom.KX);
-    float gy = 0.f, gx = 0.f;
-#pragma unroll
-    for (int i = 0; i < kFusedBins; ++i) {
-      const float2 e = cmul(__ldg(Et + kyb[i]), __ldg(Et + geom.KY + kx[i]));
-      const float2 s = cmul(__ldg(sp + (long)t * bins + bin[i]), e);
-      const float im = w[i] * (s.y * sum[i].x - s.x * sum[i].y);  // w Im(S conj Sigma)
-      gy = fmaf(cfy[i], im, gy);
-      gx = fmaf(cfx[i], im, gx);
-    }
-    gy = warp_sum(gy);
-    gx = warp_sum(gx);
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(acc + 2 * t, gy);
-      atomicAdd(acc + 2 * t + 1, gx);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * T; i += kOptThreads) {
-    const float v = -2.0f * b * acc[i];
-    if (v != 0.f) atomicAdd(grad + (long)g * T * 2 + i, v);
-  }
-}
-
-// loss = sum_g scale_g l_g(q_g, sum over ALL frames of A_t) (the same on every rank); grad_eval[t][g][c] of the local frames
-__global__ void split_finish_kernel(const double* __restrict__ sum_norms, const double* __restrict__ q,
-                                    const float* __restrict__ patch_scale, const int* __restrict__ iter_ptr, int G, int T,
-                                    int T_total, int ph, int pw, int loss_type, const float* __restrict__ grad_shifts,
-                                    float pixel_spacing, double* __restrict__ loss, float* __restrict__ grad_eval) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < T * G * 2) {
-    const int c = i & 1, r = i >> 1;
-    const int t = r / G, g = r % G;
-    grad_eval[i] = -grad_shifts[((long)g * T + t) * 2 + c] / pixel_spacing;
-  }
-  if (i < G && T_total >= 2) {
-    const int g = i;
-    const double sc = (double)patch_scale[(long)(iter_ptr ? *iter_ptr : 0) * G + g];
-    if (sc != 0.0) {
-      double l;
-      if (loss_type == 0) {
-        const double a = (double)T_total / (double)(T_total - 1);
-        l = sc * a * a * (sum_norms[g] - q[g] / T_total);
-      } else {
-        l = -sc * (q[g] - sum_norms[g]) / ((double)ph * (double)pw * (double)(T_total - 1));
-      }
-      atomicAdd(loss, l);
-    }
-  }
-}
-
 __global__ void advance_counter_kernel(int* counter) { *counter += 1; }
 
 // torch.optim.Adam (amsgrad=False, maximize=False), single-tensor formulas, step = *step_counter + 1:
@@ -620,67 +482,6 @@ TMC_API int tmc_local_loss_grad(const void* spec, const double* norms, const flo
   return TMC_OK;
 }
 
-
-// ---- frame-split movies: one loss + gradient evaluation in two halves around the all-reduce of Sigma --
-//  spec (G, tp, KY, KX): spectra of the LOCAL frames; eval_new / eval_base (t_local, G, 2) Angstrom at the local frames'
-//  patch centres.  tmc_local_split_sigma -> sigma (G, KY*KX) complex64 partial sums (all-reduce them, SUM);
-//  tmc_local_split_grad(sigma = the reduced sums, sum_norms (G) double = sum over ALL frames of the spectra norms under
-//  the loss's weighting) -> loss (device double: the full loss, identical on every rank) and grad_eval (t_local, G, 2).
-//  loss_type 0 mse / 1 cc.  workspace: tmc_local_loss_workspace_bytes(g, t_local, ky_count, kx_count), shared by both
-//  calls of one evaluation.
-TMC_API int tmc_local_split_sigma(const void* spec, const float* eval_new, const float* eval_base, int g, int t_local, int tp,
-                                  int ny, int nx, int ky_count, int kx_count, int ky_start, float pixel_spacing, void* sigma,
-                                  void* workspace, cudaStream_t stream) {
-  TMC_CHECK_ARG(spec && eval_new && eval_base && sigma && workspace, "local_split_sigma: null pointer");
-  TMC_CHECK_ARG(g >= 1 && t_local >= 0 && tp >= t_local && pixel_spacing > 0.f, "local_split_sigma: bad arguments");
-  BandGeom geom{ny, nx, ky_count, kx_count, ky_start};
-  const long bins = (long)ky_count * kx_count;
-  float* wf = (float*)workspace;
-  float2* E = (float2*)(wf + 2 * g * bins);
-  float* shifts = wf + 2 * g * bins + 2l * g * t_local * (ky_count + kx_count);
-  if (t_local == 0) {
-    TMC_CUDA(cudaMemsetAsync(sigma, 0, sizeof(float2) * (size_t)g * bins, stream));
-    return TMC_OK;
-  }
-  const int n = t_local * g * 2;
-  predicted_shifts_kernel<<<tmc_div_up(n, 128), 128, 0, stream>>>(eval_new, eval_base, t_local, g, pixel_spacing, shifts); tmc_count_launch();
-  phase_tables_kernel<<<g * t_local, 128, 0, stream>>>(shifts, t_local, geom, E); tmc_count_launch();
-  dim3 fgrid(tmc_div_up(bins, kOptThreads * 4), g);
-  split_sigma_kernel<4, 4><<<fgrid, kOptThreads, 0, stream>>>((const float2*)spec, E, t_local, tp, geom, (float2*)sigma); tmc_count_launch();
-  TMC_CHECK_LAUNCH("tmc_local_split_sigma");
-  return TMC_OK;
-}
-
-TMC_API int tmc_local_split_grad(const void* spec, const void* sigma, const double* sum_norms, const float* patch_scale,
-                                 const int* iteration, int g, int t_local, int tp, int t_total, int ny, int nx, int ky_count,
-                                 int kx_count, int ky_start, float pixel_spacing, int loss_type, double* loss, float* grad_eval,
-                                 void* workspace, cudaStream_t stream) {
-  TMC_CHECK_ARG(spec && sigma && sum_norms && patch_scale && loss && workspace, "local_split_grad: null pointer");
-  TMC_CHECK_ARG(g >= 1 && t_local >= 0 && tp >= t_local && t_total >= t_local && (loss_type == 0 || loss_type == 1) &&
-                    pixel_spacing > 0.f, "local_split_grad: bad arguments (mse and cc losses only)");
-  TMC_CHECK_ARG(t_local == 0 || grad_eval, "local_split_grad: null gradient");
-  BandGeom geom{ny, nx, ky_count, kx_count, ky_start};
-  const long bins = (long)ky_count * kx_count;
-  float* wf = (float*)workspace;
-  float2* E = (float2*)(wf + 2 * g * bins);
-  float* shifts = wf + 2 * g * bins + 2l * g * t_local * (ky_count + kx_count);
-  float* grad_shifts = shifts + 2l * g * t_local;
-  const long floats = local_loss_workspace_floats(g, t_local, ky_count, kx_count);
-  double* q = (double*)(wf + floats);
-  TMC_CUDA(cudaMemsetAsync(q, 0, sizeof(double) * (size_t)g, stream));
-  if (t_local > 0) TMC_CUDA(cudaMemsetAsync(grad_shifts, 0, sizeof(float) * 2 * (size_t)g * t_local, stream));
-  TMC_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), stream));
-  dim3 fgrid(tmc_div_up(bins, kOptThreads * 4), g);
-  split_grad_kernel<4, 4><<<fgrid, kOptThreads, sizeof(float) * 2 * (t_local > 0 ? t_local : 1), stream>>>(
-      (const float2*)spec, E, (const float2*)sigma, patch_scale, iteration, g, t_local, tp, t_total, geom, loss_type, ny, nx, q,
-      grad_shifts); tmc_count_launch();
-  const int n = t_local * g * 2;
-  split_finish_kernel<<<tmc_div_up(n > g ? n : g, 128), 128, 0, stream>>>(sum_norms, q, patch_scale, iteration, g, t_local, t_total,
-                                                                          ny, nx, loss_type, grad_shifts, pixel_spacing, loss,
-                                                                          grad_eval); tmc_count_launch();
-  TMC_CHECK_LAUNCH("tmc_local_split_grad");
-  return TMC_OK;
-}
 
 // *counter += 1 on the stream (device-side iteration index of a captured optimiser step)
 TMC_API int tmc_advance_counter(int* counter, cudaStream_t stream) {

@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 from . import _fourier, _ops
-from ._common import as_f32, grid_kind, resolve_device
+from ._common import as_f32, cached_device_tensor, grid_kind, resolve_device
 from ._lib import call, ptr, stream_ptr
 from .correct_motion import correct_motion_fast
 from .deformation_field_utils import resample_deformation_field
@@ -174,21 +174,58 @@ def estimate_patch_motion_frame_split(local_frames, pixel_spacing, frame_offset,
     return field, centers.to(dev)
 
 
+def _make_patch_shard_problem(spec_sub, centres_norm_sub, base, kind, loss_code, px, t, ph, pw, resolution, plan, dev):
+    """A ``LocalMotionProblem`` (estimate_motion_optimizer.py) for a subset of the patches with ALL frames, built from
+    spectra ``spec_sub`` (G_r, tp, KY, KX) that are already on the device."""
+    from .estimate_motion_optimizer import FUSED_STEPS, LocalMotionProblem
+    from ._lib import query
+
+    prob = LocalMotionProblem.__new__(LocalMotionProblem)
+    g = spec_sub.shape[0]
+    prob.kind, prob.loss_type, prob.dev, prob.px = kind, loss_code, dev, px
+    prob.t, prob.ph, prob.pw = t, ph, pw
+    prob.resolution = resolution
+    prob.g = g
+    prob.base = base
+    prob.plan = plan
+    prob.tp = spec_sub.shape[1]
+    prob.fused = FUSED_STEPS and loss_code != 2 and bool(query("tmc_local_steps_supported", g, t, resolution[0], resolution[1] * resolution[2]))
+    prob.frame_major = False  # (G, tp, KY, KX): patch-major
+    prob.spec = spec_sub
+    prob.norms = torch.empty((g, t, 2), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        call("tmc_local_spectra_norms", ptr(spec_sub), g, t, prob.tp, ph, pw, plan.ky, plan.kx, plan.ky_start, 0, ptr(prob.norms),
+             stream_ptr(dev))
+    prob.centres_norm = centres_norm_sub  # (T, g, 3)
+    prob.eval_base = _ops.spline_eval(base, kind, centres_norm_sub)
+    ws_bytes = query("tmc_local_loss_workspace_bytes", g, t, plan.ky, plan.kx)
+    prob.workspace = torch.empty(((ws_bytes + 7) // 8,), dtype=torch.float64, device=dev)
+    prob.loss = torch.zeros((1,), dtype=torch.float64, device=dev)
+    prob.grad_eval = torch.empty((t, g, 2), dtype=torch.float32, device=dev)
+    prob.eval_new = torch.empty((t, g, 2), dtype=torch.float32, device=dev)
+    prob.grad = torch.empty((2, *resolution), dtype=torch.float32, device=dev)
+    n_ws = query("tmc_spline_workspace_floats", 2, *resolution)
+    prob.ws_eval = torch.empty((n_ws,), dtype=torch.float32, device=dev)
+    prob.ws_back = torch.empty((n_ws,), dtype=torch.float32, device=dev)
+    if prob.fused:
+        prob._setup_fused_steps()
+    return prob
+
+
 def estimate_local_motion_frame_split(local_frames, pixel_spacing, patch_shape, deformation_field_resolution,
                                       initial_deformation_field, frame_offset, total_frames, mean_std, n_iterations=100,
                                       b_factor=500, frequency_range=(300, 10), grid_type="catmull_rom", loss_type="mse",
                                       optimizer_kwargs=None, group=None, return_losses=False):
     """``estimate_local_motion`` (Adam; "mse" / "cc" losses) for a frame-split movie.
 
-    Every rank transforms the patches of its own frames once.  Per iteration the frames are coupled only through
-    ``Sigma = sum_t S_t`` (estimate_motion_optimizer.py:391-399): each rank sums its frames
-    (``tmc_local_split_sigma``), the (patches x pass-band box) complex partial sums are all-reduced, the gradient of the
-    local frames' shifts follows from the reduced sums (``tmc_local_split_grad``), is scattered onto the spline
-    coefficients and all-reduced again (2 nt nh nw floats); the Adam update is replicated on every rank.  The shuffled
-    mini-batch weighting (quirks Q10 / Q11) is drawn on rank 0 and broadcast, so the result equals the single-GPU run with
-    the same ``random`` state.  Returns the (2, nt, nh, nw) field (identical on all ranks)."""
+    Frames for the transforms, patches for the optimiser: every rank transforms the patches of its own frames once, the
+    band-limited spectra (a few % of the movie) are exchanged so that every rank holds ALL frames of ITS share of the
+    patches, and the iterations run on the single-GPU kernels (``tmc_local_steps``).  ``Sigma = sum_t S_t``, the only
+    coupling between frames (estimate_motion_optimizer.py:391-399), is then local to a rank; per iteration only the
+    coefficient gradient (2 nt nh nw floats) is all-reduced, and the Adam update is replicated.  The shuffled mini-batch
+    weighting (quirks Q10 / Q11) is drawn on rank 0 and broadcast, so the result equals the single-GPU run with the same
+    ``random`` state up to the order of the fp32 sums.  Returns the (2, nt, nh, nw) field (identical on all ranks)."""
     from .estimate_motion_optimizer import LOSS_TYPES, _shuffled_batches
-    from ._lib import query
 
     rank, world = _world(group)
     dev = local_frames.device
@@ -220,35 +257,40 @@ def estimate_local_motion_frame_split(local_frames, pixel_spacing, patch_shape, 
         with torch.cuda.device(dev):
             call("tmc_subtract_mean", ptr(base), base.numel(), stream_ptr(dev))
 
-    # spectra of the local frames, patch-major (G, tp, KY, KX)
+    # spectra of the local frames: one plane per (frame, patch), frame-major (t_local, G, KY, KX)
     plan = _fourier.BandPlan(ph, pw, dev, px, b_factor, frequency_range)
     mask, ylo, yhi = _fourier.soft_disc_mask((ph, pw), pw / 4, pw / 4, dev)  # quirk Q18
-    tp = 2 * ((t_local + 1) // 2)
-    bins = plan.plane_elems
+    words = plan.plane_elems * 2
     if t_local > 0:
-        jobs = torch.tensor([[i, 1, i + 1 if i + 1 < t_local else -1, 1, y0[gi], x0[gi]] for gi in range(g)
-                             for i in range(0, t_local, 2)], dtype=torch.int32).to(dev)
-        spec = plan.forward(frames, mean_std, mask, ylo, yhi, jobs, job_mode=2)
-        norms = torch.empty((g, t_local, 2), dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev):
-            call("tmc_local_spectra_norms", ptr(spec), g, t_local, tp, ph, pw, plan.ky, plan.kx, plan.ky_start, 0, ptr(norms),
-                 stream_ptr(dev))
-        sum_norms = norms[:, :, 0 if lt == 0 else 1].sum(dim=1).contiguous()
+        jobs = cached_device_tensor(
+            ("split_local_jobs", (t_local, h, w, ph, pw)),
+            lambda: torch.tensor([[i, 1, i + 1 if i + 1 < t_local else -1, 1, y0[gi], x0[gi]] for i in range(0, t_local, 2)
+                                  for gi in range(g)], dtype=torch.int32), dev)
+        pairs = (t_local + 1) // 2
+        spec = plan.forward(frames, mean_std, mask, ylo, yhi, jobs, job_mode=2)  # planes [pair][patch][frame of the pair]
+        spec = spec.view(pairs, g, 2, words).permute(0, 2, 1, 3).reshape(2 * pairs, g, words)[:t_local].contiguous()
     else:
-        spec = torch.zeros((1,), dtype=torch.float32, device=dev)
-        sum_norms = torch.zeros((g,), dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(sum_norms, op=dist.ReduceOp.SUM, group=group)
+        spec = torch.zeros((0, g, words), dtype=torch.float32, device=dev)
+    full = all_gather_frames(spec, t, group)  # (T, G, words) on every rank: a few % of the movie
+    del spec
+    # this rank's share of the patches, all frames: (G_r, tp, KY, KX)
+    g0, g1 = frame_range(g, rank, world)
+    g_sub = g1 - g0
+    tp = 2 * ((t + 1) // 2)
+    spec_sub = torch.zeros((max(g_sub, 1), tp, words), dtype=torch.float32, device=dev)
+    if g_sub > 0:
+        spec_sub[:, :t] = full[:, g0:g1].permute(1, 0, 2)
+    del full
 
-    # normalised (t, y, x) centres of the local frames, time-major (t_local, G, 3)
-    norm = centers[frame_offset : frame_offset + t_local].clone().float()
+    # normalised (t, y, x) centres of this rank's patches, time-major (T, G_r, 3)
+    norm = centers.clone().float()
     norm[..., 0] /= float(t - 1) if t > 1 else float("nan")
     norm[..., 1] /= float(h - 1)
     norm[..., 2] /= float(w - 1)
-    centres_norm = norm.reshape(t_local, g, 3).contiguous().to(dev)
-    eval_base = _ops.spline_eval(base, kind, centres_norm) if t_local > 0 else torch.zeros((0, g, 2), device=dev)
+    centres_sub = norm.reshape(t, g, 3)[:, g0:max(g1, g0 + 1)].contiguous().to(dev)
+    problem = _make_patch_shard_problem(spec_sub, centres_sub, base, kind, lt, px, t, ph, pw, resolution, plan, dev)
 
-    # the mini-batch weighting of every iteration: drawn once (rank 0) and broadcast
+    # the mini-batch weighting of every iteration: drawn once (rank 0) and broadcast; each rank uses its patches' columns
     def patch_scales(batches):
         scale = [0.0] * g
         for batch in batches:
@@ -266,84 +308,33 @@ def estimate_local_motion_frame_split(local_frames, pixel_spacing, patch_shape, 
     scales = scales.to(dev)
     if world > 1:
         dist.broadcast(scales, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    scales_sub = scales[:, g0:max(g1, g0 + 1)].contiguous()
+    if g_sub == 0:
+        scales_sub.zero_()  # a rank without patches contributes nothing
 
     new = torch.zeros((2, *resolution), dtype=torch.float32, device=dev)
     exp_avg, exp_avg_sq = torch.zeros_like(new), torch.zeros_like(new)
     lr, (b1, b2) = float(kw.get("lr", 0.01)), kw.get("betas", (0.9, 0.999))
     eps, wd = float(kw.get("eps", 1e-08)), float(kw.get("weight_decay", 0))
     counter = torch.zeros((1,), dtype=torch.int32, device=dev)
-    sigma = torch.empty((g, bins, 2), dtype=torch.float32, device=dev)
-    ws = torch.empty(((query("tmc_local_loss_workspace_bytes", g, max(t_local, 1), plan.ky, plan.kx) + 7) // 8,),
-                     dtype=torch.float64, device=dev)
-    grad = torch.zeros_like(new)  # partial gradient of the local frames, all-reduced (the loss is already global)
-    loss = torch.zeros((1,), dtype=torch.float64, device=dev)
-    grad_eval = torch.empty((max(t_local, 1), g, 2), dtype=torch.float32, device=dev)
     losses = []
-    n_ws = query("tmc_spline_workspace_floats", 2, *resolution)
-    ws_eval = torch.empty((n_ws,), dtype=torch.float32, device=dev)
-    ws_back = torch.empty((n_ws,), dtype=torch.float32, device=dev)
-    eval_new = torch.empty((max(t_local, 1), g, 2), dtype=torch.float32, device=dev)
-    def one_iteration():
-        """Everything of one optimiser iteration is device-side (the mini-batch row and the Adam step number come from the
-        device counter), so it can be captured once -- the two all-reduces included -- and replayed."""
-        with torch.cuda.device(dev):
-            stream = stream_ptr(dev)
-            if t_local > 0:
-                _ops.spline_eval(new, kind, centres_norm, out=eval_new.view(-1, 2), ws=ws_eval)
-            call("tmc_local_split_sigma", ptr(spec), ptr(eval_new), ptr(eval_base), g, t_local, tp, ph, pw, plan.ky, plan.kx,
-                 plan.ky_start, px, ptr(sigma), ptr(ws), stream)
-            if world > 1:
-                dist.all_reduce(sigma, op=dist.ReduceOp.SUM, group=group)
-            call("tmc_local_split_grad", ptr(spec), ptr(sigma), ptr(sum_norms), ptr(scales), ptr(counter), g, t_local, tp, t, ph, pw,
-                 plan.ky, plan.kx, plan.ky_start, px, lt, ptr(loss), ptr(grad_eval), ptr(ws), stream)
-            if t_local > 0:
-                _ops.spline_eval_backward((2, *resolution), kind, centres_norm, grad_eval, out=grad, ws=ws_back)
+    with torch.cuda.device(dev):
+        stream = stream_ptr(dev)
+        for i in range(n_iterations):
+            if problem.fused:
+                loss, grad = problem.loss_and_grad(new, scales_sub, row=i)
             else:
-                grad.zero_()
+                loss, grad = problem.loss_and_grad(new, scales_sub[i])
             if world > 1:
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+            if return_losses:
+                total = loss.clone()
+                if world > 1:
+                    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+                losses.append(total)
             call("tmc_adam_step", ptr(new), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), new.numel(), lr, float(b1), float(b2), eps, wd,
                  ptr(counter), stream)
             call("tmc_advance_counter", ptr(counter), stream)
-
-    done = 0
-    capturable = world == 1 or dist.get_backend(group) == "nccl"  # gloo stages through the host: cannot be captured
-    use_graph = (os.environ.get("TMC_SPLIT_GRAPH", "1") != "0" and n_iterations >= 4 and not return_losses and capturable
-                 and not torch.cuda.is_current_stream_capturing())
-    if use_graph:
-        # launch-bound loop (~10 small kernels + 2 collectives per iteration): one eager iteration, one captured, the rest
-        # replayed.  Whether to capture is decided identically on every rank (a rank replaying while another runs eagerly
-        # would still issue the same collectives in the same order, but keep it simple).
-        main = torch.cuda.current_stream(dev)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(main)
-        graph = torch.cuda.CUDAGraph()
-        try:
-            with torch.cuda.stream(side):
-                one_iteration()
-                done = 1
-                graph.capture_begin()
-                try:
-                    one_iteration()
-                finally:
-                    graph.capture_end()
-                for _ in range(n_iterations - 1):  # the capture itself executed nothing
-                    graph.replay()
-                done = n_iterations
-            main.wait_stream(side)
-        except Exception as exc:  # capture refused (e.g. a process-group backend that cannot be captured): finish eagerly
-            import warnings
-
-            if os.environ.get("TMC_DEBUG"):
-                raise
-            warnings.warn(f"CUDA-graph capture of the frame-split optimiser iteration failed ({exc}); running eagerly", stacklevel=2)
-            main.wait_stream(side)
-            if done == 1:
-                pass  # the eager iteration has run; the failed capture executed nothing
-    for _ in range(done, n_iterations):
-        one_iteration()
-        if return_losses:
-            losses.append(loss.clone())
     final = (new + base).contiguous()
     with torch.cuda.device(dev):
         call("tmc_subtract_mean", ptr(final), final.numel(), stream_ptr(dev))
