@@ -142,7 +142,10 @@ int tmc_dose_filter_spectra(void* spec, const int* jobs, int njobs, int ny, int 
                             float* tables, tmc_stream_t stream);
 
 /* ---- FFT plans ------------------------------------------------------------------------------------ */
-int tmc_fft_supported_length(int n); /* powers of two in [16, 8192]; any other n in [2, 4096] (Bluestein) */
+/* 1: powers of two in [16, 8192] and any other n in [2, 4096] (Bluestein): full and band-limited transforms;
+ * 2: 2..8 times such a length (K3 5760 x 4092, super-resolution 11520 x 8184): band-limited transforms only (tmc_rfft2_band,
+ *    tmc_xc_peaks: the axis is decimated, n = R n', and the R sub-transforms are combined on the band); 0: unsupported */
+int tmc_fft_supported_length(int n);
 long tmc_fft_plan_elems(int n);      /* complex64 elements of a plan buffer, 0 if unsupported */
 int tmc_fft_plan_init(int n, void* plan, tmc_stream_t stream);
 /* out[r] = DFT_n(in[r]) for `rows` complex64 rows (utility / tests) */

@@ -190,9 +190,47 @@ def test_correct_motion_fast_golden(dev, golden_small):
 
 
 def test_unsupported_length_raises(dev):
-    # non-power-of-two lengths above 4096 would need a 16384-point shared-memory transform
+    # 8198 = 2 x 4099 (prime): no decimation into lengths the shared-memory transforms cover
     with pytest.raises(NotImplementedError):
-        tmc.estimate_global_motion(torch.zeros((2, 5000, 64), device=dev), 1.0)
+        tmc.estimate_global_motion(torch.zeros((2, 8198, 64), device=dev), 1.0)
+    # full (not band-limited) transforms of a decimated length
+    with pytest.raises(NotImplementedError):
+        tmc.correct_motion_fast(torch.zeros((2, 5000, 64), device=dev), torch.zeros((2, 2, 1, 1), device=dev))
+
+
+@pytest.mark.parametrize("shape", [(5000, 4100), (5760, 4092), (600, 9000), (11520, 96), (16384, 128)])
+def test_band_limited_spectra_of_long_axes(dev, shape):
+    """Axes beyond the shared-memory transforms (> 4096, not a power of two <= 8192) are decimated, n = R n': the R
+    sub-transforms are combined on the band (forward) / the twiddled band is inverted per sub-sequence (inverse)."""
+    ny, nx = shape
+    g = torch.Generator().manual_seed(ny + nx)
+    img = torch.randn((3, ny, nx), generator=g).to(dev)
+    px = 1.0
+    plan = _fourier.BandPlan(ny, nx, dev, px, 500.0, (300, 10))
+    mask, ylo, yhi = _fourier.soft_disc_mask((ny, nx), min(ny, nx) / 4, min(ny, nx) / 8, dev)
+    spec = plan.forward(img, None, mask, ylo, yhi, _fourier.frame_pair_jobs(3, dev), job_mode=2)[:3]
+    full = torch.fft.rfftn((img * mask).double(), dim=(-2, -1))
+    ky = (torch.arange(plan.ky, device=dev) + plan.ky_start) % ny
+    want = full[:, ky][:, :, : plan.kx] * plan.weight.double()
+    err = (as_complex(spec).to(torch.complex128) - want).abs().max() / want.abs().max()
+    assert float(err) < 5e-6, float(err)
+    # inverse + argmax: the cross-correlation of frame 0 with a rolled copy of itself peaks at the roll
+    sy, sx = 37, -21
+    pair = torch.stack([img[0], torch.roll(img[0], (sy, sx), dims=(0, 1))])
+    sp = plan.forward(pair, None, mask, ylo, yhi, _fourier.frame_pair_jobs(2, dev), job_mode=2)
+    prod = _fourier.pair_products(sp, torch.tensor([0], dtype=torch.int32, device=dev), torch.tensor([1], dtype=torch.int32, device=dev),
+                                  plan.plane_elems)
+    shifts = plan.peaks(prod.view(1, plan.ky, plan.kx, 2), sub_pixel=False)
+    assert shifts.cpu().tolist() == [[float(sy), float(sx)]]
+
+
+def test_global_motion_k3_frame_size(dev):
+    """K3-sized frames (5760 x 4092) through estimate_global_motion against the oracle."""
+    movie, walk = rp.synthetic_movie(4, 4092, 5760, seed=3, noise=1.0, drift=7.0, integer_shifts=True, sigma_f=0.08)
+    want = rp.estimate_global_motion(movie, 0.83)
+    got = tmc.estimate_global_motion(movie.to(dev), 0.83)
+    assert torch.equal(torch.round(got[:, :, 0, 0].T.cpu() / 0.83), walk)
+    assert float((got.cpu() - want).abs().max()) <= 1e-5
 
 
 def test_global_motion_non_power_of_two_frames(dev):

@@ -81,10 +81,12 @@ class BandPlan:
     def __init__(self, ny: int, nx: int, device: torch.device, pixel_spacing: float | None = None,
                  b_factor: float | None = None, frequency_range=None, full: bool = False):
         for n in (ny, nx):
-            if not query("tmc_fft_supported_length", n):
+            kind = query("tmc_fft_supported_length", n)
+            if kind == 0 or (full and kind != 1):
                 raise NotImplementedError(
-                    f"transform length {n} is not supported: the sm_100a FFT kernels take powers of two in [16, 8192] "
-                    f"and arbitrary lengths up to 4096 (patch side lengths / frame sizes)"
+                    f"transform length {n} is not supported: the sm_100a FFT kernels take powers of two in [16, 8192] and "
+                    f"arbitrary lengths up to 4096 (patch side lengths / frame sizes); band-limited transforms (the motion "
+                    f"estimators) also take 2..8 times such a length (K3 5760 x 4092, super-resolution 11520 x 8184)"
                 )
         self.ny, self.nx, self.device = ny, nx, device
         self.tw_y, self.tw_x = twiddles(ny, device), twiddles(nx, device)

@@ -44,21 +44,49 @@ inline int fft_size_for(int n) {  // 0: unsupported
   return m <= 8192 ? m : 0;
 }
 
+// Axes longer than the shared-memory transforms reach (n > 4096 and not a power of two <= 8192: K3 frames are
+// 5760 x 4092, super-resolution 11520 x 8184) are decimated: n = R n' with n' supported, and with j = R m + r
+//   forward, band-limited output:  X[k] = sum_r W_n^{r k} Y_r[k mod n'],   Y_r = DFT_n'(x[R m + r])
+//   inverse, band-limited input:   x[R m + r] = IDFT_n'( X[k] W_n^{-r k} aliased onto k mod n' )[m]
+// (the second needs the band to span <= n' bins, which a band-pass below Nyquist / R always does).  The generic
+// kernels below loop over r; R == 1 is the plain transform.
+inline int decimation_for(int n) {  // 0: unsupported
+  if (fft_size_for(n) > 0) return 1;
+  for (int r = 2; r <= 8; ++r)
+    if (n % r == 0 && fft_size_for(n / r) > 0) return r;
+  return 0;
+}
+
 struct AxisPlan {
   const float2* tw;     // W_M^m
   const float2* chirp;  // exp(-i pi j^2 / n), j < n   (Bluestein only)
   const float2* bhat;   // FFT_M of the wrapped conjugate chirp (Bluestein only)
-  int n;                // transform length
+  int n;                // length of the shared-memory transforms (n_total / R)
+  int R;                // decimation factor
+  int n_total;          // length of the axis
 };
 
-inline AxisPlan make_axis_plan(const void* buf, int n) {
+inline AxisPlan make_axis_plan(const void* buf, int n_total) {
+  const int R = decimation_for(n_total) > 0 ? decimation_for(n_total) : 1;
+  const int n = n_total / R;
   const int m = fft_size_for(n);
   AxisPlan p;
   p.tw = (const float2*)buf;
   p.chirp = p.tw + m;
   p.bhat = p.chirp + n;
   p.n = n;
+  p.R = R;
+  p.n_total = n_total;
   return p;
+}
+
+// W_N^{e} = exp(-2 pi i e / N) for any integer e (reduced exactly before the fp32 sincospi)
+__device__ __forceinline__ float2 twiddle_n(long e, int N) {
+  long m = e % N;
+  if (m < 0) m += N;
+  float s, c;
+  sincospif(-2.0f * (float)m / (float)N, &s, &c);
+  return make_float2(c, s);
 }
 
 __global__ void twiddle_kernel(int n, float2* __restrict__ tw) {
@@ -205,10 +233,13 @@ rows_forward_kernel(const float* __restrict__ image, int H, int W, const float* 
                     int x_margin, int ylo, int yhi, int NY, int KX, AxisPlan plan, float2* __restrict__ tmp) {
   constexpr int B = batch_for(MX);
   constexpr int STRIDE = padded_len(MX);
-  const int NX = BLU ? plan.n : MX;
+  const int NS = BLU ? plan.n : MX;             // length of the shared-memory transforms
+  const int R = plan.R, NX = plan.n_total;      // decimation factor, window width
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B * STRIDE;
+  float2* acc_pos = smem + 2 * B * STRIDE;      // R > 1 only: Z[k], Z[-k] accumulated over the sub-sequences
+  float2* acc_neg = acc_pos + B * KX;
   const int job = blockIdx.y;
   const int fa = jobs[job * 6 + 0], ea = jobs[job * 6 + 1], fb = jobs[job * 6 + 2], eb = jobs[job * 6 + 3];
   const int y0 = jobs[job * 6 + 4], x0 = jobs[job * 6 + 5];
@@ -221,36 +252,53 @@ rows_forward_kernel(const float* __restrict__ image, int H, int W, const float* 
   }
   const Window wa = make_window(image, fa, y0, x0, frame_shifts, H, W, ylo, yhi, NX, x_margin);
   const Window wb = make_window(image, fb >= 0 ? fb : fa, y0, x0, frame_shifts, H, W, ylo, yhi, NX, x_margin);
-  for (int idx = threadIdx.x; idx < B * NX; idx += kThreads) {
-    const int s = idx / NX, x = idx % NX;
-    const int y = row0 + s;
-    float2 z = make_float2(0.f, 0.f);
-    if (y < yhi) {
-      const float m = mask ? __ldg(mask + (long)y * NX + x) : 1.0f;
-      float va = __ldg(wa.wrap ? wa.wrapped(y, x, H, W) : wa.fast_base(W) + (long)y * W + x);
-      if (norm) va = __fdiv_rn(__fsub_rn(va, mean), stdv);
-      for (int e = 0; e < ea; ++e) va = __fmul_rn(va, m);
-      z.x = va;
-      if (fb >= 0) {
-        float vb = __ldg(wb.wrap ? wb.wrapped(y, x, H, W) : wb.fast_base(W) + (long)y * W + x);
-        if (norm) vb = __fdiv_rn(__fsub_rn(vb, mean), stdv);
-        for (int e = 0; e < eb; ++e) vb = __fmul_rn(vb, m);
-        z.y = vb;
+  for (int r = 0; r < R; ++r) {
+    for (int idx = threadIdx.x; idx < B * NS; idx += kThreads) {
+      const int s = idx / NS, m_ = idx % NS;
+      const int x = R * m_ + r;
+      const int y = row0 + s;
+      float2 z = make_float2(0.f, 0.f);
+      if (y < yhi) {
+        const float m = mask ? __ldg(mask + (long)y * NX + x) : 1.0f;
+        float va = __ldg(wa.wrap ? wa.wrapped(y, x, H, W) : wa.fast_base(W) + (long)y * W + x);
+        if (norm) va = __fdiv_rn(__fsub_rn(va, mean), stdv);
+        for (int e = 0; e < ea; ++e) va = __fmul_rn(va, m);
+        z.x = va;
+        if (fb >= 0) {
+          float vb = __ldg(wb.wrap ? wb.wrapped(y, x, H, W) : wb.fast_base(W) + (long)y * W + x);
+          if (norm) vb = __fdiv_rn(__fsub_rn(vb, mean), stdv);
+          for (int e = 0; e < eb; ++e) vb = __fmul_rn(vb, m);
+          z.y = vb;
+        }
       }
+      a[s * STRIDE + pad_idx(m_)] = z;
     }
-    a[s * STRIDE + pad_idx(x)] = z;
-  }
-  __syncthreads();
-  const float2* r = dft_smem<MX, BLU>(a, b, plan);
-  for (int idx = threadIdx.x; idx < B * KX; idx += kThreads) {
-    const int s = idx / KX, k = idx % KX;
-    const int y = row0 + s;
-    if (y >= yhi) continue;
-    const float2 zk = r[s * STRIDE + pad_idx(k)];
-    const float2 zn = r[s * STRIDE + pad_idx(k == 0 ? 0 : NX - k)];
-    // Z = A + iB with A, B Hermitian:  A = (Z[k] + conj Z[-k]) / 2,  B = (Z[k] - conj Z[-k]) / 2i
-    tmp[((long)(2 * job) * NY + y) * KX + k] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-    if (fb >= 0) tmp[((long)(2 * job + 1) * NY + y) * KX + k] = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+    __syncthreads();
+    const float2* res = dft_smem<MX, BLU>(a, b, plan);
+    for (int idx = threadIdx.x; idx < B * KX; idx += kThreads) {
+      const int s = idx / KX, k = idx % KX;
+      const int y = row0 + s;
+      if (y >= yhi) continue;
+      const int kp = k % NS;
+      float2 zk = res[s * STRIDE + pad_idx(kp)];
+      float2 zn = res[s * STRIDE + pad_idx(kp == 0 ? 0 : NS - kp)];
+      if (R > 1) {
+        const float2 tw = twiddle_n((long)r * k, NX);
+        zk = cmul(zk, tw);
+        zn = cmul(zn, make_float2(tw.x, -tw.y));
+        if (r > 0) {
+          zk = cadd(zk, acc_pos[idx]);
+          zn = cadd(zn, acc_neg[idx]);
+        }
+        acc_pos[idx] = zk;
+        acc_neg[idx] = zn;
+        if (r + 1 < R) continue;
+      }
+      // Z = A + iB with A, B Hermitian:  A = (Z[k] + conj Z[-k]) / 2,  B = (Z[k] - conj Z[-k]) / 2i
+      tmp[((long)(2 * job) * NY + y) * KX + k] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      if (fb >= 0) tmp[((long)(2 * job + 1) * NY + y) * KX + k] = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+    }
+    __syncthreads();  // the transform buffers are refilled by the next sub-sequence
   }
 }
 
@@ -263,33 +311,46 @@ cols_forward_kernel(const float2* __restrict__ tmp, int ylo, int yhi, int KX, in
                     const float* __restrict__ weight, AxisPlan plan, float2* __restrict__ out) {
   constexpr int B = batch_for(MY);
   constexpr int STRIDE = padded_len(MY);
-  const int NY = BLU ? plan.n : MY;
+  const int NS = BLU ? plan.n : MY;
+  const int R = plan.R, NY = plan.n_total;
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B * STRIDE;
+  float2* acc = smem + 2 * B * STRIDE;  // R > 1 only
   const long plane = blockIdx.y;
   const int kx0 = blockIdx.x * B;
   const float2* src = tmp + plane * NY * KX;
-  for (int idx = threadIdx.x; idx < B * NY; idx += kThreads) {
-    const int s = idx % B, y = idx / B;
-    float2 z = make_float2(0.f, 0.f);
-    if (y >= ylo && y < yhi && kx0 + s < KX) z = src[(long)y * KX + kx0 + s];
-    a[s * STRIDE + pad_idx(y)] = z;
-  }
-  __syncthreads();
-  const float2* r = dft_smem<MY, BLU>(a, b, plan);
   float2* dst = out + plane * KY * KX;
-  for (int idx = threadIdx.x; idx < B * KY; idx += kThreads) {
-    const int s = idx % B, kyb = idx / B;
-    if (kx0 + s >= KX) continue;
-    const int y = ((ky_start + kyb) % NY + NY) % NY;
-    float2 v = r[s * STRIDE + pad_idx(y)];
-    if (weight) {
-      const float wgt = __ldg(weight + (long)kyb * KX + kx0 + s);
-      v.x *= wgt;
-      v.y *= wgt;
+  for (int r = 0; r < R; ++r) {
+    for (int idx = threadIdx.x; idx < B * NS; idx += kThreads) {
+      const int s = idx % B, m_ = idx / B;
+      const int y = R * m_ + r;
+      float2 z = make_float2(0.f, 0.f);
+      if (y >= ylo && y < yhi && kx0 + s < KX) z = src[(long)y * KX + kx0 + s];
+      a[s * STRIDE + pad_idx(m_)] = z;
     }
-    dst[(long)kyb * KX + kx0 + s] = v;
+    __syncthreads();
+    const float2* res = dft_smem<MY, BLU>(a, b, plan);
+    for (int idx = threadIdx.x; idx < B * KY; idx += kThreads) {
+      const int s = idx % B, kyb = idx / B;
+      if (kx0 + s >= KX) continue;
+      const int ky = ky_start + kyb;
+      const int pos = ((ky % NS) + NS) % NS;
+      float2 v = res[s * STRIDE + pad_idx(pos)];
+      if (R > 1) {
+        v = cmul(v, twiddle_n((long)r * ky, NY));
+        if (r > 0) v = cadd(v, acc[idx]);
+        acc[idx] = v;
+        if (r + 1 < R) continue;
+      }
+      if (weight) {
+        const float wgt = __ldg(weight + (long)kyb * KX + kx0 + s);
+        v.x *= wgt;
+        v.y *= wgt;
+      }
+      dst[(long)kyb * KX + kx0 + s] = v;
+    }
+    __syncthreads();
   }
 }
 
@@ -347,47 +408,62 @@ cols_inverse_kernel(const float2* __restrict__ in, int KX, int KY, int ky_start,
                     float2* __restrict__ tmp) {
   constexpr int B = batch_for(MY);
   constexpr int STRIDE = padded_len(MY);
-  const int NY = BLU ? plan.n : MY;
+  const int NS = BLU ? plan.n : MY;
+  const int R = plan.R, NY = plan.n_total;
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B * STRIDE;
   const long item = blockIdx.y;
   const int kx0 = blockIdx.x * B;
-  for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
-  __syncthreads();
   const float2* src = in + item * KY * KX;
-  for (int idx = threadIdx.x; idx < B * KY; idx += kThreads) {
-    const int s = idx % B, kyb = idx / B;
-    if (kx0 + s >= KX) continue;
-    const float2 v = src[(long)kyb * KX + kx0 + s];
-    const int y = ((ky_start + kyb) % NY + NY) % NY;
-    a[s * STRIDE + pad_idx(y)] = make_float2(v.y, v.x);  // re/im swap: inverse via forward
-  }
-  __syncthreads();
-  const float2* r = dft_smem<MY, BLU>(a, b, plan);
   float2* dst = tmp + item * NY * KX;
-  for (int idx = threadIdx.x; idx < B * NY; idx += kThreads) {
-    const int s = idx % B, y = idx / B;
-    if (kx0 + s >= KX) continue;
-    const float2 v = r[s * STRIDE + pad_idx(y)];
-    dst[(long)y * KX + kx0 + s] = make_float2(v.y, v.x);
+  for (int r = 0; r < R; ++r) {
+    for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < B * KY; idx += kThreads) {
+      const int s = idx % B, kyb = idx / B;
+      if (kx0 + s >= KX) continue;
+      float2 v = src[(long)kyb * KX + kx0 + s];
+      const int ky = ky_start + kyb;
+      if (R > 1) v = cmul(v, twiddle_n(-(long)r * ky, NY));  // x[R m + r] = IDFT_n'(X[k] W^{-r k})[m]
+      const int pos = ((ky % NS) + NS) % NS;                 // the band spans <= n' bins: no two ky share a position
+      a[s * STRIDE + pad_idx(pos)] = make_float2(v.y, v.x);  // re/im swap: inverse via forward
+    }
+    __syncthreads();
+    const float2* res = dft_smem<MY, BLU>(a, b, plan);
+    for (int idx = threadIdx.x; idx < B * NS; idx += kThreads) {
+      const int s = idx % B, m_ = idx / B;
+      if (kx0 + s >= KX) continue;
+      const float2 v = res[s * STRIDE + pad_idx(m_)];
+      dst[(long)(R * m_ + r) * KX + kx0 + s] = make_float2(v.y, v.x);
+    }
+    __syncthreads();
   }
 }
 
 // ---- inverse: row pass (complex-to-real, two rows per transform) ------------------------------
 
-// builds the packed spectrum of rows ya (real part) and yb (imaginary part) in `a`, re/im swapped
+// builds the packed spectrum of rows ya (real part) and yb (imaginary part) in `a`, re/im swapped; for a decimated axis
+// (R > 1) the spectrum of sub-sequence r: entries times W^{-/+ r k}, aliased onto k mod NS
 __device__ __forceinline__ void load_c2r_pair(const float2* __restrict__ rowa, const float2* __restrict__ rowb, int KX,
-                                              int NX, float2* __restrict__ a_seq) {
+                                              int NX, int NS, int R, int r, float2* __restrict__ a_seq) {
   for (int k = threadIdx.x; k < KX; k += kThreads) {
     float2 ca = rowa[k];
     float2 cb = rowb ? rowb[k] : make_float2(0.f, 0.f);
     if (k == 0 || 2 * k == NX) {  // c2r ignores the imaginary part of the DC / Nyquist bins
-      a_seq[pad_idx(k)] = make_float2(cb.x, ca.x);
+      const float sgn = (k != 0 && (r & 1)) ? -1.f : 1.f;  // W^{-r N/2} = (-1)^r
+      a_seq[pad_idx(k % NS)] = make_float2(sgn * cb.x, sgn * ca.x);
     } else {
       // Z[k] = Ca + i Cb ; Z[N-k] = conj(Ca) + i conj(Cb) ; stored swapped (im, re)
-      a_seq[pad_idx(k)] = make_float2(ca.y + cb.x, ca.x - cb.y);
-      a_seq[pad_idx(NX - k)] = make_float2(cb.x - ca.y, ca.x + cb.y);
+      float2 zp = make_float2(ca.x - cb.y, ca.y + cb.x), zn = make_float2(ca.x + cb.y, cb.x - ca.y);
+      if (R > 1) {
+        const float2 tw = twiddle_n(-(long)r * k, NX);
+        zp = cmul(zp, tw);
+        zn = cmul(zn, make_float2(tw.x, -tw.y));
+      }
+      const int kp = k % NS;
+      a_seq[pad_idx(kp)] = make_float2(zp.y, zp.x);
+      a_seq[pad_idx(kp == 0 ? 0 : NS - kp)] = make_float2(zn.y, zn.x);
     }
   }
 }
@@ -406,37 +482,42 @@ rows_inverse_argmax_kernel(const float2* __restrict__ tmp, int NY, int KX, AxisP
                            PeakCandidate* __restrict__ partial) {
   constexpr int B = batch_for(MX);
   constexpr int STRIDE = padded_len(MX);
-  const int NX = BLU ? plan.n : MX;
+  const int NS = BLU ? plan.n : MX;
+  const int R = plan.R, NX = plan.n_total;
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B * STRIDE;
   const long item = blockIdx.y;
   const int row0 = blockIdx.x * 2 * B;
   const float2* src = tmp + item * NY * KX;
-  for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
-  __syncthreads();
-  for (int s = 0; s < B; ++s) {
-    const int ya = row0 + 2 * s, yb = ya + 1;
-    if (ya < NY) load_c2r_pair(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, NX, a + s * STRIDE);
-  }
-  __syncthreads();
-  const float2* r = dft_smem<MX, BLU>(a, b, plan);
   float best = -INFINITY;
   int best_idx = 0x7fffffff;
-  for (int idx = threadIdx.x; idx < B * NX; idx += kThreads) {
-    const int s = idx / NX, x = idx % NX;
-    const int ya = row0 + 2 * s;
-    if (ya >= NY) continue;
-    const float2 v = r[s * STRIDE + pad_idx(x)];  // swapped: v.y = row ya, v.x = row ya+1
-    const int ia = ya * NX + x;
-    if (better(v.y, ia, best, best_idx)) {
-      best = v.y;
-      best_idx = ia;
+  for (int r = 0; r < R; ++r) {
+    for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
+    __syncthreads();
+    for (int s = 0; s < B; ++s) {
+      const int ya = row0 + 2 * s, yb = ya + 1;
+      if (ya < NY)
+        load_c2r_pair(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, NX, NS, R, r, a + s * STRIDE);
     }
-    if (ya + 1 < NY && better(v.x, ia + NX, best, best_idx)) {
-      best = v.x;
-      best_idx = ia + NX;
+    __syncthreads();
+    const float2* res = dft_smem<MX, BLU>(a, b, plan);
+    for (int idx = threadIdx.x; idx < B * NS; idx += kThreads) {
+      const int s = idx / NS, m_ = idx % NS;
+      const int ya = row0 + 2 * s;
+      if (ya >= NY) continue;
+      const float2 v = res[s * STRIDE + pad_idx(m_)];  // swapped: v.y = row ya, v.x = row ya+1
+      const int ia = ya * NX + R * m_ + r;
+      if (better(v.y, ia, best, best_idx)) {
+        best = v.y;
+        best_idx = ia;
+      }
+      if (ya + 1 < NY && better(v.x, ia + NX, best, best_idx)) {
+        best = v.x;
+        best_idx = ia + NX;
+      }
     }
+    __syncthreads();
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -474,29 +555,35 @@ rows_inverse_store_kernel(const float2* __restrict__ tmp, int NY, int KX, AxisPl
                           float* __restrict__ out) {
   constexpr int B = batch_for(MX);
   constexpr int STRIDE = padded_len(MX);
-  const int NX = BLU ? plan.n : MX;
+  const int NS = BLU ? plan.n : MX;
+  const int R = plan.R, NX = plan.n_total;
   extern __shared__ float2 smem[];
   float2* a = smem;
   float2* b = smem + B * STRIDE;
   const long item = blockIdx.y;
   const int row0 = blockIdx.x * 2 * B;
   const float2* src = tmp + item * NY * KX;
-  for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
-  __syncthreads();
-  for (int s = 0; s < B; ++s) {
-    const int ya = row0 + 2 * s, yb = ya + 1;
-    if (ya < NY) load_c2r_pair(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, NX, a + s * STRIDE);
-  }
-  __syncthreads();
-  const float2* r = dft_smem<MX, BLU>(a, b, plan);
   float* dst = out + item * NY * NX;
-  for (int idx = threadIdx.x; idx < B * NX; idx += kThreads) {
-    const int s = idx / NX, x = idx % NX;
-    const int ya = row0 + 2 * s;
-    if (ya >= NY) continue;
-    const float2 v = r[s * STRIDE + pad_idx(x)];
-    dst[(long)ya * NX + x] = v.y * scale;
-    if (ya + 1 < NY) dst[(long)(ya + 1) * NX + x] = v.x * scale;
+  for (int r = 0; r < R; ++r) {
+    for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
+    __syncthreads();
+    for (int s = 0; s < B; ++s) {
+      const int ya = row0 + 2 * s, yb = ya + 1;
+      if (ya < NY)
+        load_c2r_pair(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, NX, NS, R, r, a + s * STRIDE);
+    }
+    __syncthreads();
+    const float2* res = dft_smem<MX, BLU>(a, b, plan);
+    for (int idx = threadIdx.x; idx < B * NS; idx += kThreads) {
+      const int s = idx / NS, m_ = idx % NS;
+      const int ya = row0 + 2 * s;
+      if (ya >= NY) continue;
+      const float2 v = res[s * STRIDE + pad_idx(m_)];
+      const int x = R * m_ + r;
+      dst[(long)ya * NX + x] = v.y * scale;
+      if (ya + 1 < NY) dst[(long)(ya + 1) * NX + x] = v.x * scale;
+    }
+    __syncthreads();
   }
 }
 
@@ -630,8 +717,10 @@ struct BoolC {
 
 // calls f(IntC<M>{}, BoolC<BLU>{}) for the FFT size / algorithm that serves a length-n transform
 template <typename F>
-int dispatch_fft(int n, const char* who, F&& f) {
-  const int m = fft_size_for(n);
+int dispatch_fft(int n_total, const char* who, F&& f) {
+  const int R = decimation_for(n_total);
+  const int n = R > 0 ? n_total / R : n_total;
+  const int m = R > 0 ? fft_size_for(n) : 0;
   const bool blu = m != n;
   switch (m) {
 #define CASE(MM) \
@@ -642,7 +731,8 @@ int dispatch_fft(int n, const char* who, F&& f) {
     default:
       break;
   }
-  tmc_set_error("%s: transform length %d is not supported (powers of two up to 8192, any length up to 4096)", who, n);
+  tmc_set_error("%s: transform length %d is not supported (powers of two up to 8192, any length up to 4096, and "
+                "multiples by 2..8 of those for band-limited transforms)", who, n_total);
   return TMC_ERR_UNSUPPORTED;
 }
 
@@ -662,23 +752,33 @@ int enable_smem(K kernel, size_t bytes) {
 
 // ---- C ABI ---------------------------------------------------------------------------------------
 
-TMC_API int tmc_fft_supported_length(int n) { return fft_size_for(n) > 0 ? 1 : 0; }
+// 1: full transforms of this length are supported (a power of two up to 8192 or any length up to 4096);
+// 2: band-limited transforms only (the axis is decimated by 2..8 into supported lengths: any such n up to 32768);
+// 0: unsupported
+TMC_API int tmc_fft_supported_length(int n) {
+  if (fft_size_for(n) > 0) return 1;
+  return decimation_for(n) > 0 ? 2 : 0;
+}
 
 // complex64 elements of the plan buffer for a length-n transform (0: unsupported length)
-TMC_API long tmc_fft_plan_elems(int n) {
+TMC_API long tmc_fft_plan_elems(int n_total) {
+  const int R = decimation_for(n_total);
+  if (R == 0) return 0;
+  const int n = n_total / R;
   const int m = fft_size_for(n);
-  if (m == 0) return 0;
   return m == n ? (long)m : 2l * m + n;
 }
 
 // fills `plan` (tmc_fft_plan_elems(n) complex64): twiddles [+ Bluestein chirp and filter spectrum]
-TMC_API int tmc_fft_plan_init(int n, void* plan, cudaStream_t stream) {
+TMC_API int tmc_fft_plan_init(int n_total, void* plan, cudaStream_t stream) {
   TMC_CHECK_ARG(plan, "fft_plan_init: null pointer");
-  const int m = fft_size_for(n);
-  if (m == 0) {
-    tmc_set_error("fft_plan_init: transform length %d is not supported", n);
+  const int R = decimation_for(n_total);
+  if (R == 0) {
+    tmc_set_error("fft_plan_init: transform length %d is not supported", n_total);
     return TMC_ERR_UNSUPPORTED;
   }
+  const int n = n_total / R;  // the plan serves the shared-memory transforms of the decimated axis
+  const int m = fft_size_for(n);
   float2* tw = (float2*)plan;
   TMC_TIMED("twiddle_kernel", stream, twiddle_kernel<<<tmc_div_up(m, 128), 128, 0, stream>>>(m, tw));
   if (m != n) {
@@ -691,6 +791,8 @@ TMC_API int tmc_fft_plan_init(int n, void* plan, cudaStream_t stream) {
     p.chirp = nullptr;
     p.bhat = nullptr;
     p.n = m;
+    p.R = 1;
+    p.n_total = m;
     int rc = dispatch_fft(m, "fft_plan_init", [&](auto M, auto) {
       constexpr int MM = decltype(M)::value;
       if (int e = enable_smem(c2c_rows_kernel<MM, false>, fft_smem_bytes<MM>())) return e;
@@ -706,6 +808,7 @@ TMC_API int tmc_fft_plan_init(int n, void* plan, cudaStream_t stream) {
 // out[r] = DFT_n(in[r]) (inverse != 0: unnormalised inverse) for `rows` complex64 rows; in may equal out
 TMC_API int tmc_fft_c2c_rows(const void* in, int rows, int n, const void* plan, void* out, cudaStream_t stream) {
   TMC_CHECK_ARG(in && out && plan && rows >= 1, "fft_c2c_rows: bad arguments");
+  TMC_CHECK_ARG(fft_size_for(n) > 0, "fft_c2c_rows: full transforms need lengths up to 4096 or powers of two up to 8192, got %d", n);
   AxisPlan p = make_axis_plan(plan, n);
   int rc = dispatch_fft(n, "fft_c2c_rows", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
@@ -748,7 +851,7 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
     constexpr bool BB = decltype(BLU)::value;
     if constexpr (MM == 1024 && !BB) {
       // polyphase path: four 256-point warp-level FFTs per row, only the band is ever formed
-      if (yhi > ylo && kx_count <= 128 && job_mode != 0 && use_poly()) {
+      if (yhi > ylo && kx_count <= 128 && job_mode != 0 && use_poly() && px.R == 1) {
         int rows_per_cta = 32;
         while (rows_per_cta > 8 && (long)tmc_div_up(yhi - ylo, rows_per_cta) * njobs < 148 * 6) rows_per_cta -= 8;
         dim3 grid(tmc_div_up(yhi - ylo, rows_per_cta), njobs);
@@ -768,7 +871,7 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
         return TMC_OK;
       }
     }
-    if constexpr (use_fast_path<MM, BB>()) {
+    if constexpr (use_fast_path<MM, BB>()) if (px.R == 1) {
       if (yhi > ylo) {
         constexpr int B = fft2::Cfg<MM>::B;
         // enough CTAs to fill the chip a few times over, each amortising its twiddle-table load
@@ -791,10 +894,17 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
       }
       return TMC_OK;
     }
-    if (int e = enable_smem(rows_forward_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
+    // generic kernel (Bluestein lengths, small transforms, decimated long axes); the accumulators of a decimated axis
+    // follow the two transform buffers
+    const size_t smem = fft_smem_bytes<MM>() + (px.R > 1 ? 2ull * batch_for(MM) * kx_count * sizeof(float2) : 0);
+    if (smem > 200 * 1024) {
+      tmc_set_error("rfft2_band: band of %d bins too wide for the decimated row transform of length %d", kx_count, nx);
+      return TMC_ERR_UNSUPPORTED;
+    }
+    if (int e = enable_smem(rows_forward_kernel<MM, BB>, smem)) return e;
     dim3 grid(tmc_div_up(yhi - ylo, batch_for(MM)), njobs);
     if (yhi > ylo) {
-      TMC_TIMED("rows_forward_kernel", stream, rows_forward_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>(
+      TMC_TIMED("rows_forward_kernel", stream, rows_forward_kernel<MM, BB><<<grid, kThreads, smem, stream>>>(
           image, h, w, mean_std, mask, jobs, frame_shifts, x_margin, ylo, yhi, ny, kx_count, px, (float2*)tmp));
     }
     return TMC_OK;
@@ -804,17 +914,22 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
   rc = dispatch_fft(ny, "rfft2_band", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
-    if constexpr (use_fast_path<MM, BB>()) {
+    if constexpr (use_fast_path<MM, BB>()) if (py.R == 1) {
       if (int e = enable_smem(cols_forward_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
       dim3 grid(tmc_div_up(kx_count, fft2::Cfg<MM>::B), 2 * njobs);
       TMC_TIMED(sized_label<MM>("cols_forward_p2<4096>", "cols_forward_p2<1024>", "cols_forward_p2"), stream, cols_forward_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
           (const float2*)tmp, ylo, yhi, kx_count, ky_count, ky_start, weight, py.tw, (float2*)out));
       return TMC_OK;
     }
-    if (int e = enable_smem(cols_forward_kernel<MM, BB>, fft_smem_bytes<MM>())) return e;
+    const size_t smem = fft_smem_bytes<MM>() + (py.R > 1 ? 1ull * batch_for(MM) * ky_count * sizeof(float2) : 0);
+    if (smem > 200 * 1024) {
+      tmc_set_error("rfft2_band: band of %d bins too wide for the decimated column transform of length %d", ky_count, ny);
+      return TMC_ERR_UNSUPPORTED;
+    }
+    if (int e = enable_smem(cols_forward_kernel<MM, BB>, smem)) return e;
     dim3 grid(tmc_div_up(kx_count, batch_for(MM)), 2 * njobs);
-    TMC_TIMED("cols_forward_kernel", stream, cols_forward_kernel<MM, BB><<<grid, kThreads, fft_smem_bytes<MM>(), stream>>>((const float2*)tmp, ylo, yhi, kx_count, ky_count,
-                                                                                 ky_start, weight, py, (float2*)out));
+    TMC_TIMED("cols_forward_kernel", stream, cols_forward_kernel<MM, BB><<<grid, kThreads, smem, stream>>>(
+                  (const float2*)tmp, ylo, yhi, kx_count, ky_count, ky_start, weight, py, (float2*)out));
     return TMC_OK;
   });
   if (rc) return rc;
@@ -873,9 +988,10 @@ TMC_API int tmc_xc_leave_one_out_products(const void* spec, int t, int g, long p
 }
 
 TMC_API int tmc_xc_peak_partials(int ny, int nx) {
-  const int m = fft_size_for(nx);
-  if (m == 0) return -1;
-  if (m == nx && m >= 256) {  // power-of-two fast path: several row-pair batches per CTA
+  const int R = decimation_for(nx);
+  if (R == 0) return -1;
+  const int m = fft_size_for(nx / R);
+  if (R == 1 && m == nx && m >= 256) {  // power-of-two fast path: several row-pair batches per CTA
     const int b = 256 / (m / 16) > 0 ? 256 / (m / 16) : 1;
     return tmc_div_up(ny, 2 * b * kRowIters);
   }
@@ -892,10 +1008,15 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
   TMC_CHECK_ARG(kx_count >= 1 && kx_count <= nx / 2 + 1 && ky_count >= 1 && ky_count <= ny, "xc_peaks: bad band box");
   if (nitems == 0) return TMC_OK;
   const AxisPlan px = make_axis_plan(plan_x, nx), py = make_axis_plan(plan_y, ny);
+  // decimated (long) axes invert band-limited input only: the band must not alias onto itself
+  TMC_CHECK_ARG(py.R == 1 || ky_count <= py.n, "xc_peaks: band of %d rows too wide for the decimated column transform of length %d",
+                ky_count, ny);
+  TMC_CHECK_ARG(px.R == 1 || 2 * kx_count - 1 <= px.n, "xc_peaks: band of %d columns too wide for the decimated row transform of length %d",
+                kx_count, nx);
   int rc = dispatch_fft(ny, "xc_peaks", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
-    if constexpr (use_fast_path<MM, BB>()) {
+    if constexpr (use_fast_path<MM, BB>()) if (py.R == 1) {
       if (int e = enable_smem(cols_inverse_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
       dim3 grid(tmc_div_up(kx_count, fft2::Cfg<MM>::B), nitems);
       TMC_TIMED(sized_label<MM>("cols_inverse_p2<4096>", "cols_inverse_p2<1024>", "cols_inverse_p2"), stream, cols_inverse_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>(
@@ -915,7 +1036,7 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
     if constexpr (MM == 1024 && !BB) {
-      if (kx_count <= 128 && use_poly()) {
+      if (kx_count <= 128 && use_poly() && px.R == 1) {
         if (int e = enable_smem(poly::rows_inverse_argmax_poly, poly::smem_bytes)) return e;
         dim3 grid(nparts, nitems);
         TMC_TIMED("rows_inverse_argmax_poly", stream, poly::rows_inverse_argmax_poly<<<grid, poly::kThreads, poly::smem_bytes, stream>>>((const float2*)tmp, ny, kx_count, px.tw,
@@ -923,7 +1044,7 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
         return TMC_OK;
       }
     }
-    if constexpr (use_fast_path<MM, BB>()) {
+    if constexpr (use_fast_path<MM, BB>()) if (px.R == 1) {
       if (int e = enable_smem(rows_inverse_argmax_p2<MM>, rows_inverse_smem_bytes<MM>())) return e;
       dim3 grid(nparts, nitems);
       TMC_TIMED(sized_label<MM>("rows_inverse_argmax_p2<4096>", "rows_inverse_argmax_p2<1024>", "rows_inverse_argmax_p2"), stream, rows_inverse_argmax_p2<MM><<<grid, fft2::kThreads, rows_inverse_smem_bytes<MM>(), stream>>>(
@@ -951,6 +1072,10 @@ TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const 
   if (nitems == 0) return TMC_OK;
   const int kx = nx / 2 + 1;
   const AxisPlan px = make_axis_plan(plan_x, nx), py = make_axis_plan(plan_y, ny);
+  if (px.R != 1 || py.R != 1) {
+    tmc_set_error("irfft2_full: full transforms need lengths up to 4096 or powers of two up to 8192, got (%d, %d)", ny, nx);
+    return TMC_ERR_UNSUPPORTED;
+  }
   int rc = dispatch_fft(ny, "irfft2_full", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
