@@ -811,3 +811,37 @@ def prepare_movie(movie: np.ndarray, gain: np.ndarray | None = None, hot_pixel_t
     if zero_frame_means:
         out = out - np.mean(out, axis=(1, 2), keepdims=True, dtype=np.float64).astype(np.float32)
     return out, n_hot
+
+
+# --------------------------------------------------------------------------------------
+# iterative refinement driver   (examples/ttMotion.py:287-329 -- example code, sketched there)
+# --------------------------------------------------------------------------------------
+
+
+def estimate_motion_pipeline(image, pixel_spacing: float, patch_sidelength: int, frequency_range=(300, 10), b_factor: float = 500,
+                             n_refinements: int = 0, refinement_tolerance: float = 1e-3, smoothing_window_size: int = 5):
+    """The B200 build's ``estimate_motion`` restated with the functions above: global estimate (whole pixels) -> patch
+    cross-correlation on the rigidly pre-shifted movie (global / pixel_spacing handed over as the reference's
+    correct_motion_fast route wants pixels, quirk Q2) WITHOUT smoothing -> the base it accumulated on swapped for the
+    true global field -> Savitzky-Golay + one joint mean; then up to ``n_refinements`` passes of the example's loop
+    (``deformation_field=`` the cumulative field of the pass before) until the mean absolute change drops below the
+    tolerance.  Returns ``(field, [mean absolute change per pass])``."""
+    g = estimate_global_motion(image, pixel_spacing, b_factor=b_factor, frequency_range=frequency_range)
+    pre = g / pixel_spacing
+    handed = pre.clone()
+    f, _ = estimate_motion_cross_correlation_patches(image, pixel_spacing, patch_sidelength=patch_sidelength, b_factor=b_factor,
+                                                     frequency_range=frequency_range, deformation_field=pre, smooth=False)
+    shape = f.shape[1:]
+    field = f - resample_deformation_field(-handed, shape) + resample_deformation_field(g, shape)
+    field = temporal_smoothing(field, smoothing_window_size)
+    field = field - field.mean()
+    history = []
+    for _ in range(n_refinements):
+        refined, _ = estimate_motion_cross_correlation_patches(image, pixel_spacing, patch_sidelength=patch_sidelength,
+                                                               b_factor=b_factor, frequency_range=frequency_range,
+                                                               deformation_field=field.clone())
+        history.append(float((refined - field).abs().mean()))
+        field = refined
+        if history[-1] < refinement_tolerance:
+            break
+    return field, history

@@ -135,3 +135,35 @@ def test_pipeline_composes_global_and_patch_fields_before_smoothing(dev):
     got = field.mean(dim=(2, 3)).cpu()
     got = got - got.mean(dim=1, keepdim=True)
     assert float((got - truth).abs().max()) / px <= 0.5
+
+
+def test_iterative_refinement_matches_the_oracle(dev):
+    """estimate_motion(n_refinements=...) -- the example's loop (examples/ttMotion.py:287-329) -- pass by pass against the
+    oracle's restatement, early stop included."""
+    px, fr = 1.3, (120.0, 6.0)
+    movie, _ = rp.synthetic_movie(8, 160, 160, seed=23, noise=0.4, drift=3.0, local=1.0, sigma_f=0.07)
+    want, want_hist = rp.estimate_motion_pipeline(movie, px, 32, frequency_range=fr, n_refinements=3, refinement_tolerance=1e-3)
+    got, _, hist = tmc.estimate_motion(movie.to(dev), px, patch_sidelength=32, frequency_range=fr, n_refinements=3,
+                                       refinement_tolerance=1e-3, return_history=True)
+    assert len(hist) == len(want_hist) >= 1
+    assert float((got.cpu() - want).abs().max()) <= 0.01 * px
+    assert np.allclose(hist, want_hist, atol=2e-3 * px)
+    # a loose tolerance stops after the first pass
+    _, _, hist1 = tmc.estimate_motion(movie.to(dev), px, patch_sidelength=32, frequency_range=fr, n_refinements=3,
+                                      refinement_tolerance=1e3, return_history=True)
+    assert len(hist1) == 1
+
+
+@pytest.mark.parametrize("values", [[2.0, -1.0, 0.0, 3.0, -6.0, 1.0], [2.5, -1.0, 0.0, 3.0, -6.0, 1.0]])
+def test_quirk_q2_reaches_a_cpu_callers_tensor(dev, values):
+    """correct_motion_fast negates the caller's field in place (quirk Q2): also when the caller's tensor lives on the host
+    and had to be copied to the device -- whole-pixel (shifted windows) and fractional (Fourier shift) routes."""
+    movie, _ = rp.synthetic_movie(6, 128, 128, seed=17, noise=0.5, drift=3.0, integer_shifts=True, sigma_f=0.07)
+    field = torch.tensor([values, values[::-1]]).reshape(2, 6, 1, 1)
+    keep = field.clone()
+    tmc.estimate_motion_cross_correlation_patches(movie.to(dev), 1.3, patch_sidelength=32, frequency_range=(120.0, 6.0),
+                                                  deformation_field=field)
+    assert torch.equal(field, -keep)
+    field = keep.clone()
+    tmc.correct_motion_fast(movie.to(dev), field)
+    assert torch.equal(field, -keep)

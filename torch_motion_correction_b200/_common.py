@@ -45,7 +45,12 @@ def grid_kind(grid_type: str) -> int:
         raise ValueError(f"Invalid grid type: {grid_type}. Must be 'catmull_rom' or 'bspline'.") from None
 
 
-_device_cache: dict = {}
+import collections
+import threading
+
+_device_cache: "collections.OrderedDict" = collections.OrderedDict()
+_device_cache_lock = threading.Lock()
+_DEVICE_CACHE_ENTRIES = 256
 
 
 def cached_device_tensor(key, build, device: torch.device) -> torch.Tensor:
@@ -53,16 +58,20 @@ def cached_device_tensor(key, build, device: torch.device) -> torch.Tensor:
     geometry: build them once per device and geometry instead of paying a host-blocking pageable
     H2D copy in the middle of every call.  The tensors must be treated as read-only."""
     full_key = (device.type, device.index, key)
-    hit = _device_cache.get(full_key)
-    if hit is None:
-        if len(_device_cache) > 256:
-            _device_cache.clear()
-        hit = build().to(device)
+    with _device_cache_lock:
+        hit = _device_cache.get(full_key)
+        if hit is not None:
+            _device_cache.move_to_end(full_key)
+            return hit
+    hit = build().to(device)
+    with _device_cache_lock:
         _device_cache[full_key] = hit
+        while len(_device_cache) > _DEVICE_CACHE_ENTRIES:  # least recently used first; tensors in use stay alive
+            _device_cache.popitem(last=False)
     return hit
 
 
-_staging: dict = {}
+_staging_local = threading.local()  # one ring of pinned buffers per host thread and device
 _STAGING_SLOTS = 4
 
 
@@ -77,7 +86,10 @@ def to_device_async(host_tensor: torch.Tensor, device: torch.device) -> torch.Te
         staged.copy_(src)
         return staged.to(device, non_blocking=True)
     key = (device.type, device.index)
-    ring = _staging.setdefault(key, {"next": 0, "slots": [None] * _STAGING_SLOTS})
+    rings = getattr(_staging_local, "rings", None)
+    if rings is None:
+        rings = _staging_local.rings = {}
+    ring = rings.setdefault(key, {"next": 0, "slots": [None] * _STAGING_SLOTS})
     i = ring["next"]
     ring["next"] = (i + 1) % _STAGING_SLOTS
     slot = ring["slots"][i]

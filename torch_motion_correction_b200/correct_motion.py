@@ -74,7 +74,10 @@ def correct_motion_fast(
     movie = _movie(image, dev)
     t, h, w = movie.shape
     moved = deformation_grid.to(dev)
-    moved *= -1  # Q2: visible to the caller whenever .to() did not have to copy
+    moved *= -1  # Q2: the reference negates the caller's tensor in place ...
+    if moved.data_ptr() != deformation_grid.data_ptr():
+        with torch.no_grad():
+            deformation_grid.mul_(-1)  # ... also when .to() had to copy it to the device (CPU callers)
     field = moved.detach().to(torch.float32).contiguous()
     plan = _fourier.BandPlan(h, w, dev, full=True)
     if _fourier.query("tmc_fourier_shift_frames_supported", h, w):

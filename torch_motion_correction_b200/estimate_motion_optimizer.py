@@ -76,6 +76,7 @@ class LocalMotionProblem:
         t, h, w = movie.shape
         ph, pw = patch_shape
         self.t, self.ph, self.pw = t, ph, pw
+        self.geometry = (t, h, w, ph, pw)
         self.resolution = tuple(int(r) for r in resolution)
         if stats is None:
             stats = _ops.stack_stats(movie)
@@ -167,11 +168,14 @@ class LocalMotionProblem:
         self.sum_norms = self.norms[:, :, 0 if self.loss_type == 0 else 1].sum(dim=1).contiguous()
         # the patch centres are a product grid (frame) x (patch): the 64-tap spline weights factor into a dense
         # (T, nt) time matrix and a dense (G, nh nw) spatial matrix, phantom nodes folded in (spline of unit grids)
-        key = ("local_weights", self.kind, self.resolution, tuple(self.centres_norm.shape), self.centres_norm.data_ptr())
-        hit = _separable_weights.get(key)
+        # keyed by the geometry the centres are a function of (never by a device pointer); problems built from ad-hoc
+        # centres (frame-split patch shards) carry no geometry key and are not cached
+        geometry = getattr(self, "geometry", None)
+        key = ("local_weights", (dev.type, dev.index), self.kind, self.resolution, geometry) if geometry is not None else None
+        hit = _separable_weights.get(key) if key is not None else None
         if hit is None:
-            if len(_separable_weights) > 64:
-                _separable_weights.clear()
+            while len(_separable_weights) > 64:
+                _separable_weights.pop(next(iter(_separable_weights)))
             cn = self.centres_norm
             pts_t = torch.zeros((t, 3), dtype=torch.float32, device=dev)
             pts_t[:, 0] = cn[:, 0, 0]
@@ -179,9 +183,9 @@ class LocalMotionProblem:
             pts_s[:, 0] = 0.0
             eye_t = torch.eye(nt, dtype=torch.float32, device=dev).reshape(nt, nt, 1, 1).contiguous()
             eye_s = torch.eye(nh * nw, dtype=torch.float32, device=dev).reshape(nh * nw, 1, nh, nw).contiguous()
-            hit = (_ops.spline_eval(eye_t, self.kind, pts_t).contiguous(), _ops.spline_eval(eye_s, self.kind, pts_s).contiguous(),
-                   cn)  # keep cn alive: its data_ptr is part of the key
-            _separable_weights[key] = hit
+            hit = (_ops.spline_eval(eye_t, self.kind, pts_t).contiguous(), _ops.spline_eval(eye_s, self.kind, pts_s).contiguous())
+            if key is not None:
+                _separable_weights[key] = hit
         self.w_t, self.w_sp = hit[0], hit[1]
         ws_bytes = query("tmc_local_steps_workspace_bytes", self.g, t, nt)
         self.step_ws = torch.empty(((ws_bytes + 7) // 8,), dtype=torch.float64, device=dev)

@@ -159,6 +159,7 @@ def estimate_motion_cross_correlation_patches(
     source, source_stats = movie, stats  # patches are read from here, normalised on load
     frame_shifts = None
     if deformation_field is not None:
+        callers_field = deformation_field
         deformation_field = deformation_field.to(dev)
         if tuple(deformation_field.shape[-2:]) == (1, 1):
             if deformation_field.shape[1] != t:
@@ -171,9 +172,15 @@ def estimate_motion_cross_correlation_patches(
             if whole:
                 frame_shifts = shifts
                 deformation_field *= -1  # quirk Q2: correct_motion_fast negates the caller's field in place
+                if deformation_field.data_ptr() != callers_field.data_ptr():
+                    with torch.no_grad():
+                        callers_field.mul_(-1)  # a CPU caller's tensor was copied to the device: negate the original too
             else:
                 source = correct_motion_fast(movie, deformation_field, device=dev, _mean_std=stats)
                 source_stats = None
+                if deformation_field.data_ptr() != callers_field.data_ptr():
+                    with torch.no_grad():
+                        callers_field.mul_(-1)  # quirk Q2 for a CPU caller's tensor (negated on the device copy above)
         else:
             source = correct_motion(movie, deformation_field, pixel_spacing, grid_type="bspline", device=dev, _mean_std=stats)
             source_stats = None

@@ -58,10 +58,19 @@ def estimate_motion(
     dose_per_frame: float | None = None,
     pre_exposure: float = 0.0,
     voltage: float = 300.0,
+    n_refinements: int = 0,
+    refinement_tolerance: float = 1e-3,
+    return_history: bool = False,
 ):
-    """Returns ``(field (2, nt, nh, nw) Angstrom, patch_centres)``.
+    """Returns ``(field (2, nt, nh, nw) Angstrom, patch_centres)`` (and the refinement history with ``return_history``).
 
     ``dose_per_frame`` switches on the exposure pre-filter of the patch cross-correlation.
+
+    ``n_refinements > 0``: the iterative refinement the reference sketches in ``examples/ttMotion.py:287-329`` -- up to
+    that many further passes of the patch cross-correlation, each on the movie pre-corrected with the cumulative field
+    of the pass before (``deformation_field=`` route: B-spline warp, residual shifts accumulated on the field, smoothed).
+    It stops early when the mean absolute change of the field drops below ``refinement_tolerance`` Angstrom (the
+    criterion the example prints and leaves commented out, ``:311-316``; one host synchronisation per pass).
 
     With ``n_iterations > 0`` the patch-XC field initialises ``estimate_local_motion`` on a
     ``deformation_field_resolution`` spline grid (default (3, 5, 5), BASELINE config 2)."""
@@ -83,6 +92,18 @@ def estimate_motion(
             _whole_pixel_field=True,  # estimate_global_motion returns whole pixels (quirk Q5): no pre-correction pass, no sync
         ),
     )
+    history = []
+    for _ in range(int(n_refinements)):
+        refined, _ = estimate_motion_cross_correlation_patches(
+            image, pixel_spacing, b_factor=b_factor, frequency_range=frequency_range, patch_sidelength=patch_sidelength,
+            deformation_field=field.clone(), device=device, dose_per_frame=dose_per_frame, pre_exposure=pre_exposure,
+            voltage=voltage, _stats=stats,
+        )
+        change = float((refined - field).abs().mean())
+        history.append(change)
+        field = refined
+        if change < refinement_tolerance:
+            break
     if n_iterations > 0:
         from .estimate_motion_optimizer import estimate_local_motion
 
@@ -92,6 +113,8 @@ def estimate_motion(
             n_iterations=n_iterations, b_factor=b_factor, frequency_range=frequency_range, grid_type=grid_type,
             optimizer_kwargs=optimizer_kwargs, _stats=stats,
         )
+    if return_history:
+        return field, centres, history
     return field, centres
 
 
