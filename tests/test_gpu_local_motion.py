@@ -67,9 +67,10 @@ def test_estimate_local_motion_golden(dev, small, name):
     )
     assert res.shape == (2, 3, 3, 3)
     want = torch.as_tensor(g[f"local_{name}"])
-    # L-BFGS with a strong-Wolfe line search amplifies fp32 rounding of loss/gradient (different
-    # summation order than autograd); it still lands within 0.03 px after six iterations
-    tol = (0.03 if "lbfgs" in name else SHIFT_PX) * px
+    # north-star tolerance for every optimiser.  (L-BFGS with a strong-Wolfe line search amplifies the ~1e-6 relative
+    # differences of loss and gradient -- different summation order than autograd; tools/lbfgs_check.py: the default
+    # kernels land 6e-4 px from the reference after six iterations, the fp64 oracle 3e-4 px from the fp32 one.)
+    tol = SHIFT_PX * px
     assert float((res.cpu() - want).abs().max()) <= tol, float((res.cpu() - want).abs().max())
     losses = np.asarray([c.loss for c in traj.checkpoints])
     assert np.allclose(losses, g[f"local_{name}_losses"], rtol=2e-3, atol=1e-6), (losses, g[f"local_{name}_losses"])
