@@ -527,6 +527,21 @@ def main():
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e_ms)
 
+    # the ceiling of that number: the bare pinned-host -> device copy of the movie, all ranks at once (no compute at all)
+    sink = torch.empty(host.shape, dtype=torch.float32, device=dev)
+    sink.copy_(host, non_blocking=True)
+    barrier()
+    s2.record()
+    for _ in range(3):
+        sink.copy_(host, non_blocking=True)
+    e2.record()
+    barrier()
+    c_ms = torch.tensor([s2.elapsed_time(e2) / 3], device=dev)
+    if world > 1:
+        dist.all_reduce(c_ms, op=dist.ReduceOp.MAX)
+    h2d_ms = float(c_ms)
+    del sink
+
     # the same with the movie held as uint16 detector counts on the host (K3 / Falcon movies are integer counts): half the
     # PCIe bytes, converted to fp32 on the device (additional record; the fp32 number above stays the headline)
     host16 = torch.empty(host.shape, dtype=torch.uint16, pin_memory=True)
@@ -675,6 +690,9 @@ def main():
             "value": movies / (e2e_ms * 1e-3), "unit": "movies/s", "ms_per_step": e2e_ms / args.steps,
             # whole job: every rank copies its own movie in and its frame sum out each step
             "h2d_bytes_per_step": host.numel() * 4 * world, "d2h_bytes_per_step": cfg["h"] * cfg["w"] * 4 * world,
+            # machine ceiling: the bare host -> device copy of one movie per rank, all ranks copying at once
+            "h2d_copy_only_ms_per_step": h2d_ms, "h2d_ceiling_gbs": host.numel() * 4 * world / (h2d_ms * 1e-3) / 1e9,
+            "fraction_of_h2d_ceiling": h2d_ms / (e2e_ms / args.steps),
         },
         "e2e_uint16": {
             "value": movies / (e2e16_ms * 1e-3), "unit": "movies/s", "ms_per_step": e2e16_ms / args.steps,
