@@ -10,8 +10,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
 i=0
 for k in 'local_loss_tile_kernel' 'local_coefficient_kernel' 'rows_forward_poly<.int.1' 'rows_forward_poly<.int.2' 'cols_forward_p2<.int.1024>' \
          'rows_inverse_argmax_poly' 'cols_inverse_p2<.int.1024>' 'rows_forward_p2<.int.4096' 'cols_forward_p2<.int.4096>' \
-         'cols_inverse_p2<.int.4096>' 'rows_inverse_argmax_p2<.int.4096>' 'rows_inverse_store_p2<.int.4096>' 'cols_shift_quad_p2<.int.4096>' \
-         'warp_lattice_kernel' 'xc_leave_one_out_kernel' 'stats_partial_kernel'; do
+         'cols_inverse_p2<.int.4096>' 'rows_inverse_argmax_p2<.int.4096>' \
+         'warp_tma_kernel' 'lattice_xinterp_kernel' 'xc_leave_one_out_kernel' 'stats_partial_kernel'; do
   i=$((i+1))
   ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base demangled \
       -k regex:"$k" -c 1 -o gpurun_out/prof_${tag}_$i python tools/profile_step.py --iterations 3 > gpurun_out/ncu_$i.log 2>&1

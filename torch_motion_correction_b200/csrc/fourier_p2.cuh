@@ -24,8 +24,10 @@ constexpr size_t rows_forward_smem_bytes() {
   return fft2::Cfg<N>::smem_bytes + 3ull * fft2::Cfg<N>::B * N * sizeof(float);
 }
 
+// 4096-point rows: uncapped the kernel takes 217 registers (1 CTA per SM, 12 % occupancy); at 128 registers two CTAs are
+// resident and the whole-frame estimate is 0.4 ms faster (measured, C2)
 template <int N, int MODE>
-__global__ void __launch_bounds__(fft2::kThreads)
+__global__ void __launch_bounds__(fft2::kThreads, N == 4096 ? 2 : 1)
 rows_forward_p2(const float* __restrict__ image, int H, int W, const float* __restrict__ mean_std,
                 const float* __restrict__ mask, const int* __restrict__ jobs, const int* __restrict__ frame_shifts,
                 int x_margin, int ylo, int yhi, int NY, int KX, const float2* __restrict__ tw, float2* __restrict__ tmp,
@@ -317,7 +319,7 @@ __device__ __forceinline__ void rows_inverse_driver(const float2* __restrict__ s
 
 // ---- inverse rows + argmax: tmp[item][y][kx] -> partial[item][cta] ------------------------------------
 template <int N>
-__global__ void __launch_bounds__(fft2::kThreads)
+__global__ void __launch_bounds__(fft2::kThreads, N == 4096 ? 3 : 1)
 rows_inverse_argmax_p2(const float2* __restrict__ tmp, int NY, int KX, const float2* __restrict__ tw,
                        PeakCandidate* __restrict__ partial) {
   using P = fft2::Plan<N>;
