@@ -222,7 +222,11 @@ __device__ __forceinline__ Window make_window(const float* image, int frame, int
   const bool cols_masked = w.ox >= -x_margin && w.ox + NX <= W + x_margin;
   // plain reads of the first / last frame row with columns beyond the row would leave the movie buffer
   const bool buffer_end = (w.oy + ylo == 0 && w.ox < 0) || (w.oy + yhi == H && w.ox + NX > W);
+#ifdef TMC_NO_WRAP
+  w.wrap = false;
+#else
   w.wrap = !(rows_inside && (cols_inside || (cols_masked && !buffer_end)));
+#endif
   return w;
 }
 
