@@ -39,6 +39,12 @@ WORKLOADS = {
 }
 
 
+def workload_text(name, cfg, iterations):
+    """The workload both arms (ours and --impl reference) name in `config.workload`."""
+    return (f"{name}: {cfg['t']}x{cfg['h']}x{cfg['w']} fp32 movie, whole-frame XC + patch XC ({cfg['patch']} px, 50% overlap) on the "
+            f"rigidly pre-corrected movie + {iterations}-iteration {cfg['resolution']} spline optimiser + warp-and-sum")
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -430,9 +436,8 @@ def main():
             "impl": "reference", "metric": "movies_per_second_estimate_plus_correct", "value": base["value"], "unit": "movies/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {cfg['t']}x{cfg['h']}x{cfg['w']} fp32 movie, whole-frame XC + rigid pre-correction + "
-                                   f"patch XC ({cfg['patch']} px) + {ref_iterations}-iteration {cfg['resolution']} spline optimiser + warp-and-sum "
-                                   f"(CPU oracle port on a bounded sample)"},
+            "config": {"workload": workload_text(args.workload, cfg, ref_iterations), "pixel_spacing": cfg["pixel_spacing"],
+                       "arm": "CPU oracle port (the reference's algorithm op for op) on a bounded sample, see cpu_baseline.sample"},
             # ms_per_step is the measured wall time of one pass over the sample; value extrapolates it to whole movies
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "seconds_per_step",
                                                   "extrapolated_seconds_per_movie")},
@@ -683,9 +688,8 @@ def main():
         "dtype": "f32",
         "data": "synthetic",
         "config": {
-            "workload": f"{args.workload}: {cfg['t']}x{cfg['h']}x{cfg['w']} fp32 movie, whole-frame XC + patch XC ({p} px, 50% "
-                        f"overlap) on the whole-pixel pre-shifted windows + {iterations}-iteration {cfg['resolution']} spline "
-                        f"optimiser + fused warp-and-sum",
+            "workload": workload_text(args.workload, cfg, iterations),
+            "arm": "CUDA: the rigid pre-correction is served by whole-pixel shifted patch windows, the warp-and-sum is fused",
             "pixel_spacing": px, "movies_per_rank_per_step": 1, "sharding": "independent movies per rank, no collective",
             "l2_policy": "inputs (2.7 GB/movie) exceed L2 (126 MB); no explicit flush",
         },
