@@ -53,3 +53,40 @@ def test_frame_split_bookkeeping_world2(tmp_path, total_frames):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), total_frames, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def _reshard_worker(rank, world, port, t, g, out_dir):
+    """The frame-split optimiser's re-sharding: spectra computed where the frames live, (t_local, G, words), gathered to
+    (T, G, words) and cut into this rank's share of the patches with ALL frames."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        words = 5
+        full = torch.arange(t * g * words, dtype=torch.float32).reshape(t, g, words)
+        f0, f1 = frame_range(t, rank, world)
+        gathered = all_gather_frames(full[f0:f1].contiguous(), t)
+        assert torch.equal(gathered, full)
+        g0, g1 = frame_range(g, rank, world)
+        mine = gathered[:, g0:g1].permute(1, 0, 2).contiguous()  # (G_r, T, words)
+        assert mine.shape == (g1 - g0, t, words)
+        # every patch is owned by exactly one rank
+        owned = torch.zeros(g)
+        owned[g0:g1] = 1
+        dist.all_reduce(owned)
+        assert torch.equal(owned, torch.ones(g))
+        # the coefficient gradient is a sum over patches: partial sums all-reduce to the whole
+        part = mine.sum(dim=(0, 1))
+        dist.all_reduce(part)
+        assert torch.allclose(part, full.sum(dim=(0, 1)))
+        with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("t,g", [(7, 9), (10, 3)])
+def test_frame_split_patch_resharding_world2(tmp_path, t, g):
+    world = 2
+    mp.spawn(_reshard_worker, args=(world, _free_port(), t, g, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))

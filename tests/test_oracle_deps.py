@@ -122,3 +122,51 @@ def test_dose_weight_known_answers():
     a, b = torch.randn((t, h, w), generator=g), torch.randn((t, h, w), generator=g)
     lhs = rp.dose_weight(a + 2 * b, 1.1, 0.5, 1.0)
     assert torch.allclose(lhs, rp.dose_weight(a, 1.1, 0.5, 1.0) + 2 * rp.dose_weight(b, 1.1, 0.5, 1.0), atol=1e-4)
+
+
+# ---- movie preparation (examples/ttMotion.py:90-202 restated in oracle.reference_path.prepare_movie) ----
+
+
+def test_prepare_movie_restatement_follows_the_example():
+    import numpy as np
+
+    from oracle import reference_path as rp
+
+    rng = np.random.default_rng(7)
+    movie = rng.poisson(20.0, size=(3, 24, 31)).astype(np.uint16)
+    gain = (1.0 + 0.1 * rng.standard_normal((24, 31))).astype(np.float32)
+    # gain_correct (:123) and set_frames_mean_zero (:195-198), transliterated
+    want = movie.astype(np.float32) * gain
+    want = want - np.mean(want, axis=(1, 2), keepdims=True)
+    got, n_hot = rp.prepare_movie(movie, gain=gain, zero_frame_means=True)
+    assert n_hot == 0 and got.dtype == np.float32
+    assert np.allclose(got, want, atol=1e-5)
+    # remove_hot_pixels (:141-176): the mask is the reference's, the replacement one of the neighbours
+    movie[1, 10, 12] = 4000
+    movie[2, 0, 0] = 3000
+    f32 = movie.astype(np.float32)
+    got, n_hot = rp.prepare_movie(movie, hot_pixel_threshold=10.0)
+    hot = np.zeros_like(f32, dtype=bool)
+    for f in range(3):
+        m, s = f32[f].mean(), f32[f].std()
+        hot[f] = (f32[f] > m + 10.0 * s) | (f32[f] < m - 10.0 * s)
+    assert n_hot == int(hot.sum()) == 2
+    assert np.array_equal(got[~hot], f32[~hot])
+    assert got[1, 10, 12] in f32[1, 9:12, 11:14] and got[1, 10, 12] != 4000
+    assert got[2, 0, 0] in (f32[2, 0, 1], f32[2, 1, 0], f32[2, 1, 1])
+    # reproducible
+    again, _ = rp.prepare_movie(movie, hot_pixel_threshold=10.0)
+    assert np.array_equal(got, again)
+
+
+def test_estimate_motion_pipeline_restatement_composes_before_smoothing():
+    """global + patch residuals, smoothed after the composition, then the example's refinement loop: shapes, the joint
+    mean (quirk Q4) and the early stop."""
+    from oracle import reference_path as rp
+
+    movie, _ = rp.synthetic_movie(6, 96, 96, seed=4, noise=0.4, drift=2.0, local=0.5, sigma_f=0.07)
+    field, hist = rp.estimate_motion_pipeline(movie, 1.2, 32, frequency_range=(100, 5), n_refinements=2, refinement_tolerance=1e9)
+    assert field.shape[0] == 2 and field.shape[1] == 6 and len(hist) == 1
+    assert abs(float(field.mean())) < 1e-5
+    field0, hist0 = rp.estimate_motion_pipeline(movie, 1.2, 32, frequency_range=(100, 5))
+    assert hist0 == [] and abs(float(field0.mean())) < 1e-5
