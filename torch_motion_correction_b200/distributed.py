@@ -157,12 +157,18 @@ def estimate_patch_motion_frame_split(local_frames, pixel_spacing, frame_offset,
         field = torch.zeros((2, t, gh, gw), dtype=torch.float32, device=dev)
     else:
         field = resample_deformation_field(deformation_field, (t, gh, gw))
-    jobs = torch.tensor([[k, 1, k, 2, y0, x0] for k in range(t_local) for (y0, x0) in origins], dtype=torch.int32).to(dev)
+    # planning tensors are pure functions of the geometry: built once per device (no host-blocking copies per call)
+    jobs = cached_device_tensor(
+        ("split_xc_jobs", (t_local, h, w, p)),
+        lambda: torch.tensor([[k, 1, k, 2, y0, x0] for k in range(t_local) for (y0, x0) in origins], dtype=torch.int32), dev)
     spec_local = plan.forward(source, source_stats, mask, ylo, yhi, jobs, job_mode=1, frame_shifts=frame_shifts).view(t_local, g * 2 * plan.plane_elems * 2)
     spec_all = all_gather_frames(spec_local, t, group)
-    offsets, deltas = _aliasing_schedule(t, "mean_except_current", t // 2)
-    d_off = torch.tensor(offsets, dtype=torch.int32).to(dev)
-    d_val = torch.tensor(deltas if deltas else [0], dtype=torch.int32).to(dev)
+    def schedule(part):
+        offsets, deltas = _aliasing_schedule(t, "mean_except_current", t // 2)
+        return torch.tensor(offsets if part == 0 else (deltas if deltas else [0]), dtype=torch.int32)
+
+    d_off = cached_device_tensor(("xc_delta_offsets", t), lambda: schedule(0), dev)  # same keys as estimate_motion_xc
+    d_val = cached_device_tensor(("xc_deltas", t), lambda: schedule(1), dev)
     prod = _fourier.leave_one_out_products(spec_all, t, g, plan.plane_elems, d_off, d_val, frame_offset, t_local)
     shifts = plan.peaks(prod.view(t_local * g, plan.ky, plan.kx, 2), sub_pixel=bool(sub_pixel_refinement))
     shifts = all_gather_frames(shifts.view(t_local, g * 2), t, group).contiguous()
@@ -171,7 +177,7 @@ def estimate_patch_motion_frame_split(local_frames, pixel_spacing, frame_offset,
         call("tmc_xc_postprocess", ptr(shifts), t, g, float(pixel_spacing), -1, int(bool(outlier_rejection)),
              float(outlier_threshold), int(bool(temporal_smoothing)), int(smoothing_window_size), 1, ptr(field), ptr(scratch),
              stream_ptr(dev))
-    return field, centers.to(dev)
+    return field, cached_device_tensor(("patch_centres", (t, h, w, p)), lambda: centers, dev).clone()
 
 
 def _make_patch_shard_problem(spec_sub, centres_norm_sub, base, kind, loss_code, px, t, ph, pw, resolution, plan, dev):
@@ -287,7 +293,8 @@ def estimate_local_motion_frame_split(local_frames, pixel_spacing, patch_shape, 
     norm[..., 0] /= float(t - 1) if t > 1 else float("nan")
     norm[..., 1] /= float(h - 1)
     norm[..., 2] /= float(w - 1)
-    centres_sub = norm.reshape(t, g, 3)[:, g0:max(g1, g0 + 1)].contiguous().to(dev)
+    centres_sub = cached_device_tensor(("split_centres", (t, h, w, ph, pw), g0, g1),
+                                       lambda: norm.reshape(t, g, 3)[:, g0:max(g1, g0 + 1)].contiguous(), dev)
     problem = _make_patch_shard_problem(spec_sub, centres_sub, base, kind, lt, px, t, ph, pw, resolution, plan, dev)
 
     # the mini-batch weighting of every iteration: drawn once (rank 0) and broadcast; each rank uses its patches' columns
