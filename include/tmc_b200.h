@@ -142,9 +142,11 @@ int tmc_dose_filter_spectra(void* spec, const int* jobs, int njobs, int ny, int 
                             float* tables, tmc_stream_t stream);
 
 /* ---- FFT plans ------------------------------------------------------------------------------------ */
-/* 1: powers of two in [16, 8192] and any other n in [2, 4096] (Bluestein): full and band-limited transforms;
- * 2: 2..8 times such a length (K3 5760 x 4092, super-resolution 11520 x 8184): band-limited transforms only (tmc_rfft2_band,
- *    tmc_xc_peaks: the axis is decimated, n = R n', and the R sub-transforms are combined on the band); 0: unsupported */
+/* 1: full and band-limited transforms: powers of two in [16, 8192], any other n in [2, 4096] (Bluestein), and 2..8
+ *    times such a length (the axis is decimated, n = R n', and the R sub-transforms are combined) while the accumulators
+ *    of a full spectrum fit in shared memory (n <= 12158, 12288, 16384: K3 5760 x 4092, super-resolution 11520 x 8184);
+ * 2: longer decimated axes (<= 32768): band-limited transforms only (tmc_rfft2_band with a narrow band, tmc_xc_peaks);
+ * 0: unsupported */
 int tmc_fft_supported_length(int n);
 long tmc_fft_plan_elems(int n);      /* complex64 elements of a plan buffer, 0 if unsupported */
 int tmc_fft_plan_init(int n, void* plan, tmc_stream_t stream);

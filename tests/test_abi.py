@@ -40,8 +40,11 @@ def test_library_loads_through_the_binding_and_answers_queries():
     assert lib.tmc_version() >= 100
     assert _lib.query("tmc_fft_supported_length", 1024) == 1
     assert _lib.query("tmc_fft_supported_length", 959) == 1  # Bluestein
-    assert _lib.query("tmc_fft_supported_length", 5000) == 2  # 2 x 2500: band-limited transforms only (decimated axis)
-    assert _lib.query("tmc_fft_supported_length", 5760) == 2 and _lib.query("tmc_fft_supported_length", 11520) == 2
+    assert _lib.query("tmc_fft_supported_length", 5000) == 1  # 2 x 2500: decimated axis, full spectrum fits on chip
+    assert _lib.query("tmc_fft_supported_length", 5760) == 1 and _lib.query("tmc_fft_supported_length", 11520) == 1
+    assert _lib.query("tmc_fft_supported_length", 16384) == 1  # 4 x 4096
+    assert _lib.query("tmc_fft_supported_length", 13000) == 2  # 4 x 3250: band-limited transforms only
+    assert _lib.query("tmc_fft_supported_length", 32768) == 2
     assert _lib.query("tmc_fft_supported_length", 8198) == 0  # 2 x 4099 (prime)
     assert _lib.query("tmc_fft_plan_elems", 5760) == 2 * 8192 + 2880  # plan of the 2880-point sub-transforms
     assert _lib.query("tmc_fft_plan_elems", 1024) == 1024

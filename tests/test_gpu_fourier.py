@@ -27,7 +27,10 @@ def as_complex(t):
     "shape",
     [(16, 16), (32, 32), (64, 128), (128, 64), (256, 256), (512, 1024), (2048, 2048),
      # arbitrary lengths run as Bluestein chirp-z transforms on the same FFT core
-     (96, 96), (48, 80), (100, 36), (959, 927), (30, 4092)],
+     (96, 96), (48, 80), (100, 36), (959, 927), (30, 4092),
+     # axes beyond the shared-memory transforms: decimated by R (5000 = 2 x 2500, 5760 = 2 x 2880, 9000 = 3 x 3000,
+     # 11520 = 3 x 3840, 12288 = 3 x 4096, 16384 = 4 x 4096), every output bin sums R aliased sources
+     (5000, 48), (64, 5760), (4100, 5000), (9000, 40), (32, 11520), (12288, 32), (48, 16384)],
 )
 def test_full_rfft2_and_irfft2_match_torch(dev, shape):
     ny, nx = shape
@@ -193,9 +196,19 @@ def test_unsupported_length_raises(dev):
     # 8198 = 2 x 4099 (prime): no decimation into lengths the shared-memory transforms cover
     with pytest.raises(NotImplementedError):
         tmc.estimate_global_motion(torch.zeros((2, 8198, 64), device=dev), 1.0)
-    # full (not band-limited) transforms of a decimated length
+    # full (not band-limited) transforms of a decimated length whose accumulators do not fit in shared memory
+    assert _ops.query("tmc_fft_supported_length", 13000) == 2
     with pytest.raises(NotImplementedError):
-        tmc.correct_motion_fast(torch.zeros((2, 5000, 64), device=dev), torch.zeros((2, 2, 1, 1), device=dev))
+        tmc.correct_motion_fast(torch.zeros((2, 13000, 64), device=dev), torch.zeros((2, 2, 1, 1), device=dev))
+
+
+def test_correct_motion_fast_k3_frame_size(dev):
+    """correct_motion_fast (full-spectrum Fourier shift) on K3-sized frames, 5760 = 2 x 2880 columns, against the oracle."""
+    movie, _ = rp.synthetic_movie(3, 4092, 5760, seed=5, noise=1.0, drift=3.0, sigma_f=0.08)
+    field = torch.tensor([[0.0, 1.7, -2.4], [0.0, -3.2, 5.5]]).reshape(2, 3, 1, 1)
+    want = rp.correct_motion_fast(movie, field.clone())
+    got = tmc.correct_motion_fast(movie.to(dev), field.clone().to(dev))
+    assert float(torch.linalg.norm(got.cpu() - want) / torch.linalg.norm(want)) <= 1e-4
 
 
 @pytest.mark.parametrize("shape", [(5000, 4100), (5760, 4092), (600, 9000), (11520, 96), (16384, 128)])

@@ -84,9 +84,10 @@ class BandPlan:
             kind = query("tmc_fft_supported_length", n)
             if kind == 0 or (full and kind != 1):
                 raise NotImplementedError(
-                    f"transform length {n} is not supported: the sm_100a FFT kernels take powers of two in [16, 8192] and "
-                    f"arbitrary lengths up to 4096 (patch side lengths / frame sizes); band-limited transforms (the motion "
-                    f"estimators) also take 2..8 times such a length (K3 5760 x 4092, super-resolution 11520 x 8184)"
+                    f"transform length {n} is not supported: the sm_100a FFT kernels take powers of two in [16, 8192], "
+                    f"arbitrary lengths up to 4096 and 2..8 times such a length (K3 5760 x 4092, super-resolution "
+                    f"11520 x 8184); full-spectrum transforms (correct_motion_fast, dose_weight) of the latter stop at "
+                    f"12158 (plus 12288 and 16384), the band-limited ones of the motion estimators at 32768"
                 )
         self.ny, self.nx, self.device = ny, nx, device
         self.tw_y, self.tw_x = twiddles(ny, device), twiddles(nx, device)

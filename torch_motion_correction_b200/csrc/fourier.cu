@@ -46,12 +46,15 @@ inline int fft_size_for(int n) {  // 0: unsupported
 
 // Axes longer than the shared-memory transforms reach (n > 4096 and not a power of two <= 8192: K3 frames are
 // 5760 x 4092, super-resolution 11520 x 8184) are decimated: n = R n' with n' supported, and with j = R m + r
-//   forward, band-limited output:  X[k] = sum_r W_n^{r k} Y_r[k mod n'],   Y_r = DFT_n'(x[R m + r])
-//   inverse, band-limited input:   x[R m + r] = IDFT_n'( X[k] W_n^{-r k} aliased onto k mod n' )[m]
-// (the second needs the band to span <= n' bins, which a band-pass below Nyquist / R always does).  The generic
-// kernels below loop over r; R == 1 is the plain transform.
+//   forward:  X[k] = sum_r W_n^{r k} Y_r[k mod n'],   Y_r = DFT_n'(x[R m + r])
+//   inverse:  x[R m + r] = IDFT_n'( Z_r )[m],   Z_r[j] = sum_q X[j + q n'] W_n^{-r (j + q n')}
+// (a band that spans <= n' bins aliases without collisions: one term per j).  The generic kernels below loop over r;
+// R == 1 is the plain transform.
 inline int decimation_for(int n) {  // 0: unsupported
   if (fft_size_for(n) > 0) return 1;
+  // sub-sequences of exactly 8192 points leave no shared memory for the accumulators of a full spectrum: take them last
+  for (int r = 2; r <= 8; ++r)
+    if (n % r == 0 && fft_size_for(n / r) > 0 && n / r != 8192) return r;
   for (int r = 2; r <= 8; ++r)
     if (n % r == 0 && fft_size_for(n / r) > 0) return r;
   return 0;
@@ -422,16 +425,21 @@ cols_inverse_kernel(const float2* __restrict__ in, int KX, int KY, int ky_start,
   const float2* src = in + item * KY * KX;
   float2* dst = tmp + item * NY * KX;
   for (int r = 0; r < R; ++r) {
-    for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < B * KY; idx += kThreads) {
-      const int s = idx % B, kyb = idx / B;
-      if (kx0 + s >= KX) continue;
-      float2 v = src[(long)kyb * KX + kx0 + s];
-      const int ky = ky_start + kyb;
-      if (R > 1) v = cmul(v, twiddle_n(-(long)r * ky, NY));  // x[R m + r] = IDFT_n'(X[k] W^{-r k})[m]
-      const int pos = ((ky % NS) + NS) % NS;                 // the band spans <= n' bins: no two ky share a position
-      a[s * STRIDE + pad_idx(pos)] = make_float2(v.y, v.x);  // re/im swap: inverse via forward
+    // position j of the sub-sequence's spectrum gathers every band row ky = j (mod n'): one row for a band of <= n'
+    // rows, R rows for a full spectrum
+    for (int idx = threadIdx.x; idx < B * NS; idx += kThreads) {
+      const int s = idx % B, pos = idx / B;
+      float2 z = make_float2(0.f, 0.f);
+      if (kx0 + s < KX) {
+        int kyb = (pos - ky_start) % NS;
+        if (kyb < 0) kyb += NS;
+        for (; kyb < KY; kyb += NS) {
+          float2 v = src[(long)kyb * KX + kx0 + s];
+          if (R > 1) v = cmul(v, twiddle_n(-(long)r * (ky_start + kyb), NY));
+          z = cadd(z, v);
+        }
+      }
+      a[s * STRIDE + pad_idx(pos)] = make_float2(z.y, z.x);  // re/im swap: inverse via forward
     }
     __syncthreads();
     const float2* res = dft_smem<MY, BLU>(a, b, plan);
@@ -447,26 +455,47 @@ cols_inverse_kernel(const float2* __restrict__ in, int KX, int KY, int ky_start,
 
 // ---- inverse: row pass (complex-to-real, two rows per transform) ------------------------------
 
-// builds the packed spectrum of rows ya (real part) and yb (imaginary part) in `a`, re/im swapped; for a decimated axis
-// (R > 1) the spectrum of sub-sequence r: entries times W^{-/+ r k}, aliased onto k mod NS
+// entry k in [0, NX) of the packed spectrum Z = Ca + i Cb of rows ya (real part) and yb (imaginary part), times the
+// sub-sequence twiddle W_NX^{-r k}; Ca, Cb are given on [0, KX) and Hermitian beyond
+__device__ __forceinline__ float2 c2r_entry(const float2* __restrict__ rowa, const float2* __restrict__ rowb, int KX, int NX,
+                                            int R, int r, int k) {
+  const bool neg = 2 * k > NX;
+  const int kk = neg ? NX - k : k;
+  if (kk >= KX) return make_float2(0.f, 0.f);
+  const float2 ca = rowa[kk];
+  const float2 cb = rowb ? rowb[kk] : make_float2(0.f, 0.f);
+  if (kk == 0 || 2 * kk == NX) {  // c2r ignores the imaginary part of the DC / Nyquist bins
+    const float sgn = (kk != 0 && (r & 1)) ? -1.f : 1.f;  // W^{-r N/2} = (-1)^r
+    return make_float2(sgn * ca.x, sgn * cb.x);
+  }
+  // Z[k] = Ca + i Cb ; Z[N-k] = conj(Ca) + i conj(Cb)
+  float2 z = neg ? make_float2(ca.x + cb.y, cb.x - ca.y) : make_float2(ca.x - cb.y, ca.y + cb.x);
+  if (R > 1) {
+    const float2 tw = twiddle_n(-(long)r * kk, NX);
+    z = cmul(z, neg ? make_float2(tw.x, -tw.y) : tw);
+  }
+  return z;
+}
+
+// builds the packed spectrum of rows ya (real part) and yb (imaginary part) in `a_seq` (zeroed by the caller unless
+// `gather`), re/im swapped; for a decimated axis (R > 1) the spectrum of sub-sequence r: entries times W^{-/+ r k},
+// aliased onto k mod NS.  gather: the band may alias onto itself (2 KX - 1 > NS), every position sums its R sources.
 __device__ __forceinline__ void load_c2r_pair(const float2* __restrict__ rowa, const float2* __restrict__ rowb, int KX,
-                                              int NX, int NS, int R, int r, float2* __restrict__ a_seq) {
+                                              int NX, int NS, int R, int r, bool gather, float2* __restrict__ a_seq) {
+  if (gather) {
+    for (int j = threadIdx.x; j < NS; j += kThreads) {
+      float2 z = make_float2(0.f, 0.f);
+      for (int q = 0; q < R; ++q) z = cadd(z, c2r_entry(rowa, rowb, KX, NX, R, r, j + q * NS));
+      a_seq[pad_idx(j)] = make_float2(z.y, z.x);
+    }
+    return;
+  }
   for (int k = threadIdx.x; k < KX; k += kThreads) {
-    float2 ca = rowa[k];
-    float2 cb = rowb ? rowb[k] : make_float2(0.f, 0.f);
-    if (k == 0 || 2 * k == NX) {  // c2r ignores the imaginary part of the DC / Nyquist bins
-      const float sgn = (k != 0 && (r & 1)) ? -1.f : 1.f;  // W^{-r N/2} = (-1)^r
-      a_seq[pad_idx(k % NS)] = make_float2(sgn * cb.x, sgn * ca.x);
-    } else {
-      // Z[k] = Ca + i Cb ; Z[N-k] = conj(Ca) + i conj(Cb) ; stored swapped (im, re)
-      float2 zp = make_float2(ca.x - cb.y, ca.y + cb.x), zn = make_float2(ca.x + cb.y, cb.x - ca.y);
-      if (R > 1) {
-        const float2 tw = twiddle_n(-(long)r * k, NX);
-        zp = cmul(zp, tw);
-        zn = cmul(zn, make_float2(tw.x, -tw.y));
-      }
-      const int kp = k % NS;
-      a_seq[pad_idx(kp)] = make_float2(zp.y, zp.x);
+    const float2 zp = c2r_entry(rowa, rowb, KX, NX, R, r, k);
+    const int kp = k % NS;
+    a_seq[pad_idx(kp)] = make_float2(zp.y, zp.x);
+    if (k != 0 && 2 * k != NX) {
+      const float2 zn = c2r_entry(rowa, rowb, KX, NX, R, r, NX - k);
       a_seq[pad_idx(kp == 0 ? 0 : NS - kp)] = make_float2(zn.y, zn.x);
     }
   }
@@ -496,13 +525,14 @@ rows_inverse_argmax_kernel(const float2* __restrict__ tmp, int NY, int KX, AxisP
   const float2* src = tmp + item * NY * KX;
   float best = -INFINITY;
   int best_idx = 0x7fffffff;
+  const bool gather = R > 1 && 2 * KX - 1 > NS;  // the band aliases onto itself: full spectrum of a decimated axis
   for (int r = 0; r < R; ++r) {
     for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
     __syncthreads();
     for (int s = 0; s < B; ++s) {
       const int ya = row0 + 2 * s, yb = ya + 1;
       if (ya < NY)
-        load_c2r_pair(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, NX, NS, R, r, a + s * STRIDE);
+        load_c2r_pair(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, NX, NS, R, r, gather, a + s * STRIDE);
     }
     __syncthreads();
     const float2* res = dft_smem<MX, BLU>(a, b, plan);
@@ -568,13 +598,14 @@ rows_inverse_store_kernel(const float2* __restrict__ tmp, int NY, int KX, AxisPl
   const int row0 = blockIdx.x * 2 * B;
   const float2* src = tmp + item * NY * KX;
   float* dst = out + item * NY * NX;
+  const bool gather = R > 1 && 2 * KX - 1 > NS;  // the band aliases onto itself: full spectrum of a decimated axis
   for (int r = 0; r < R; ++r) {
     for (int idx = threadIdx.x; idx < B * STRIDE; idx += kThreads) a[idx] = make_float2(0.f, 0.f);
     __syncthreads();
     for (int s = 0; s < B; ++s) {
       const int ya = row0 + 2 * s, yb = ya + 1;
       if (ya < NY)
-        load_c2r_pair(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, NX, NS, R, r, a + s * STRIDE);
+        load_c2r_pair(src + (long)ya * KX, yb < NY ? src + (long)yb * KX : nullptr, KX, NX, NS, R, r, gather, a + s * STRIDE);
     }
     __syncthreads();
     const float2* res = dft_smem<MX, BLU>(a, b, plan);
@@ -752,16 +783,34 @@ int enable_smem(K kernel, size_t bytes) {
   return TMC_OK;
 }
 
+constexpr size_t kMaxSmem = 227 * 1024;
+
+// shared memory of the generic kernels' transform buffers for FFT size m (runtime twin of fft_smem_bytes)
+inline size_t fft_smem_runtime(int m) { return 2ull * batch_for(m) * padded_len(m) * sizeof(float2); }
+
+// a decimated axis of length n: do the accumulators of a FULL spectrum (row pass: n/2+1 bins twice, column pass: n bins)
+// fit beside the transform buffers?
+inline bool decimated_full_fits(int n) {
+  const int R = decimation_for(n);
+  if (R <= 1) return R == 1;
+  const int m = fft_size_for(n / R), b = batch_for(m);
+  return fft_smem_runtime(m) + 2ull * b * (n / 2 + 1) * sizeof(float2) <= kMaxSmem &&
+         fft_smem_runtime(m) + 1ull * b * n * sizeof(float2) <= kMaxSmem;
+}
+
 }  // namespace
 
 // ---- C ABI ---------------------------------------------------------------------------------------
 
-// 1: full transforms of this length are supported (a power of two up to 8192 or any length up to 4096);
-// 2: band-limited transforms only (the axis is decimated by 2..8 into supported lengths: any such n up to 32768);
+// 1: full transforms of this length are supported (a power of two up to 8192, any length up to 4096, or 2..8 times
+//    such a length while the accumulators of the full spectrum fit in shared memory: up to 12158, and 12288, 16384);
+// 2: band-limited transforms only (longer decimated axes, up to 32768);
 // 0: unsupported
 TMC_API int tmc_fft_supported_length(int n) {
   if (fft_size_for(n) > 0) return 1;
-  return decimation_for(n) > 0 ? 2 : 0;
+  const int R = decimation_for(n);
+  if (R == 0) return 0;
+  return decimated_full_fits(n) ? 1 : 2;
 }
 
 // complex64 elements of the plan buffer for a length-n transform (0: unsupported length)
@@ -901,7 +950,7 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
     // generic kernel (Bluestein lengths, small transforms, decimated long axes); the accumulators of a decimated axis
     // follow the two transform buffers
     const size_t smem = fft_smem_bytes<MM>() + (px.R > 1 ? 2ull * batch_for(MM) * kx_count * sizeof(float2) : 0);
-    if (smem > 200 * 1024) {
+    if (smem > kMaxSmem) {
       tmc_set_error("rfft2_band: band of %d bins too wide for the decimated row transform of length %d", kx_count, nx);
       return TMC_ERR_UNSUPPORTED;
     }
@@ -926,7 +975,7 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
       return TMC_OK;
     }
     const size_t smem = fft_smem_bytes<MM>() + (py.R > 1 ? 1ull * batch_for(MM) * ky_count * sizeof(float2) : 0);
-    if (smem > 200 * 1024) {
+    if (smem > kMaxSmem) {
       tmc_set_error("rfft2_band: band of %d bins too wide for the decimated column transform of length %d", ky_count, ny);
       return TMC_ERR_UNSUPPORTED;
     }
@@ -1012,11 +1061,6 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
   TMC_CHECK_ARG(kx_count >= 1 && kx_count <= nx / 2 + 1 && ky_count >= 1 && ky_count <= ny, "xc_peaks: bad band box");
   if (nitems == 0) return TMC_OK;
   const AxisPlan px = make_axis_plan(plan_x, nx), py = make_axis_plan(plan_y, ny);
-  // decimated (long) axes invert band-limited input only: the band must not alias onto itself
-  TMC_CHECK_ARG(py.R == 1 || ky_count <= py.n, "xc_peaks: band of %d rows too wide for the decimated column transform of length %d",
-                ky_count, ny);
-  TMC_CHECK_ARG(px.R == 1 || 2 * kx_count - 1 <= px.n, "xc_peaks: band of %d columns too wide for the decimated row transform of length %d",
-                kx_count, nx);
   int rc = dispatch_fft(ny, "xc_peaks", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
@@ -1076,14 +1120,10 @@ TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const 
   if (nitems == 0) return TMC_OK;
   const int kx = nx / 2 + 1;
   const AxisPlan px = make_axis_plan(plan_x, nx), py = make_axis_plan(plan_y, ny);
-  if (px.R != 1 || py.R != 1) {
-    tmc_set_error("irfft2_full: full transforms need lengths up to 4096 or powers of two up to 8192, got (%d, %d)", ny, nx);
-    return TMC_ERR_UNSUPPORTED;
-  }
   int rc = dispatch_fft(ny, "irfft2_full", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
-    if constexpr (use_fast_path<MM, BB>()) {
+    if constexpr (use_fast_path<MM, BB>()) if (py.R == 1) {
       if (int e = enable_smem(cols_inverse_p2<MM>, fft2::Cfg<MM>::smem_bytes)) return e;
       dim3 grid(tmc_div_up(kx, fft2::Cfg<MM>::B), nitems);
       TMC_TIMED(sized_label<MM>("cols_inverse_p2<4096>", "cols_inverse_p2<1024>", "cols_inverse_p2"), stream, cols_inverse_p2<MM><<<grid, fft2::kThreads, fft2::Cfg<MM>::smem_bytes, stream>>>((const float2*)spec, kx, ny, 0, py.tw,
@@ -1099,7 +1139,7 @@ TMC_API int tmc_irfft2_full(const void* spec, int nitems, int ny, int nx, const 
   rc = dispatch_fft(nx, "irfft2_full", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
-    if constexpr (use_fast_path<MM, BB>()) {
+    if constexpr (use_fast_path<MM, BB>()) if (px.R == 1) {
       if (int e = enable_smem(rows_inverse_store_p2<MM>, rows_inverse_smem_bytes<MM>())) return e;
       dim3 grid(tmc_div_up(ny, rows_per_cta_inverse<MM>()), nitems);
       TMC_TIMED(sized_label<MM>("rows_inverse_store_p2<4096>", "rows_inverse_store_p2<1024>", "rows_inverse_store_p2"), stream, rows_inverse_store_p2<MM><<<grid, fft2::kThreads, rows_inverse_smem_bytes<MM>(), stream>>>(
