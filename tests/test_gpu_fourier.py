@@ -317,7 +317,8 @@ def test_polyphase_rows_1024_peaks(dev):
     assert int(((gy == want // p) & (gx == want % p)).sum()) >= n - 1
 
 
-@pytest.mark.parametrize("shape,voltage", [((6, 96, 128), 300.0), ((5, 300, 256), 200.0), ((7, 64, 90), 300.0)])
+@pytest.mark.parametrize("shape,voltage", [((6, 96, 128), 300.0), ((5, 300, 256), 200.0), ((7, 64, 90), 300.0),
+                                           ((3, 600, 5000), 300.0)])  # 5000 = 2 x 2500: decimated full-spectrum rows
 def test_dose_weighted_sum_matches_oracle(dev, shape, voltage, monkeypatch):
     """tmc.dose_weight (full rfft2 of every frame, exposure-filtered sum in Fourier space, ONE inverse transform)
     against the example script's per-frame filter + irfft2 + sum; frame blocks accumulate (forced small blocks)."""
