@@ -633,6 +633,7 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
         const char* dbg = getenv("TMC_WARP_TMA_DEBUG");
         prm.debug = dbg ? atoi(dbg) : 0;
       }
+      tma::fill_constants(prm);
       int dev_id = 0, sms = 148;
       TMC_CUDA(cudaGetDevice(&dev_id));
       TMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));

@@ -87,7 +87,7 @@ __device__ __forceinline__ float2 pk_add(float2 a, float2 b) { return __fadd2_rn
 
 // Keys cubic-convolution weights (A = -0.75, ATen's bicubic) of two fractions at once (.x = y axis, .y = x axis) in
 // factored form: w0 = A t (1 - t)^2, w3 = A t^2 (1 - t), w1 = ((A + 2) t - (A + 3)) t^2 + 1, w2 = w1(1 - t).  Same
-// polynomials as get_cubic_upsample_coefficients (cubic_weights2), 11 instead of 15 packed instructions; the results
+// polynomials as get_cubic_upsample_coefficients (cubic_weights2), 10 instead of 15 packed instructions; the results
 // differ from ATen's evaluation order by rounding only (<= 2e-7 absolute, against a 1e-4 tolerance on the frame sum).
 __device__ __forceinline__ void keys_weights2(float2 t, float2 (&w)[4]) {
   const float2 A = dup(kA), A2 = dup(kA + 2.0f), mA3 = dup(-(kA + 3.0f)), one = dup(1.0f);
@@ -96,7 +96,7 @@ __device__ __forceinline__ void keys_weights2(float2 t, float2 (&w)[4]) {
   w[0] = pk_mul(a, u);
   w[3] = pk_mul(a, t);
   w[1] = pk_fma(pk_fma(A2, t, mA3), pk_mul(t, t), one);
-  w[2] = pk_fma(pk_fma(A2, u, mA3), pk_mul(u, u), one);
+  w[2] = pk_add(pk_fma(a, dup(-1.0f), one), pk_mul(w[1], dup(-1.0f)));  // w0 + w1 + w2 + w3 = 1 and w0 + w3 = A t (1 - t)
 }
 
 // the same with an L2 eviction-priority hint (createpolicy)
@@ -108,6 +108,11 @@ __device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* m
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+
+template <bool V>
+struct BoolTag {
+  static constexpr bool value = V;
+};
 
 struct Params {
   const float* image;
@@ -122,6 +127,10 @@ struct Params {
   int accumulate_sum;
   int tiles_x, n_tiles;
   int debug;  // TMC_WARP_TMA_DEBUG bits: 1 no image loads, 2 no lattice loads, 4 consumers skip the arithmetic
+  // constants of the coordinate chain, formed on the host so that they reach the arithmetic as constant-bank operands
+  // (the kernel is bound by register-file reads: a register operand less per instruction is what counts)
+  float2 nden, rcp, half_scale;  // .x = y axis, .y = x axis
+  float inv_px;
 };
 
 template <bool WRITE_STACK, bool WRITE_SUM, bool NORMALISE>
@@ -238,11 +247,10 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
     inv_std = 1.0f / __ldg(p.mean_std + 1);
   }
   // grid_sample round trip constants, .x = y axis (H), .y = x axis (W); see warp_lattice_kernel
-  const float dy = __fsub_rn(__fmul_rn(0.5f, (float)H), 0.5f), dx = __fsub_rn(__fmul_rn(0.5f, (float)W), 0.5f);
-  const float2 nden = f2(-dy, -dx), rcp = f2(__frcp_rn(dy), __frcp_rn(dx));
-  // ((g + 1) * 0.5) * (n - 1) == (g + 1) * (0.5 * (n - 1)) bit for bit: the halving is exact, so is 0.5 * (n - 1)
-  const float2 half_scale = f2(0.5f * (float)(H - 1), 0.5f * (float)(W - 1));
-  const float2 inv_px = dup(inv_px_s);
+  // nden = -(0.5 n - 0.5), rcp = fl(1 / (0.5 n - 0.5)), half_scale = 0.5 (n - 1): ((g + 1) * 0.5) * (n - 1) ==
+  // (g + 1) * (0.5 * (n - 1)) bit for bit (the halving is exact, so is 0.5 * (n - 1)); see fill_constants
+  const float2 nden = p.nden, rcp = p.rcp, half_scale = p.half_scale;
+  const float2 inv_px = dup(p.inv_px);
   uint32_t stage = 0, phase = 0;
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int x0 = (tile % p.tiles_x) * kTX, y0 = (tile / p.tiles_x) * kTY;
@@ -273,6 +281,11 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
 
+    // the frame loop, specialised on whether the thread's 4 rows read the same lattice rows (warp-uniform, true for all
+    // but the few row groups that straddle a lattice cell boundary): no branch inside the coordinate arithmetic, so
+    // the 4 pixels' dependent chains interleave
+    auto frames = [&](auto same_tag) {
+    constexpr bool SAME = decltype(same_tag)::value;
     for (int f = 0; f < T; ++f) {
       mbar_wait(&full_bar[stage], phase);
       if (active && !(p.debug & 4)) {
@@ -280,22 +293,19 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
         const float* srx = simg + kImgBytesPadded / 4;
         const int4 org = *reinterpret_cast<const int4*>(stage_hdr[stage]);       // oy + 1, ox + 1, by_lo, by_n
         const int2 xr = *reinterpret_cast<const int2*>(stage_hdr[stage] + 4);    // bx_lo, bx_n
-        float2 R[4];
-        if (same_cell) {
+        float2 R[SAME ? 1 : kRows][4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) R[k] = f2(srx[lat[0] + k * 2 * kTX], srx[lat[0] + (k * 2 + 1) * kTX]);
-        }
+        for (int r = 0; r < (SAME ? 1 : kRows); ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) R[r][k] = f2(srx[lat[r] + k * 2 * kTX], srx[lat[r] + (k * 2 + 1) * kTX]);
         float2 c[kRows], fl[kRows], frac[kRows];
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
-          if (!same_cell) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) R[k] = f2(srx[lat[r] + k * 2 * kTX], srx[lat[r] + (k * 2 + 1) * kTX]);
-          }
-          float2 s = pk_mul(dup(wy[r][0]), R[0]);
-          s = pk_fma(dup(wy[r][1]), R[1], s);
-          s = pk_fma(dup(wy[r][2]), R[2], s);
-          s = pk_fma(dup(wy[r][3]), R[3], s);
+          const float2* Rr = R[SAME ? 0 : r];
+          float2 s = pk_mul(dup(wy[r][0]), Rr[0]);
+          s = pk_fma(dup(wy[r][1]), Rr[1], s);
+          s = pk_fma(dup(wy[r][2]), Rr[2], s);
+          s = pk_fma(dup(wy[r][3]), Rr[3], s);
           // Angstrom -> px, then pixel_grid + pixel_shifts (two roundings, like the reference)
           c[r] = pk_add(f2(yf[r], xf), pk_mul(s, inv_px));
           // grid_sample round trip: g = c / (0.5 n - 0.5) - 1 ; u = ((g + 1) / 2) (n - 1); the division as
@@ -411,6 +421,8 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
         phase ^= 1u;
       }
     }
+    };
+    if (same_cell) frames(BoolTag<true>{}); else frames(BoolTag<false>{});
     if (WRITE_SUM && active) {
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
@@ -449,9 +461,20 @@ inline bool make_map_3d(CUtensorMap* map, const float* base, uint64_t d0, uint64
   const cuuint64_t strides[2] = {d0 * sizeof(float), d0 * d1 * sizeof(float)};
   const cuuint32_t box[3] = {b0, b1, b2};
   const cuuint32_t elem[3] = {1, 1, 1};
+  // 64-byte L2 promotion: measured DRAM reads of the C2 warp 4.64 GB against 6.13 GB with none / 128 B and 6.62 GB with
+  // 256 B (box rows are 192 bytes at arbitrary 16-byte offsets; same kernel time)
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, elem,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// the coordinate-chain constants of Params, rounded exactly as the device code of warp_lattice_kernel rounds them
+inline void fill_constants(Params& p) {
+  const float dy = 0.5f * (float)p.H - 0.5f, dx = 0.5f * (float)p.W - 0.5f;  // both exact in fp32
+  p.nden = make_float2(-dy, -dx);
+  p.rcp = make_float2(1.0f / dy, 1.0f / dx);  // IEEE division == __frcp_rn
+  p.half_scale = make_float2(0.5f * (float)(p.H - 1), 0.5f * (float)(p.W - 1));
+  p.inv_px = 1.0f / p.pixel_spacing;
 }
 
 // lattice rows a tile needs: its kTY image rows span at most floor((kTY - 1) / cell) + 2 lattice cells (+ 3 taps)
