@@ -201,7 +201,9 @@ LARGE = dict(c2half=dict(t=40, size=2048, seed=40, px=0.83, resolution=(3, 5, 5)
              c3half=dict(t=60, size=2048, seed=60, px=0.83, resolution=(5, 6, 6), iters=3),
              # BASELINE configs 2 and 3 at their full size (about 5 and 8 CPU-minutes, ~25 GB of host memory)
              c2full=dict(t=40, size=4096, seed=41, px=0.83, resolution=(3, 5, 5), iters=3),
-             c3full=dict(t=60, size=4096, seed=61, px=0.83, resolution=(5, 6, 6), iters=2))
+             c3full=dict(t=60, size=4096, seed=61, px=0.83, resolution=(5, 6, 6), iters=2),
+             # BASELINE config 4's code paths (8192-point whole-frame transforms, 15 x 15 / 14 x 14 patch grids) on 10 frames
+             c4short=dict(t=10, size=8192, seed=81, px=0.83, resolution=(3, 5, 5), iters=2))
 
 
 def sum_samples(s):
@@ -255,7 +257,7 @@ def case_large(ref, name):
         out["local_field"] = np32(res)
         out["local_losses"] = np.asarray([c.loss for c in traj.checkpoints])
         print(name, "local done", time.time() - tic, file=sys.__stdout__, flush=True)
-        if name.startswith("c2"):
+        if name.startswith("c2") or name.startswith("c4"):
             corr = ref.correct_motion(movie, res, px, grid_type="bspline")
             out.update(sum_samples(corr.sum(dim=0)))
             del corr
@@ -265,12 +267,12 @@ def case_large(ref, name):
     print(name, "done", time.time() - tic, file=sys.__stdout__, flush=True)
 
 
-def case_whole4096(ref):
-    """4 frames of 4096^2: the 4096-point whole-frame transforms (global estimate, rigid Fourier-shift correction)."""
+def case_whole4096(ref, n=4096, seed=7):
+    """4 frames of n^2: the n-point whole-frame transforms (global estimate, rigid Fourier-shift correction)."""
     out = {}
     px = 0.83
-    movie, walk = synthetic_movie(4, 4096, 4096, seed=7, noise=1.0, drift=9.0, integer_shifts=True, sigma_f=0.08)
-    out["seed"] = np.int64(7)
+    movie, walk = synthetic_movie(4, n, n, seed=seed, noise=1.0, drift=9.0, integer_shifts=True, sigma_f=0.08)
+    out["seed"] = np.int64(seed)
     out["true_shifts"] = np32(walk)
     with verbatim.quiet():
         g = ref.estimate_global_motion(movie.clone(), px)
@@ -278,12 +280,12 @@ def case_whole4096(ref):
         field = torch.tensor([[1.5, -2.25, 0.0, 3.7], [-0.5, 4.125, 2.0, -6.3]]).reshape(2, 4, 1, 1)
         out["fast_field"] = np32(field)
         corr = ref.correct_motion_fast(movie, field.clone())
-        out["fast_centre"] = np32(corr[:, 2048 - 64 : 2048 + 64, 2048 - 64 : 2048 + 64])
+        out["fast_centre"] = np32(corr[:, n // 2 - 64 : n // 2 + 64, n // 2 - 64 : n // 2 + 64])
         out["fast_corner"] = np32(corr[:, :64, :64])
-        out["fast_rows"] = np32(corr[:, ::512, :])
+        out["fast_rows"] = np32(corr[:, :: n // 8, :])
         out["fast_norm"] = np.float64(torch.linalg.norm(corr.double()))
-    np.savez_compressed(os.path.join(OUT, "whole4096.npz"), **out)
-    print("whole4096.npz done", file=sys.__stdout__, flush=True)
+    np.savez_compressed(os.path.join(OUT, f"whole{n}.npz"), **out)
+    print(f"whole{n}.npz done", file=sys.__stdout__, flush=True)
 
 
 def main():
@@ -296,7 +298,8 @@ def main():
         if name in LARGE:
             case_large(ref, name)
         else:
-            {"small": case_small, "eviction": case_eviction, "c1": case_c1, "whole4096": case_whole4096}[name](ref)
+            {"small": case_small, "eviction": case_eviction, "c1": case_c1, "whole4096": case_whole4096,
+             "whole8192": lambda r: case_whole4096(r, 8192, 8)}[name](ref)
 
 
 if __name__ == "__main__":

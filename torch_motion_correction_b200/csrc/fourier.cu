@@ -906,6 +906,7 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
       // polyphase path: four 256-point warp-level FFTs per row, only the band is ever formed
       if (yhi > ylo && kx_count <= 128 && job_mode != 0 && use_poly() && px.R == 1) {
         int rows_per_cta = 32;
+        if (const char* e = getenv("TMC_POLY_ROWS")) rows_per_cta = atoi(e);  // experiment
         while (rows_per_cta > 8 && (long)tmc_div_up(yhi - ylo, rows_per_cta) * njobs < 148 * 6) rows_per_cta -= 8;
         dim3 grid(tmc_div_up(yhi - ylo, rows_per_cta), njobs);
         if (job_mode == 1) {

@@ -328,21 +328,31 @@ rows_inverse_argmax_p2(const float2* __restrict__ tmp, int NY, int KX, const flo
   float best = -INFINITY;
   int best_idx = 0x7fffffff;
   rows_inverse_driver<N>(tmp + item * NY * KX, NY, KX, tw, smem, [&](int ya, bool has_b, int j, const float2* v) {
+    // the thread visits its samples in increasing index order (out_index = j + g TPS + r NS with G TPS == NS: r outer,
+    // g inner; row ya, then row ya + 1; later calls have larger ya), so "strictly greater" keeps the first of equal
+    // maxima: one compare and two selects per sample
 #pragma unroll
-    for (int g = 0; g < P::Last::G; ++g)
+    for (int r = 0; r < P::Last::R; ++r)
 #pragma unroll
-      for (int r = 0; r < P::Last::R; ++r) {
-        const float2 val = P::Last::result(v, g, r);  // swapped: .y = row ya, .x = row ya + 1
-        const int ia = ya * N + P::Last::out_index(j, g, r);
-        if (better(val.y, ia, best, best_idx)) {
-          best = val.y;
-          best_idx = ia;
-        }
-        if (has_b && better(val.x, ia + N, best, best_idx)) {
-          best = val.x;
-          best_idx = ia + N;
+      for (int g = 0; g < P::Last::G; ++g) {
+        const float val = P::Last::result(v, g, r).y;  // swapped: .y = row ya, .x = row ya + 1
+        if (val > best) {
+          best = val;
+          best_idx = ya * N + P::Last::out_index(j, g, r);
         }
       }
+    if (has_b) {
+#pragma unroll
+      for (int r = 0; r < P::Last::R; ++r)
+#pragma unroll
+        for (int g = 0; g < P::Last::G; ++g) {
+          const float val = P::Last::result(v, g, r).x;
+          if (val > best) {
+            best = val;
+            best_idx = (ya + 1) * N + P::Last::out_index(j, g, r);
+          }
+        }
+    }
   });
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

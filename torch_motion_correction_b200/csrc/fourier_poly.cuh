@@ -226,27 +226,32 @@ rows_inverse_argmax_poly(const float2* __restrict__ tmp, int NY, int KX, const f
     }
     fft256_halfwarp(va, j, buf, tw_step);
     fft256_halfwarp(vb, j, buf, tw_step);
+    // the thread visits its samples in increasing index order (row ya left to right, then row ya + 1; pairs ascend), so
+    // "strictly greater" keeps the first of equal maxima: one compare and two selects per sample
+    const int ia0 = ya * N + 4 * j + q0;
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
-      const int n = 4 * (j + 16 * k1) + q0;
-      const int ia = ya * N + n;
       const float2 a = va[tmcfft::bitrev<16>(k1)], b = vb[tmcfft::bitrev<16>(k1)];  // swapped: .y = row ya, .x = row ya + 1
-      if (better(a.y, ia, best, best_idx)) {
+      if (a.y > best) {
         best = a.y;
-        best_idx = ia;
+        best_idx = ia0 + 64 * k1;
       }
-      if (better(b.y, ia + 1, best, best_idx)) {
+      if (b.y > best) {
         best = b.y;
-        best_idx = ia + 1;
+        best_idx = ia0 + 64 * k1 + 1;
       }
-      if (has_b) {
-        if (better(a.x, ia + N, best, best_idx)) {
+    }
+    if (has_b) {
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) {
+        const float2 a = va[tmcfft::bitrev<16>(k1)], b = vb[tmcfft::bitrev<16>(k1)];
+        if (a.x > best) {
           best = a.x;
-          best_idx = ia + N;
+          best_idx = ia0 + N + 64 * k1;
         }
-        if (better(b.x, ia + N + 1, best, best_idx)) {
+        if (b.x > best) {
           best = b.x;
-          best_idx = ia + N + 1;
+          best_idx = ia0 + N + 64 * k1 + 1;
         }
       }
     }

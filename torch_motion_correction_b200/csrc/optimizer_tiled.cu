@@ -25,8 +25,11 @@
 namespace {
 
 constexpr int kTileKy = 8, kTileKx = 16, kTileBins = kTileKy * kTileKx;
-constexpr int kChunkFrames = 8;
-constexpr int kMaxChunks = 32;  // T <= 256
+#ifndef TMC_CHUNK_FRAMES
+#define TMC_CHUNK_FRAMES 8
+#endif
+constexpr int kChunkFrames = TMC_CHUNK_FRAMES;
+constexpr int kMaxChunks = 256 / kChunkFrames;  // T <= 256
 constexpr int kTileThreads = 256;
 constexpr int kCoefThreads = 1024;
 
