@@ -622,6 +622,13 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
       prm.rx = workspace;
       prm.lh = lh;
       prm.rx_rows = tma::staged_lattice_rows(h, lh);
+      prm.stage_bytes = tma::stage_bytes_for(prm.rx_rows);
+      prm.n_stages = tma::stages_for(prm.rx_rows);
+      if (const char* e = getenv("TMC_WARP_TMA_STAGES")) {  // experiment: shallower ring
+        const int v = atoi(e);
+        if (v >= 2 && v < prm.n_stages) prm.n_stages = v;
+      }
+      const size_t smem_bytes = (size_t)prm.n_stages * prm.stage_bytes + 128;  // + alignment slack
       prm.pixel_spacing = pixel_spacing;
       prm.mean_std = mean_std;
       prm.out_stack = out_stack;
@@ -641,9 +648,9 @@ TMC_API int tmc_warp_lattice(const float* image, int t, int h, int w, const floa
 #define LAUNCH_TMA(S, A, N)                                                                                                  \
   {                                                                                                                          \
     TMC_CUDA(cudaFuncSetAttribute(tma::warp_tma_kernel<S, A, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
-                                  (int)tma::kSmemBytes));                                                                    \
+                                  tma::kMaxSmemBytes));                                                                      \
     tmc_timing_begin(stream);                                                                                                \
-    tma::warp_tma_kernel<S, A, N><<<grid, tma::kThreads, tma::kSmemBytes, stream>>>(img_map, rx_map, prm);                    \
+    tma::warp_tma_kernel<S, A, N><<<grid, tma::kThreads, smem_bytes, stream>>>(img_map, rx_map, prm);                         \
     tmc_timing_end("warp_tma_kernel", stream);                                                                               \
   }
       if (s && a && n) LAUNCH_TMA(true, true, true)

@@ -33,14 +33,23 @@ constexpr int kBoxH = kTY + 2 * kMargin + 3;   // 71
 constexpr int kRxRows = 16;             // lattice rows staged per tile and channel
 constexpr int kImgBytes = kBoxW * kBoxH * 4;                      // 13632
 constexpr int kImgBytesPadded = (kImgBytes + 127) / 128 * 128;    // 13696
-constexpr int kRxBytes = kTX * kRxRows * 2 * 4;                   // 4096
-constexpr int kStageBytes = kImgBytesPadded + kRxBytes;
-constexpr int kStages = 8;
+// The ring is as deep as shared memory allows (a stage holds only the lattice rows actually staged, rx_rows = 5..16, so
+// 13-15 stages fit).  Measured on C2: 4 stages 2.37 ms, 8 stages 2.34 ms, 15 stages 2.33 ms -- one frame of a tile takes
+// a CTA ~1 us, several DRAM round trips, so the ring never runs dry; the kernel is bound by instruction issue (about
+// 300 warp instructions per warp and frame at 0.65 per cycle and scheduler: the packed fp32 instructions hold the fp32
+// pipe for two cycles each and collide between the 4 warps of a scheduler), not by memory (0.64 ms with the
+// arithmetic switched off).
+constexpr int kMaxStages = 16;
+constexpr int kMaxSmemBytes = 227 * 1024 - 2048;  // dynamic part: the static barriers / headers and alignment slack stay below 2 KB
 constexpr int kConsumers = kTX * (kTY / kRows);  // 480 threads, 15 warps
 static_assert(kTX % 32 == 0 && kTY % kRows == 0 && (kTX & (kTX - 1)) == 0, "tile shape");
 constexpr int kThreads = kConsumers + 32;        // + the producer warp
 constexpr int kConsumerWarps = kConsumers / 32;
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 128;  // + alignment slack
+__host__ __device__ constexpr int stage_bytes_for(int rx_rows) { return kImgBytesPadded + (rx_rows * kTX * 2 * 4 + 127) / 128 * 128; }
+inline int stages_for(int rx_rows) {
+  const int n = (kMaxSmemBytes - 128) / stage_bytes_for(rx_rows);
+  return n < kMaxStages ? n : kMaxStages;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -119,6 +128,7 @@ struct Params {
   int T, H, W;
   const float* rx;  // (T, lh + 3, 2, W): x-interpolated lattice, rows padded by reflection (row p <-> lattice row p - 1)
   int rx_rows;      // lattice rows staged per tile (5 .. kRxRows)
+  int n_stages, stage_bytes;  // depth of the ring and bytes per stage (stages_for / stage_bytes_for)
   int lh;
   float pixel_spacing;
   const float* mean_std;
@@ -137,18 +147,18 @@ template <bool WRITE_STACK, bool WRITE_SUM, bool NORMALISE>
 __global__ void __launch_bounds__(kThreads, 1)
 warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_constant__ CUtensorMap rx_map, const Params p) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStages];
-  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   // per stage: {oy + 1, ox + 1, by_lo, by_n, bx_lo, bx_n, -, -}: box origin (+1: the first tap is one before the floor) and
   // the first-tap positions (by - by_lo <= by_n, unsigned) that keep 4 + 3 stacked tap rows / 4 tap columns inside the
   // box AND inside the image (the zero-filled part of a box that hangs over the frame edge is never used)
-  __shared__ __align__(16) int stage_hdr[kStages][8];
+  __shared__ __align__(16) int stage_hdr[kMaxStages][8];
   unsigned char* stages = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const int tid = threadIdx.x;
   const int T = p.T, H = p.H, W = p.W, lh = p.lh;
   const int lhp = lh + 3;
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kConsumerWarps);
     }
@@ -217,12 +227,12 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
             hdr[4] = bx_n >= 0 ? bx_lo : 0x40000000;
             hdr[5] = bx_n >= 0 ? bx_n : 0;
           }
-          unsigned char* dst = stages + (size_t)stage * kStageBytes;
+          unsigned char* dst = stages + (size_t)stage * p.stage_bytes;
           mbar_expect_tx(&full_bar[stage], stage_tx);
           tma_load_3d(dst, &img_map, fox, foy, f0 + i, &full_bar[stage]);
           tma_load_3d_hint(dst + kImgBytesPadded, &rx_map, x0, 0, (f0 + i) * lhp + i0_tile, &full_bar[stage], keep_policy);
         }
-        if (++stage == kStages) {
+        if (++stage == (uint32_t)p.n_stages) {
           stage = 0;
           phase ^= 1u;
         }
@@ -289,7 +299,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
     for (int f = 0; f < T; ++f) {
       mbar_wait(&full_bar[stage], phase);
       if (active && !(p.debug & 4)) {
-        const float* simg = reinterpret_cast<const float*>(stages + (size_t)stage * kStageBytes);
+        const float* simg = reinterpret_cast<const float*>(stages + (size_t)stage * p.stage_bytes);
         const float* srx = simg + kImgBytesPadded / 4;
         const int4 org = *reinterpret_cast<const int4*>(stage_hdr[stage]);       // oy + 1, ox + 1, by_lo, by_n
         const int2 xr = *reinterpret_cast<const int2*>(stage_hdr[stage] + 4);    // bx_lo, bx_n
@@ -416,7 +426,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
-      if (++stage == kStages) {
+      if (++stage == (uint32_t)p.n_stages) {
         stage = 0;
         phase ^= 1u;
       }
