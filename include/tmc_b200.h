@@ -58,7 +58,7 @@ int tmc_moments_to_mean_std(const double* moments, float* mean_std, tmc_stream_t
 
 /* ---- movie preparation: examples/ttMotion.py:90-202,357 (gain_correct, remove_hot_pixels, set_frames_mean_zero, the
  *      cast to float32) for movies that arrive in their detector-native type ------------------------------------------- */
-/* src (t, n) of dtype 0 uint8 / 1 uint16 / 2 int16 / 3 float16 / 4 float32 -> dst (t, n) fp32, times gain (n, nullable);
+/* src (t, n) of dtype 0 uint8 / 1 uint16 / 2 int16 / 3 float16 / 4 float32 / 5 int8 -> dst (t, n) fp32, times gain (n, nullable);
  * moments (t, 2) double (nullable) = per-frame {sum, sum of squares} of the result */
 int tmc_convert_stack(const void* src, int dtype, int t, long n, const float* gain, float* dst, double* moments,
                       tmc_stream_t stream);

@@ -29,6 +29,7 @@ from .patch_grid import patch_grid_centers
 from .spline_grids import CubicBSplineGrid3d, CubicCatmullRomGrid3d
 from .pipeline import estimate_motion, motion_correct, motion_correct_many
 from .prepare import prepare_movie
+from .movie_io import mrc_movies, read_mrc, read_mrc_header, write_mrc
 from .utils import normalize_image
 
 __version__ = "0.1.0"
@@ -51,4 +52,8 @@ __all__ = [
     "motion_correct_many",
     "dose_weight",
     "prepare_movie",
+    "read_mrc",
+    "read_mrc_header",
+    "write_mrc",
+    "mrc_movies",
 ]

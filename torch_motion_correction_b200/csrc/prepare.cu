@@ -173,12 +173,13 @@ int blocks_per_frame(int t) {
 
 }  // namespace
 
-// src (t, n) in its native type (dtype 0 uint8, 1 uint16, 2 int16, 3 float16, 4 float32) -> dst (t, n) fp32, times
+// src (t, n) in its native type (dtype 0 uint8, 1 uint16, 2 int16, 3 float16, 4 float32, 5 int8) -> dst (t, n) fp32, times
 // gain (n) when given; moments (t, 2) double = per-frame {sum, sum of squares} of the result (nullable; zeroed here)
 TMC_API int tmc_convert_stack(const void* src, int dtype, int t, long n, const float* gain, float* dst, double* moments,
                               cudaStream_t stream) {
   TMC_CHECK_ARG(src && dst && t >= 1 && n >= 1, "convert_stack: bad arguments");
-  TMC_CHECK_ARG(dtype >= 0 && dtype <= 4, "convert_stack: dtype must be 0 (uint8), 1 (uint16), 2 (int16), 3 (float16) or 4 (float32)");
+  TMC_CHECK_ARG(dtype >= 0 && dtype <= 5,
+                "convert_stack: dtype must be 0 (uint8), 1 (uint16), 2 (int16), 3 (float16), 4 (float32) or 5 (int8)");
   if (moments) TMC_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * (size_t)t, stream));
   dim3 grid(blocks_per_frame(t), t);
   switch (dtype) {
@@ -186,6 +187,7 @@ TMC_API int tmc_convert_stack(const void* src, int dtype, int t, long n, const f
     case 1: TMC_TIMED("convert_stack_kernel", stream, convert_stack_kernel<unsigned short><<<grid, kPrepThreads, 0, stream>>>((const unsigned short*)src, n, gain, dst, moments)); break;
     case 2: TMC_TIMED("convert_stack_kernel", stream, convert_stack_kernel<short><<<grid, kPrepThreads, 0, stream>>>((const short*)src, n, gain, dst, moments)); break;
     case 3: TMC_TIMED("convert_stack_kernel", stream, convert_stack_kernel<__half><<<grid, kPrepThreads, 0, stream>>>((const __half*)src, n, gain, dst, moments)); break;
+    case 5: TMC_TIMED("convert_stack_kernel", stream, convert_stack_kernel<signed char><<<grid, kPrepThreads, 0, stream>>>((const signed char*)src, n, gain, dst, moments)); break;
     default: TMC_TIMED("convert_stack_kernel", stream, convert_stack_kernel<float><<<grid, kPrepThreads, 0, stream>>>((const float*)src, n, gain, dst, moments)); break;
   }
   TMC_CHECK_LAUNCH("tmc_convert_stack");

@@ -142,7 +142,7 @@ def motion_correct_many(host_movies, pixel_spacing: float, device=None, out_host
                         zero_frame_means=False, **kwargs):
     """Align a sequence of movies held in (ideally pinned) HOST memory; yields ``(sum_host, field)``.
 
-    Movies may arrive in their detector-native type (uint8 / uint16 / int16 / float16, or float32): they cross PCIe as
+    Movies may arrive in their detector-native type (uint8 / int8 / uint16 / int16 / float16, or float32): they cross PCIe as
     they are (1-2 bytes per pixel instead of 4) and are converted on the device, together with the optional preparation of
     ``prepare_movie`` (``gain`` multiply, hot-pixel replacement, per-frame mean removal; examples/ttMotion.py:90-202).
 

@@ -10,7 +10,7 @@ import torch
 from ._common import resolve_device
 from ._lib import call, ptr, query, stream_ptr
 
-DTYPE_CODES = {torch.uint8: 0, torch.uint16: 1, torch.int16: 2, torch.float16: 3, torch.float32: 4}
+DTYPE_CODES = {torch.uint8: 0, torch.uint16: 1, torch.int16: 2, torch.float16: 3, torch.float32: 4, torch.int8: 5}
 
 
 def oriented_gain(gain: torch.Tensor, flip_gain: int = 0, rot_gain: int = 0) -> torch.Tensor:
@@ -28,7 +28,7 @@ def oriented_gain(gain: torch.Tensor, flip_gain: int = 0, rot_gain: int = 0) -> 
 def prepare_movie(movie: torch.Tensor, gain: torch.Tensor | None = None, hot_pixel_threshold: float | None = None,
                   zero_frame_means: bool = False, device=None, out: torch.Tensor | None = None,
                   max_hot_pixels: int = 1 << 20, return_hot_pixel_count: bool = False):
-    """(t, h, w) movie of dtype uint8 / uint16 / int16 / float16 / float32 -> fp32 device tensor.
+    """(t, h, w) movie of dtype uint8 / int8 / uint16 / int16 / float16 / float32 -> fp32 device tensor.
 
     ``gain`` (h, w): multiplied in (``gain_correct``); ``hot_pixel_threshold``: pixels further than that many standard
     deviations from their frame's mean are replaced by a neighbour (``remove_hot_pixels``; the reference picks the
