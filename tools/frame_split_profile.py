@@ -52,11 +52,9 @@ def main():
         return motion_correct_frame_split(local_frames, px, f0, t, **kw)
 
     out = {}
-    for graph in ("1", "0"):
-        os.environ["TMC_SPLIT_GRAPH"] = graph
-        dist.barrier()
-        ms, wall, per = timed(split, _lib)
-        out[f"split_graph{graph}"] = {"device_ms": round(ms, 2), "wall_ms": round(wall, 2), "entries": per}
+    dist.barrier()
+    ms, wall, per = timed(split, _lib)
+    out["split"] = {"device_ms": round(ms, 2), "wall_ms": round(wall, 2), "entries": per}
     dist.barrier()
     if rank == 0:
         del local_frames

@@ -225,11 +225,7 @@ __device__ __forceinline__ Window make_window(const float* image, int frame, int
   const bool cols_masked = w.ox >= -x_margin && w.ox + NX <= W + x_margin;
   // plain reads of the first / last frame row with columns beyond the row would leave the movie buffer
   const bool buffer_end = (w.oy + ylo == 0 && w.ox < 0) || (w.oy + yhi == H && w.ox + NX > W);
-#ifdef TMC_NO_WRAP
-  w.wrap = false;
-#else
   w.wrap = !(rows_inside && (cols_inside || (cols_masked && !buffer_end)));
-#endif
   return w;
 }
 
@@ -905,8 +901,7 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
     if constexpr (MM == 1024 && !BB) {
       // polyphase path: four 256-point warp-level FFTs per row, only the band is ever formed
       if (yhi > ylo && kx_count <= 128 && job_mode != 0 && use_poly() && px.R == 1) {
-        int rows_per_cta = 32;
-        if (const char* e = getenv("TMC_POLY_ROWS")) rows_per_cta = atoi(e);  // experiment
+        int rows_per_cta = 32;  // measured on C2: 64 .. 256 rows per CTA change the row kernels by less than 2 %
         while (rows_per_cta > 8 && (long)tmc_div_up(yhi - ylo, rows_per_cta) * njobs < 148 * 6) rows_per_cta -= 8;
         dim3 grid(tmc_div_up(yhi - ylo, rows_per_cta), njobs);
         if (job_mode == 1) {

@@ -136,7 +136,7 @@ struct Params {
   float* out_sum;
   int accumulate_sum;
   int tiles_x, n_tiles;
-  int debug;  // TMC_WARP_TMA_DEBUG bits: 1 no image loads, 2 no lattice loads, 4 consumers skip the arithmetic
+  int debug;  // TMC_WARP_TMA_DEBUG: 4 = the consumers skip the arithmetic (times the memory pipeline alone)
   // constants of the coordinate chain, formed on the host so that they reach the arithmetic as constant-bank operands
   // (the kernel is bound by register-file reads: a register operand less per instruction is what counts)
   float2 nden, rcp, half_scale;  // .x = y axis, .y = x axis
