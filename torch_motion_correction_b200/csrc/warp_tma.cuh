@@ -74,6 +74,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// the same on 32-bit shared-window addresses formed once outside the loops (the generic -> shared conversion of a
+// __shared__ array element costs an S2R and two LEAs every time it is written inside a loop)
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ int4 lds_int4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int2 lds_int2(uint32_t addr) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
 // 3-D tiled tensor-map load: box at (c0, c1, c2) (innermost first) -> shared memory, completion on an mbarrier
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile(
@@ -262,6 +290,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
   const float2 nden = p.nden, rcp = p.rcp, half_scale = p.half_scale;
   const float2 inv_px = dup(p.inv_px);
   uint32_t stage = 0, phase = 0;
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), hdr0 = smem_u32(stage_hdr);
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int x0 = (tile % p.tiles_x) * kTX, y0 = (tile / p.tiles_x) * kTY;
     const int x = x0 + tx, y_base = y0 + tyg * kRows;
@@ -297,12 +326,12 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
     auto frames = [&](auto same_tag) {
     constexpr bool SAME = decltype(same_tag)::value;
     for (int f = 0; f < T; ++f) {
-      mbar_wait(&full_bar[stage], phase);
+      mbar_wait_addr(full0 + 8u * stage, phase);
       if (active && !(p.debug & 4)) {
         const float* simg = reinterpret_cast<const float*>(stages + (size_t)stage * p.stage_bytes);
         const float* srx = simg + kImgBytesPadded / 4;
-        const int4 org = *reinterpret_cast<const int4*>(stage_hdr[stage]);       // oy + 1, ox + 1, by_lo, by_n
-        const int2 xr = *reinterpret_cast<const int2*>(stage_hdr[stage] + 4);    // bx_lo, bx_n
+        const int4 org = lds_int4(hdr0 + 32u * stage);       // oy + 1, ox + 1, by_lo, by_n
+        const int2 xr = lds_int2(hdr0 + 32u * stage + 16u);  // bx_lo, bx_n
         float2 R[SAME ? 1 : kRows][4];
 #pragma unroll
         for (int r = 0; r < (SAME ? 1 : kRows); ++r)
@@ -425,7 +454,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap img_map, const __grid_consta
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (lane == 0) mbar_arrive_addr(empty0 + 8u * stage);
       if (++stage == (uint32_t)p.n_stages) {
         stage = 0;
         phase ^= 1u;
