@@ -196,10 +196,13 @@ def frame_split_record(dev, rank, world, steps, iterations, dist):
             "ms_per_movie": float(ms), "single_gpu_ms_per_movie": single_ms, "speedup_vs_1_gpu": single_ms / float(ms),
             "frame_sum_allreduce_ms": float(ar_ms), "frame_sum_allreduce_bytes": h * w * 4,
             "frame_sum_allreduce_busbw_gbs": h * w * 4 * 2 * (world - 1) / world / (float(ar_ms) * 1e-3) / 1e9,
-            # the optimiser runs patch-sharded (all frames of a share of the patches per rank): per iteration only the
-            # coefficient gradient is all-reduced; the band-limited spectra are exchanged once (XC: both mask powers; optimiser)
+            # patch XC and optimiser run patch-sharded (all frames of a share of the patches per rank): per iteration only the
+            # coefficient gradient is all-reduced; the band-limited spectra are exchanged once each (XC: both mask powers)
             "optimiser_allreduce_bytes_per_iteration": 2 * cfg["resolution"][0] * cfg["resolution"][1] * cfg["resolution"][2] * 4,
-            "spectra_allgather_bytes": 3 * t * g * band.plane_elems * 8,
+            # all-to-all: every rank keeps 1/world of its own planes and receives the rest of its patches' planes
+            "spectra_exchange": "all-to-all (frames -> patches)",
+            "spectra_total_bytes": 3 * t * g * band.plane_elems * 8,
+            "spectra_received_bytes_per_rank": int(3 * t * g * band.plane_elems * 8 * (world - 1) / world / world),
             "max_abs_field_diff_angstrom": float((field - want_field).abs().max()),
             "rel_l2_sum_diff": float(torch.linalg.norm(total - want_total) / torch.linalg.norm(want_total)),
         }

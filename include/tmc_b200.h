@@ -260,7 +260,11 @@ long tmc_local_steps_workspace_bytes(int g, int t, int nt);
 /* n_steps iterations (1 + 2 n_steps launches).  sum_norms (g) double = sum_t A_t; eval_base (t, g, 2) Angstrom; w_t (t, nt)
  * and w_sp (g, nhw): dense separable spline weights of the patch centres (time / space); patch_scale (rows, g), step i
  * uses row first_row + i; coef (2, nt, nhw).  mode 0: Adam update in place (step number first_row + i + 1),
- * loss_out[first_row + i]; mode 1 (n_steps == 1): gradient only -> grad_out (2, nt, nhw), loss_out[0]. */
+ * loss_out[first_row + i]; mode 1 (n_steps == 1): gradient only -> grad_out (2, nt, nhw), loss_out[0];
+ * modes 2 / 3 (n_steps == 1; one movie split over several GPUs, the caller all-reduces grad_out between calls and keeps the
+ * workspace of the preceding mode 1 / 2 call untouched): mode 2 = Adam step number first_row on the gradient found in
+ * grad_out, then gradient and loss_out[0] of the updated coefficients under patch_scale row first_row; mode 3 = that Adam
+ * step only. */
 int tmc_local_steps(const void* tiled, const int* tiles, int n_tiles, int g, int t, int ny, int nx, int ky_count,
                     int kx_count, int ky_start, const double* sum_norms, const float* eval_base, const float* w_t,
                     const float* w_sp, int nt, int nhw, const float* patch_scale, float pixel_spacing, int loss_type,

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from torch_motion_correction_b200.distributed import all_gather_frames, frame_range
+from torch_motion_correction_b200.distributed import _reshard_frames_to_patches, all_gather_frames, frame_range
 
 
 def _free_port():
@@ -70,6 +70,11 @@ def _reshard_worker(rank, world, port, t, g, out_dir):
         g0, g1 = frame_range(g, rank, world)
         mine = gathered[:, g0:g1].permute(1, 0, 2).contiguous()  # (G_r, T, words)
         assert mine.shape == (g1 - g0, t, words)
+        # the product's exchange (all-to-all of the planes each peer owns) delivers exactly that block
+        tp = 2 * ((t + 1) // 2)
+        sub = torch.zeros((max(g1 - g0, 1), tp, words))
+        _reshard_frames_to_patches(full[f0:f1].contiguous(), sub, t, g, words, rank, world, None)
+        assert torch.equal(sub[: g1 - g0, :t], mine) and float(sub[:, t:].abs().sum()) == 0.0
         # every patch is owned by exactly one rank
         owned = torch.zeros(g)
         owned[g0:g1] = 1

@@ -109,7 +109,9 @@ __device__ __forceinline__ float2 fast_cis(float x) {
 }
 
 // ---- the coefficient kernel -------------------------------------------------------------------------------------------
-// flags: 1 = backward (gradient, loss, re-arm), 2 = Adam update, 4 = shifts of the (updated) coefficients
+// flags: 1 = backward (gradient, loss, re-arm), 2 = Adam update with that gradient, 4 = shifts of the (updated)
+// coefficients, 8 = Adam update with the gradient found in grad_out (complete: all-reduced over the ranks of a
+// frame-split movie by the caller), before the shifts
 // dynamic shared memory (floats): grad_shifts 2GT | eval_base 2GT | W_t T nt | W_sp G nhw | coef 2 nt nhw | u G 2 nt |
 // exp_avg, exp_avg_sq 2 nt nhw each
 // Everything the kernel reads is staged with one batch of independent loads (one memory latency), the rest is
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(kCoefThreads) local_coefficient_kernel(const S
   if (flags & 1)
     for (int i = tid; i < ngt; i += kCoefThreads) gs_s[i] = p.grad_shifts[i] * neg_inv_px;  // dL/d eval_new = -(1/px) dL/ds
   for (int i = tid; i < ncoef; i += kCoefThreads) coef_s[i] = p.coef[i];
-  if (flags & 2)
+  if (flags & (2 | 8))
     for (int i = tid; i < ncoef; i += kCoefThreads) {
       ea_s[i] = p.exp_avg[i];
       eas_s[i] = p.exp_avg_sq[i];
@@ -204,6 +206,24 @@ __global__ void __launch_bounds__(kCoefThreads) local_coefficient_kernel(const S
       }
     }
     __syncthreads();  // coef_s updated, u_s (as gu) consumed
+  }
+  if (flags & 8) {
+    // torch.optim.Adam on the gradient the caller completed (same formulas as above)
+    const float step_size = p.step_size, bc2_sqrt = p.bc2_sqrt, w1 = p.w1, w2 = p.w2, b2 = p.b2, epsf = p.epsf;
+    for (int o = tid; o < ncoef; o += kCoefThreads) {
+      float gr = p.grad_out[o];
+      float par = coef_s[o];
+      if (p.weight_decay != 0.f) gr = __fadd_rn(gr, __fmul_rn(p.weight_decay, par));
+      const float m = __fadd_rn(ea_s[o], __fmul_rn(w1, __fsub_rn(gr, ea_s[o])));
+      const float v = __fadd_rn(__fmul_rn(eas_s[o], b2), __fmul_rn(w2, __fmul_rn(gr, gr)));
+      p.exp_avg[o] = m;
+      p.exp_avg_sq[o] = v;
+      const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), epsf);
+      par = __fadd_rn(par, __fmul_rn(-step_size, __fdiv_rn(m, denom)));
+      p.coef[o] = par;
+      coef_s[o] = par;
+    }
+    __syncthreads();
   }
   if (!(flags & 4)) return;
   // u[g][c][k] = sum_j W_sp[g][j] coef[c][k][j]
@@ -477,8 +497,9 @@ TMC_API int tmc_local_steps(const void* tiled, const int* tiles, int n_tiles, in
                             void* workspace, cudaStream_t stream) {
   TMC_CHECK_ARG(tiled && tiles && sum_norms && eval_base && w_t && w_sp && patch_scale && coef && loss_out && grad_out && workspace,
                 "local_steps: null pointer");
+  TMC_CHECK_ARG(mode >= 0 && mode <= 3, "local_steps: mode must be 0 .. 3");
   TMC_CHECK_ARG(mode == 1 || (exp_avg && exp_avg_sq), "local_steps: Adam state missing");
-  TMC_CHECK_ARG(mode == 0 || n_steps == 1, "local_steps: gradient-only mode takes one step");
+  TMC_CHECK_ARG(mode == 0 || n_steps == 1, "local_steps: modes 1 .. 3 take one step");
   TMC_CHECK_ARG(n_tiles >= 1 && n_steps >= 1 && first_row >= 0 && pixel_spacing > 0.f && (loss_type == 0 || loss_type == 1),
                 "local_steps: bad arguments");
   if (!tmc_local_steps_supported(g, t, nt, nhw)) {
@@ -522,7 +543,7 @@ TMC_API int tmc_local_steps(const void* tiled, const int* tiles, int n_tiles, in
   p.grad_shifts = wf + 2l * g * t;
   const long floats = (4l * g * t + 1) & ~1l;
   p.q = (double*)(wf + floats);
-  TMC_CUDA(cudaMemsetAsync(workspace, 0, (size_t)tmc_local_steps_workspace_bytes(g, t, nt), stream));
+  if (mode < 2) TMC_CUDA(cudaMemsetAsync(workspace, 0, (size_t)tmc_local_steps_workspace_bytes(g, t, nt), stream));
   const size_t smem = tile_smem_bytes(t), csmem = coef_smem_bytes(g, t, nt, nhw);
   // per-device attributes: set on every call (cheap) so whichever device is current is configured
   TMC_CUDA(cudaFuncSetAttribute(local_loss_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
@@ -530,8 +551,18 @@ TMC_API int tmc_local_steps(const void* tiled, const int* tiles, int n_tiles, in
   dim3 grid(n_tiles, g);
   p.patch_scale = patch_scale + (long)first_row * g;
   p.loss_out = loss_out;
-  local_coefficient_kernel<<<1, kCoefThreads, csmem, stream>>>(p, 4);  // shifts of the current coefficients
+  if (mode >= 2) {
+    // Adam step number first_row on the caller's (all-reduced) gradient [+ the shifts of the updated coefficients]
+    const double step = (double)first_row;
+    p.step_size = (float)(lr / (1.0 - pow(beta1, step)));
+    p.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, step));
+  }
+  local_coefficient_kernel<<<1, kCoefThreads, csmem, stream>>>(p, mode == 2 ? (8 | 4) : (mode == 3 ? 8 : 4));
   tmc_count_launch();
+  if (mode == 3) {
+    TMC_CHECK_LAUNCH("tmc_local_steps");
+    return TMC_OK;
+  }
   // the loss kernel is a programmatic dependent of the coefficient kernel before it: its CTAs become resident and
   // start their bulk copies while the (single-CTA) coefficient kernel still runs
   cudaLaunchAttribute attr[1];
@@ -561,7 +592,7 @@ TMC_API int tmc_local_steps(const void* tiled, const int* tiles, int n_tiles, in
     TMC_CUDA(cudaLaunchKernelEx(&cfg, local_loss_tile_kernel, p));
     tmc_count_launch();
     const int last = i == n_steps - 1;
-    TMC_CUDA(cudaLaunchKernelEx(&ccfg, local_coefficient_kernel, p, mode == 0 ? (last ? 3 : 7) : 1));
+    TMC_CUDA(cudaLaunchKernelEx(&ccfg, local_coefficient_kernel, p, mode == 0 ? (last ? 3 : 7) : 1));  // modes 1, 2: backward only
     tmc_count_launch();
   }
   TMC_CHECK_LAUNCH("tmc_local_steps");

@@ -63,6 +63,59 @@ def all_gather_frames(local: torch.Tensor, total_frames: int, group=None) -> tor
     return torch.cat(out, dim=0)
 
 
+def _reshard_frames_to_patches(spec, spec_sub, t, g, words, rank, world, group, frame_major=False):
+    """spec (t_local, G, words): every patch of this rank's frames -> every frame of this rank's patches, written to
+    spec_sub[:, :t] (G_r, T, words) or, ``frame_major``, to spec_sub[:t, :G_r] (T, G_r, words).  An all-to-all: every rank
+    sends each peer only the planes of that peer's patches (1/world of what an all-gather would deliver to everybody);
+    falls back to the all-gather where the backend has no all-to-all."""
+    g0, g1 = frame_range(g, rank, world)
+
+    def put(f0, f1, block):  # block (f1 - f0, G_r, words)
+        if frame_major:
+            spec_sub[f0:f1, : g1 - g0] = block
+        else:
+            spec_sub[: g1 - g0, f0:f1] = block.permute(1, 0, 2)
+
+    if world == 1:
+        if g1 > g0:
+            put(0, t, spec)
+        return
+    t_local = spec.shape[0]
+    frames_of = [frame_range(t, r, world) for r in range(world)]
+    patches_of = [frame_range(g, r, world) for r in range(world)]
+    try:
+        send = torch.cat([spec[:, a:b].reshape(-1) for a, b in patches_of]) if t_local > 0 else spec.reshape(-1)
+        in_splits = [t_local * (b - a) * words for a, b in patches_of]
+        out_splits = [(f1 - f0) * (g1 - g0) * words for f0, f1 in frames_of]
+        recv = torch.empty((sum(out_splits),), dtype=spec.dtype, device=spec.device)
+        dist.all_to_all_single(recv, send, out_splits, in_splits, group=group)
+        offset = 0
+        for (f0, f1), n in zip(frames_of, out_splits):
+            if n:
+                put(f0, f1, recv[offset : offset + n].view(f1 - f0, g1 - g0, words))
+            offset += n
+    except (RuntimeError, NotImplementedError):
+        full = all_gather_frames(spec, t, group)  # (T, G, words) on every rank
+        if g1 > g0:
+            put(0, t, full[:, g0:g1])
+
+
+def _all_gather_patches(local, g, rank, world, group):
+    """(t, G_r, c) blocks of consecutive patch ranges (frame_range(g, r, world)) -> (t, G, c) on every rank."""
+    if world == 1:
+        return local
+    g_max = -(-g // world)
+    padded = torch.zeros((local.shape[0], g_max, local.shape[2]), dtype=local.dtype, device=local.device)
+    padded[:, : local.shape[1]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    out = []
+    for r in range(world):
+        a, b = frame_range(g, r, world)
+        out.append(parts[r][:, : b - a])
+    return torch.cat(out, dim=1)
+
+
 def stack_stats_frame_split(local_frames: torch.Tensor, group=None) -> torch.Tensor:
     """normalize_image statistics of the WHOLE movie from per-rank moments (24 bytes all-reduced)."""
     moments = _ops.stack_moments(local_frames)
@@ -123,8 +176,9 @@ def estimate_patch_motion_frame_split(local_frames, pixel_spacing, frame_offset,
                                       outlier_rejection=True, outlier_threshold=3.0, group=None, whole_pixel_field=False):
     """``estimate_motion_cross_correlation_patches`` (``mean_except_current``) for a frame-split movie.
 
-    Each rank transforms the patches of its own frames; the band-limited spectra (both mask powers,
-    quirk Q1) are all-gathered so every rank can form the leave-one-out references of its frames."""
+    Each rank transforms the patches of its own frames; the band-limited spectra (both mask powers, quirk Q1) are
+    re-sharded by patch (all-to-all) so that every rank forms the leave-one-out references and peaks of ALL frames of its
+    share of the patches; the shifts are all-gathered."""
     rank, world = _world(group)
     dev = local_frames.device
     t_local, h, w = local_frames.shape
@@ -161,17 +215,27 @@ def estimate_patch_motion_frame_split(local_frames, pixel_spacing, frame_offset,
     jobs = cached_device_tensor(
         ("split_xc_jobs", (t_local, h, w, p)),
         lambda: torch.tensor([[k, 1, k, 2, y0, x0] for k in range(t_local) for (y0, x0) in origins], dtype=torch.int32), dev)
-    spec_local = plan.forward(source, source_stats, mask, ylo, yhi, jobs, job_mode=1, frame_shifts=frame_shifts).view(t_local, g * 2 * plan.plane_elems * 2)
-    spec_all = all_gather_frames(spec_local, t, group)
+    words = 2 * plan.plane_elems * 2  # both mask powers of one (frame, patch), float32 words
+    spec_local = plan.forward(source, source_stats, mask, ylo, yhi, jobs, job_mode=1, frame_shifts=frame_shifts).view(t_local, g, words)
+    # frames for the transforms, patches for the cross-correlation: every rank receives ALL frames of ITS share of the
+    # patches (all-to-all, 1/world of an all-gather), forms their leave-one-out references and peaks, and the shifts
+    # (KBs) are gathered
+    g0, g1 = frame_range(g, rank, world)
+    g_sub = g1 - g0
+    spec_sub = torch.zeros((t, max(g_sub, 1), words), dtype=torch.float32, device=dev)
+    _reshard_frames_to_patches(spec_local, spec_sub, t, g, words, rank, world, group, frame_major=True)
+    del spec_local
+
     def schedule(part):
         offsets, deltas = _aliasing_schedule(t, "mean_except_current", t // 2)
         return torch.tensor(offsets if part == 0 else (deltas if deltas else [0]), dtype=torch.int32)
 
     d_off = cached_device_tensor(("xc_delta_offsets", t), lambda: schedule(0), dev)  # same keys as estimate_motion_xc
     d_val = cached_device_tensor(("xc_deltas", t), lambda: schedule(1), dev)
-    prod = _fourier.leave_one_out_products(spec_all, t, g, plan.plane_elems, d_off, d_val, frame_offset, t_local)
-    shifts = plan.peaks(prod.view(t_local * g, plan.ky, plan.kx, 2), sub_pixel=bool(sub_pixel_refinement))
-    shifts = all_gather_frames(shifts.view(t_local, g * 2), t, group).contiguous()
+    gs = max(g_sub, 1)
+    prod = _fourier.leave_one_out_products(spec_sub, t, gs, plan.plane_elems, d_off, d_val)
+    shifts = plan.peaks(prod.view(t * gs, plan.ky, plan.kx, 2), sub_pixel=bool(sub_pixel_refinement))
+    shifts = _all_gather_patches(shifts.view(t, gs, 2)[:, :g_sub], g, rank, world, group).contiguous()
     scratch = torch.empty_like(field)
     with torch.cuda.device(dev):
         call("tmc_xc_postprocess", ptr(shifts), t, g, float(pixel_spacing), -1, int(bool(outlier_rejection)),
@@ -277,16 +341,13 @@ def estimate_local_motion_frame_split(local_frames, pixel_spacing, patch_shape, 
         spec = spec.view(pairs, g, 2, words).permute(0, 2, 1, 3).reshape(2 * pairs, g, words)[:t_local].contiguous()
     else:
         spec = torch.zeros((0, g, words), dtype=torch.float32, device=dev)
-    full = all_gather_frames(spec, t, group)  # (T, G, words) on every rank: a few % of the movie
-    del spec
     # this rank's share of the patches, all frames: (G_r, tp, KY, KX)
     g0, g1 = frame_range(g, rank, world)
     g_sub = g1 - g0
     tp = 2 * ((t + 1) // 2)
     spec_sub = torch.zeros((max(g_sub, 1), tp, words), dtype=torch.float32, device=dev)
-    if g_sub > 0:
-        spec_sub[:, :t] = full[:, g0:g1].permute(1, 0, 2)
-    del full
+    _reshard_frames_to_patches(spec, spec_sub, t, g, words, rank, world, group)
+    del spec
 
     # normalised (t, y, x) centres of this rank's patches, time-major (T, G_r, 3)
     norm = centers.clone().float()
@@ -323,25 +384,34 @@ def estimate_local_motion_frame_split(local_frames, pixel_spacing, patch_shape, 
     exp_avg, exp_avg_sq = torch.zeros_like(new), torch.zeros_like(new)
     lr, (b1, b2) = float(kw.get("lr", 0.01)), kw.get("betas", (0.9, 0.999))
     eps, wd = float(kw.get("eps", 1e-08)), float(kw.get("weight_decay", 0))
-    counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+    steps = torch.arange(max(n_iterations, 1), dtype=torch.int32, device=dev)  # Adam's step number - 1 of every iteration
     losses = []
+    def reduce_gradient(loss, grad):
+        if world > 1:
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+        if return_losses:
+            total = loss.clone()
+            if world > 1:
+                dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+            losses.append(total)
+
     with torch.cuda.device(dev):
         stream = stream_ptr(dev)
-        for i in range(n_iterations):
-            if problem.fused:
-                loss, grad = problem.loss_and_grad(new, scales_sub, row=i)
-            else:
+        if problem.fused:
+            # three launches and one all-reduce per iteration: [Adam on the reduced gradient + next shifts] -> loss /
+            # gradient kernel -> backward to the coefficient gradient (tmc_local_steps modes 1, 2, 3)
+            adam = (exp_avg, exp_avg_sq, lr, float(b1), float(b2), eps, wd)
+            for i in range(n_iterations):
+                problem.fused_steps(new, scales_sub, i, 1, 1 if i == 0 else 2, problem.loss, adam=adam)
+                reduce_gradient(problem.loss, problem.grad)
+            if n_iterations > 0:
+                problem.fused_steps(new, scales_sub, n_iterations, 1, 3, problem.loss, adam=adam)
+        else:
+            for i in range(n_iterations):
                 loss, grad = problem.loss_and_grad(new, scales_sub[i])
-            if world > 1:
-                dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
-            if return_losses:
-                total = loss.clone()
-                if world > 1:
-                    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
-                losses.append(total)
-            call("tmc_adam_step", ptr(new), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), new.numel(), lr, float(b1), float(b2), eps, wd,
-                 ptr(counter), stream)
-            call("tmc_advance_counter", ptr(counter), stream)
+                reduce_gradient(loss, grad)
+                call("tmc_adam_step", ptr(new), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), new.numel(), lr, float(b1), float(b2), eps,
+                     wd, steps.data_ptr() + 4 * i, stream)
     final = (new + base).contiguous()
     with torch.cuda.device(dev):
         call("tmc_subtract_mean", ptr(final), final.numel(), stream_ptr(dev))
