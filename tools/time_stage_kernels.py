@@ -7,7 +7,8 @@ import torch_motion_correction_b200 as tmc
 from torch_motion_correction_b200 import _lib
 
 dev = torch.device("cuda:0")
-movie, _ = bench.synthetic_movie_gpu(40, 4096, 4096, 1000, dev)
+size = int(os.environ.get("TMC_TIME_SIZE", "4096"))  # 8192: BASELINE config 4's frame size
+movie, _ = bench.synthetic_movie_gpu(40, size, size, 1000, dev)
 for _ in range(2):
     tmc.motion_correct(movie, 0.83, n_iterations=20)
 torch.cuda.synchronize()
