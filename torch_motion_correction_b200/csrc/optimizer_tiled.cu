@@ -285,8 +285,11 @@ __global__ void __launch_bounds__(kTileThreads) local_loss_tile_kernel(const Ste
   const int ty = __ldg(p.tiles + 2 * tile_id), tx = __ldg(p.tiles + 2 * tile_id + 1);
   // frequency factors fp32(-2 pi) * fp32(k * fp32(1/n)) (torch_fourier_shift on torch.fft.fftfreq grids) of the tile's
   // 8 rows and 16 columns (clamped inside the band box: the padding holds zeros); every thread forms the one it needs
-  // for the phase table below, threads 224..247 also publish the table for the gradient factors
-  const int my_r = tid < 128 ? (tid & 7) : kTileKy + (tid & 15);  // phase-table slot of this thread (see the loops below)
+  // for the phase table below; one thread per slot also publishes it (cf[24]) for the gradient factors
+  // phase-table slot of this thread (see the loops below): 96 threads share the 8 rows, 160 threads the 16 columns, so that
+  // both halves of the table take the same number of sweeps over the frames (T = 40: 4 and 4 instead of 3 and 5)
+  constexpr int kRowThreads = 96;
+  const int my_r = tid < kRowThreads ? (tid & 7) : kTileKy + ((tid - kRowThreads) & 15);
   float my_cf;
   {
     if (my_r < kTileKy) {
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(kTileThreads) local_loss_tile_kernel(const Ste
       my_cf = __fmul_rn(-6.283185307179586f, __fmul_rn((float)min(tx * kTileKx + my_r - kTileKy, p.KX - 1), p.inv_nx));
     }
     if (tid < kTileKy) cf[tid] = my_cf;
-    if (tid >= 128 && tid < 128 + kTileKx) cf[kTileKy + tid - 128] = my_cf;
+    if (tid >= kRowThreads && tid < kRowThreads + kTileKx) cf[kTileKy + tid - kRowThreads] = my_cf;
   }
   sigma[tid] = 0.f;
   // everything above is independent of the coefficient kernel that precedes this launch (programmatic dependent
@@ -310,18 +313,18 @@ __global__ void __launch_bounds__(kTileThreads) local_loss_tile_kernel(const Ste
     for (int c = 0; c < nchunks; ++c) mbar_wait(bars + c, 0);
     return;
   }
-  // phase factors exp(i c f_y s_y) of the 8 rows (duplicated for the packed arithmetic: threads 0..127, 16 frames per
-  // sweep) and exp(i c f_x s_x) of the 8 column pairs (threads 128..255, 8 frames per sweep), every frame; the shifts
+  // phase factors exp(i c f_y s_y) of the 8 rows (duplicated for the packed arithmetic: threads 0..95, 12 frames per
+  // sweep) and exp(i c f_x s_x) of the 8 column pairs (threads 96..255, 10 frames per sweep), every frame; the shifts
   // come straight from the coefficient kernel's (G, T, 2) table
   const float* shg = p.shifts + (long)g * T * 2;
-  if (tid < 128) {
-    for (int t = tid >> 3; t < T; t += 16) {
+  if (tid < kRowThreads) {
+    for (int t = tid >> 3; t < T; t += kRowThreads / 8) {
       const float2 e = fast_cis(__fmul_rn(my_cf, shg[2 * t]));
       Ey[t * 8 + my_r] = make_float4(e.x, e.x, e.y, e.y);
     }
   } else {
-    const int j = tid & 15;
-    for (int t = (tid - 128) >> 4; t < T; t += 8) {
+    const int j = (tid - kRowThreads) & 15;
+    for (int t = (tid - kRowThreads) >> 4; t < T; t += (kTileThreads - kRowThreads) / 16) {
       const float2 e = fast_cis(__fmul_rn(my_cf, shg[2 * t + 1]));
       float* o = reinterpret_cast<float*>(Ex + t * 8 + (j >> 1)) + (j & 1);
       o[0] = e.x;
