@@ -386,15 +386,8 @@ __global__ void __launch_bounds__(kTileThreads) local_loss_tile_kernel(const Ste
     // gy += S_im (cfy w Sig_re) - S_re (cfy w Sig_im); the same with cfx
     Cy[pb] = make_float4(cfy * wr0, cfy * wr1, -cfy * wi0, -cfy * wi1);
     Cx[pb] = make_float4(cfx0 * wr0, cfx1 * wr1, -cfx0 * wi0, -cfx1 * wi1);
-    double v = (double)w0 * ((double)re.x * re.x + (double)im.x * im.x) + (double)w1 * ((double)re.y * re.y + (double)im.y * im.y);
-    v = warp_sum(v);
-    if ((tid & 31) == 0) red[tid >> 5] = v;
   }
-  __syncthreads();  // Ctab, red complete
-  if (tid == 0) {
-    const double v = red[0] + red[1];
-    if (v != 0.0) atomicAdd(p.q + g, v);
-  }
+  __syncthreads();  // Ctab complete
 
   // pass 2: half-warp per frame, lane = 2 adjacent bins, 4 steps over the 128 bins
   float bscale;
@@ -430,6 +423,17 @@ __global__ void __launch_bounds__(kTileThreads) local_loss_tile_kernel(const Ste
       v *= -2.0f * bscale;
       if (v != 0.f) atomicAdd(p.grad_shifts + ((long)g * T + t) * 2 + (keep_x ? 1 : 0), v);
     }
+  }
+  // q_g += sum_bins w |Sigma|^2 (the loss value; double): after the gradient pass, off the critical path of the CTA
+  if (tid < 64) {
+    const int pb = tid;
+    const float2 re = make_float2(sigma[pb], sigma[64 + pb]), im = make_float2(sigma[128 + pb], sigma[192 + pb]);
+    const int kx0 = tx * kTileKx + 2 * (pb & 7);
+    const float w0 = (p.loss_type == 0 || kx0 == 0 || 2 * kx0 == p.nx) ? 1.0f : 2.0f;
+    const float w1 = (p.loss_type == 0 || 2 * (kx0 + 1) == p.nx) ? 1.0f : 2.0f;
+    double v = (double)w0 * ((double)re.x * re.x + (double)im.x * im.x) + (double)w1 * ((double)re.y * re.y + (double)im.y * im.y);
+    v = warp_sum(v);
+    if ((tid & 31) == 0 && v != 0.0) atomicAdd(p.q + g, v);
   }
 }
 
