@@ -246,6 +246,30 @@ def test_global_motion_k3_frame_size(dev):
     assert float((got.cpu() - want).abs().max()) <= 1e-5
 
 
+def test_half_length_row_transforms_agree_with_the_full_length_kernels(dev, monkeypatch):
+    """4096-point rows of frame pairs: two 2048-point transforms of pixel pairs (rows_forward_real2n, the default) against
+    one 4096-point transform of the packed pair (TMC_FFT_REAL2N=0) and against torch.fft; odd window origins take the
+    4-byte load path, an odd frame count the single-frame job."""
+    n = 4096
+    g = torch.Generator().manual_seed(23)
+    movie = (torch.randn((3, 700, n + 8), generator=g) * 2.0 + 1.0).to(dev)
+    plan = _fourier.BandPlan(512, n, dev, 0.83, 500, (300, 10))
+    mask, ylo, yhi = _fourier.soft_disc_mask((512, n), 128.0, 64.0, dev)
+    jobs = torch.tensor([[0, 1, 1, 1, 100, 4], [2, 1, -1, 1, 37, 5]], dtype=torch.int32).to(dev)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TMC_FFT_REAL2N", flag)
+        out[flag] = as_complex(plan.forward(movie, None, mask, ylo, yhi, jobs, job_mode=2)).clone()
+    scale = float(out["0"].abs().max())
+    assert float((out["1"][:3] - out["0"][:3]).abs().max()) <= 5e-6 * scale
+    ky = (torch.arange(plan.ky, device=dev) + plan.ky_start) % 512
+    for plane, (f, y0, x0) in ((0, (0, 100, 4)), (1, (1, 100, 4)), (2, (2, 37, 5))):
+        want = torch.fft.rfftn((movie[f, y0 : y0 + 512, x0 : x0 + n] * mask).double(), dim=(-2, -1))[ky][:, : plan.kx]
+        want = want * plan.weight.double()
+        err = (out["1"][plane].to(torch.complex128) - want).abs().max() / want.abs().max()
+        assert float(err) < 5e-6, (plane, float(err))
+
+
 def test_global_motion_non_power_of_two_frames(dev):
     """96x80 frames (Bluestein on both axes) recover known integer drifts exactly."""
     movie, walk = rp.synthetic_movie(6, 96, 80, seed=2, noise=0.3, drift=4.0, integer_shifts=True, sigma_f=0.1)

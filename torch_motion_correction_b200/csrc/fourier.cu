@@ -630,6 +630,14 @@ inline bool use_poly() {
   return on;
 }
 
+// rows of two frames as half-length transforms of pixel pairs (rows_forward_real2n) for 8192- and 4096-point rows;
+// TMC_FFT_REAL2N=0 selects the full-length kernels (A/B testing; read per call: tests toggle it).  Measured, 40 frames:
+// 8192^2 12.4 -> 4.7 ms, 4096^2 1.28 -> 1.20 ms.
+inline bool use_real2n(int) {
+  const char* e = getenv("TMC_FFT_REAL2N");
+  return !(e && e[0] == '0');
+}
+
 // TMC_FFT_COL_QUADS=0 selects the one-column-per-CTA kernel for 4096-point whole-frame columns (A/B testing)
 inline bool use_col_quads() {
   const char* e = getenv("TMC_FFT_COL_QUADS");
@@ -917,6 +925,24 @@ TMC_API int tmc_rfft2_band(const float* image, int t, int h, int w, const float*
                         image, h, w, mean_std, mask, jobs, frame_shifts, x_margin, ylo, yhi, ny, kx_count, px.tw, (float2*)tmp,
                         rows_per_cta));
         }
+        return TMC_OK;
+      }
+    }
+    if constexpr ((MM == 8192 || MM == 4096) && !BB) {
+      // rows of two frames as two half-length complex transforms of pixel pairs instead of one full-length transform
+      // of a packed pair (the 8192-point kernel is confined to one 8-warp CTA per SM)
+      if (yhi > ylo && job_mode == 2 && px.R == 1 && kx_count <= MM / 2 && use_real2n(MM)) {
+        constexpr int NH = MM / 2;
+        constexpr int B = fft2::Cfg<NH>::B;
+        int rows_per_cta = B * 4;
+        while (rows_per_cta > B && (long)tmc_div_up(yhi - ylo, rows_per_cta) * njobs < 148 * 8) rows_per_cta -= B;
+        dim3 grid(tmc_div_up(yhi - ylo, rows_per_cta), njobs);
+        constexpr size_t smem = rows_forward_real2n_smem_bytes<NH>();
+        if (int e = enable_smem(rows_forward_real2n<NH>, smem)) return e;
+        TMC_TIMED(MM == 8192 ? "rows_forward_real2n<4096>" : "rows_forward_real2n<2048>", stream,
+                  rows_forward_real2n<NH><<<grid, fft2::kThreads, smem, stream>>>(image, h, w, mean_std, mask, jobs, frame_shifts, x_margin,
+                                                                                   ylo, yhi, ny, kx_count, px.tw, (float2*)tmp,
+                                                                                   rows_per_cta));
         return TMC_OK;
       }
     }

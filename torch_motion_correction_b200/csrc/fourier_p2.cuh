@@ -125,6 +125,118 @@ rows_forward_p2(const float* __restrict__ image, int H, int W, const float* __re
   }
 }
 
+// ---- forward rows of length 2N as N-point complex transforms (one real row per transform) -------------------------
+//
+// x[0 .. 2N) real, z[m] = x[2m] + i x[2m+1], Z = DFT_N(z):  X[k] = E[k] + W_2N^k O[k] with
+// E[k] = (Z[k] + conj Z[N-k]) / 2 (spectrum of the even samples), O[k] = (Z[k] - conj Z[N-k]) / 2i (odd samples).
+// Same job format and output as rows_forward_p2<2N, 2> (two frames per job, mask power 1), but the two frames are two
+// N-point transforms instead of one 2N-point transform of a packed pair: the 8192-point kernel holds 32 values per thread
+// and 168 KB of shared memory (one 8-warp CTA per SM); this one runs in the 4096-point configuration (two CTAs per SM)
+// and reads pixel PAIRS (8-byte loads).  tw2n: the W_2N^m table of the 2N-point plan; needs KX <= N.
+__device__ __forceinline__ void cp_async_f32x2_any(float2* smem_dst, const float2* gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(gmem_src));
+}
+
+template <int N>
+constexpr size_t rows_forward_real2n_smem_bytes() {
+  return fft2::Cfg<N>::smem_bytes + 2ull * fft2::Cfg<N>::B * N * sizeof(float2);
+}
+
+template <int N>
+__global__ void __launch_bounds__(fft2::kThreads, N >= 2048 ? 2 : 1)
+rows_forward_real2n(const float* __restrict__ image, int H, int W, const float* __restrict__ mean_std,
+                    const float* __restrict__ mask, const int* __restrict__ jobs, const int* __restrict__ frame_shifts,
+                    int x_margin, int ylo, int yhi, int NY, int KX, const float2* __restrict__ tw2n,
+                    float2* __restrict__ tmp, int rows_per_cta) {
+  using C = fft2::Cfg<N>;
+  using P = fft2::Plan<N>;
+  extern __shared__ float2 smem[];
+  const fft2::Smem<N> sm(smem);
+  // W_N^m = W_2N^{2m}: the factorised tables of the N-point transform from the 2N-point plan
+  for (int i = threadIdx.x; i < 64 + C::TW_HI; i += fft2::kThreads)
+    sm.tw_lo[i] = i < 64 ? __ldg(tw2n + 2 * i) : __ldg(tw2n + 2 * (i - 64) * 64);
+  const int seq = threadIdx.x / C::TPS, j = threadIdx.x % C::TPS;
+  float2* myseq = sm.data + seq * C::STRIDE;
+  float2* stage_p = smem + C::B * C::STRIDE + 64 + C::TW_HI;  // pixel pairs, slot e * kThreads + threadIdx.x
+  float2* stage_m = stage_p + C::B * N;                        // mask pairs of the same row
+  const int job = blockIdx.y;
+  const int fa = jobs[job * 6 + 0], fb = jobs[job * 6 + 2];
+  const int y0 = jobs[job * 6 + 4], x0 = jobs[job * 6 + 5];
+  float mean = 0.f, inv_std = 1.f;
+  if (mean_std != nullptr) {
+    mean = __ldg(mean_std);
+    inv_std = 1.0f / __ldg(mean_std + 1);
+  }
+  const Window wa = make_window(image, fa, y0, x0, frame_shifts, H, W, ylo, yhi, 2 * N, x_margin);
+  const Window wb = make_window(image, fb >= 0 ? fb : fa, y0, x0, frame_shifts, H, W, ylo, yhi, 2 * N, x_margin);
+  const int halves = fb >= 0 ? 2 : 1;
+  const int row_begin = ylo + blockIdx.x * rows_per_cta;
+  const int row_end = min(yhi, row_begin + rows_per_cta);
+  const int nunits = row_end > row_begin ? ((row_end - row_begin + C::B - 1) / C::B) * halves : 0;
+  float2* plane_a = tmp + (long)(2 * job) * NY * KX;
+
+  auto prefetch = [&](int u) {
+    const int y = row_begin + (u / halves) * C::B + seq;
+    if (y >= row_end) return;
+    const bool second = (u % halves) == 1;
+    const Window& wd = second ? wb : wa;
+    const float* row = wd.fast_base(W) + (long)y * W;
+    const bool pair_ok = !wd.wrap && (reinterpret_cast<uintptr_t>(row) & 7) == 0;
+#pragma unroll
+    for (int e = 0; e < C::VPT; ++e) {
+      const int x = 2 * P::First::in_index(j, e / P::First::R, e % P::First::R);
+      const int slot = e * fft2::kThreads + threadIdx.x;
+      if (pair_ok) {
+        cp_async_f32x2_any(stage_p + slot, reinterpret_cast<const float2*>(row + x));
+      } else {
+        float* dst = reinterpret_cast<float*>(stage_p + slot);
+        cp_async_f32(dst, wd.wrap ? wd.wrapped(y, x, H, W) : row + x);
+        cp_async_f32(dst + 1, wd.wrap ? wd.wrapped(y, x + 1, H, W) : row + x + 1);
+      }
+      // the mask row serves both frames: staged with the first one
+      if (mask && !second) cp_async_f32x2_any(stage_m + slot, reinterpret_cast<const float2*>(mask + (long)y * (2 * N) + x));
+    }
+  };
+  if (nunits > 0) prefetch(0);
+  __syncthreads();  // twiddle tables
+  for (int u = 0; u < nunits; ++u) {
+    const int y = row_begin + (u / halves) * C::B + seq;
+    const bool active = y < row_end;
+    const bool second = (u % halves) == 1;
+    cp_async_commit_and_wait();
+    float2 v[C::VPT];
+#pragma unroll
+    for (int e = 0; e < C::VPT; ++e) {
+      float2 z = make_float2(0.f, 0.f);
+      if (active) {
+        const int slot = e * fft2::kThreads + threadIdx.x;
+        const float2 px = stage_p[slot];
+        const float2 m = mask ? stage_m[slot] : make_float2(1.f, 1.f);
+        z.x = (px.x - mean) * inv_std * m.x;
+        z.y = (px.y - mean) * inv_std * m.y;
+      }
+      v[e] = z;
+    }
+    if (u + 1 < nunits) prefetch(u + 1);  // overlaps with the transform below
+    fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+    __syncthreads();
+    P::Last::store(myseq, j, v);
+    __syncthreads();
+    if (active) {
+      float2* plane = plane_a + (second ? (long)NY * KX : 0l);
+      for (int k = j; k < KX; k += C::TPS) {
+        const float2 zk = myseq[fft2::pad_idx(k)];
+        const float2 zn = myseq[fft2::pad_idx(k == 0 ? 0 : N - k)];
+        const float2 ev = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        const float2 od = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+        plane[(long)y * KX + k] = cadd(ev, cmul(__ldg(tw2n + k), od));
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- forward columns: tmp[plane][y][kx] -> out[plane][kyb][kx] * weight --------------------------------
 template <int N>
 __global__ void __launch_bounds__(fft2::kThreads)
