@@ -1068,6 +1068,10 @@ TMC_API int tmc_xc_peak_partials(int ny, int nx) {
   const int m = fft_size_for(nx / R);
   if (R == 1 && m == nx && m >= 256) {  // power-of-two fast path: several row-pair batches per CTA
     const int b = 256 / (m / 16) > 0 ? 256 / (m / 16) : 1;
+    if (m == 8192 || m == 4096) {  // may run as half-length transforms, one row each (rows_inverse_argmax_real2n): more CTAs
+      const int bh = 256 / (m / 32) > 0 ? 256 / (m / 32) : 1;
+      return tmc_div_up(ny, bh * kRowIters);
+    }
     return tmc_div_up(ny, 2 * b * kRowIters);
   }
   return tmc_div_up(ny, 2 * batch_for(m));
@@ -1101,10 +1105,24 @@ TMC_API int tmc_xc_peaks(const void* prod, int nitems, int ny, int nx, int kx_co
   });
   if (rc) return rc;
   TMC_CHECK_LAUNCH("tmc_xc_peaks(cols)");
-  const int nparts = tmc_xc_peak_partials(ny, nx);
+  int nparts = tmc_xc_peak_partials(ny, nx);  // size of the caller's buffer per item; the kernel chosen may use fewer
   rc = dispatch_fft(nx, "xc_peaks", [&](auto M, auto BLU) {
     constexpr int MM = decltype(M)::value;
     constexpr bool BB = decltype(BLU)::value;
+    if constexpr ((MM == 8192 || MM == 4096) && !BB) {
+      // one row per half-length transform instead of two rows per full-length transform (see rows_forward_real2n)
+      if (px.R == 1 && kx_count <= MM / 4 && use_real2n(MM)) {
+        constexpr int NH = MM / 2;
+        if (int e = enable_smem(rows_inverse_argmax_real2n<NH>, rows_inverse_real2n_smem_bytes<NH>())) return e;
+        nparts = tmc_div_up(ny, rows_per_cta_inverse_real2n<NH>());
+        dim3 grid(nparts, nitems);
+        TMC_TIMED(MM == 8192 ? "rows_inverse_argmax_real2n<4096>" : "rows_inverse_argmax_real2n<2048>", stream,
+                  rows_inverse_argmax_real2n<NH><<<grid, fft2::kThreads, rows_inverse_real2n_smem_bytes<NH>(), stream>>>(
+                      (const float2*)tmp, ny, kx_count, px.tw, (PeakCandidate*)partial));
+        return TMC_OK;
+      }
+      nparts = tmc_div_up(ny, rows_per_cta_inverse<MM>());
+    }
     if constexpr (MM == 1024 && !BB) {
       if (kx_count <= 128 && use_poly() && px.R == 1) {
         if (int e = enable_smem(poly::rows_inverse_argmax_poly, poly::smem_bytes)) return e;

@@ -495,6 +495,131 @@ rows_inverse_argmax_p2(const float2* __restrict__ tmp, int NY, int KX, const flo
   }
 }
 
+// ---- inverse rows of length 2N as N-point complex transforms + argmax ------------------------------------------------
+//
+// x[0 .. 2N) real with spectrum X[k], k < KX <= N / 2:  z[m] = x[2m] + i x[2m+1] = IDFT_N(Z),
+// Z[k] = X[k] + i Y[k], Z[N-k] = conj X[k] + i conj Y[k], Y[k] = X[k] W_2N^{-k} -- the packed spectrum of the "two rows"
+// Ca = X (even samples) and Cb = Y (odd samples) of the kernel above, with Cb formed on the fly: ONE row per N-point
+// transform instead of two rows per 2N-point transform (the 8192-point kernel holds 32 values per thread and is
+// confined to one CTA per SM).  tw2n: the W_2N^m table of the 2N-point plan.
+template <int N>
+__host__ __device__ constexpr int rows_per_cta_inverse_real2n() {
+  return fft2::Cfg<N>::B * kRowIters;
+}
+template <int N>
+constexpr size_t rows_inverse_real2n_smem_bytes() {
+  return fft2::Cfg<N>::smem_bytes + 1ull * fft2::Cfg<N>::B * N * sizeof(float2);
+}
+
+template <int N>
+__global__ void __launch_bounds__(fft2::kThreads, N >= 2048 ? 3 : 1)
+rows_inverse_argmax_real2n(const float2* __restrict__ tmp, int NY, int KX, const float2* __restrict__ tw2n,
+                           PeakCandidate* __restrict__ partial) {
+  using C = fft2::Cfg<N>;
+  using P = fft2::Plan<N>;
+  extern __shared__ float2 smem[];
+  const fft2::Smem<N> sm(smem);
+  for (int i = threadIdx.x; i < 64 + C::TW_HI; i += fft2::kThreads)
+    sm.tw_lo[i] = i < 64 ? __ldg(tw2n + 2 * i) : __ldg(tw2n + 2 * (i - 64) * 64);
+  const long item = blockIdx.y;
+  const float2* src = tmp + item * NY * KX;
+  const int seq = threadIdx.x / C::TPS, j = threadIdx.x % C::TPS;
+  float2* myseq = sm.data + seq * C::STRIDE;
+  float2* stage_a = smem + C::B * C::STRIDE + 64 + C::TW_HI;
+  auto row_of = [&](int it) { return (int)blockIdx.x * rows_per_cta_inverse_real2n<N>() + it * C::B + seq; };
+  auto prefetch = [&](int it) {
+    const int y = row_of(it);
+    if (y >= NY) return;
+    const float2* row = src + (long)y * KX;
+#pragma unroll
+    for (int e = 0; e < C::VPT; ++e) {
+      constexpr int R = P::First::R;
+      // whole blocks of entries are zero for a band-limited spectrum: warp-uniform skip
+      const int lo = (e / R) * C::TPS + (e % R) * P::First::NBR;
+      if (lo >= KX && lo + C::TPS <= N - KX + 1) continue;
+      const int k = c2r_source_index<N>(P::First::in_index(j, e / R, e % R), KX);
+      if (k >= 0) cp_async_f32x2(stage_a + e * fft2::kThreads + threadIdx.x, row + k);
+    }
+  };
+  float best = -INFINITY;
+  int best_idx = 0x7fffffff;
+  prefetch(0);
+  __syncthreads();
+  for (int it = 0; it < kRowIters; ++it) {
+    const int y = row_of(it);
+    const bool active = y < NY;
+    cp_async_commit_and_wait();
+    float2 v[C::VPT];
+#pragma unroll
+    for (int e = 0; e < C::VPT; ++e) {
+      constexpr int R = P::First::R;
+      float2 z = make_float2(0.f, 0.f);
+      const int lo = (e / R) * C::TPS + (e % R) * P::First::NBR;
+      if (active && !(lo >= KX && lo + C::TPS <= N - KX + 1)) {
+        const int i = P::First::in_index(j, e / R, e % R);
+        const int k = c2r_source_index<N>(i, KX);
+        if (k >= 0) {
+          const float2 ca = stage_a[e * fft2::kThreads + threadIdx.x];
+          const float2 w = __ldg(tw2n + k);  // W_2N^k; Y[k] = X[k] conj(W_2N^k)
+          const float2 cb = make_float2(ca.x * w.x + ca.y * w.y, ca.y * w.x - ca.x * w.y);
+          z = c2r_pack<N>(ca, cb, i, KX);
+        }
+      }
+      v[e] = z;
+    }
+    if (it + 1 < kRowIters) prefetch(it + 1);
+    fft2::fft_regs_to_regs<N>(sm, myseq, j, v);
+    if (active) {
+      // samples in increasing index order (m = out_index ascends with r outer, g inner; 2m before 2m + 1; later rows
+      // later): a strictly-greater compare keeps the first of equal maxima
+      const int base = y * (2 * N);
+#pragma unroll
+      for (int r = 0; r < P::Last::R; ++r)
+#pragma unroll
+        for (int g = 0; g < P::Last::G; ++g) {
+          const float2 val = P::Last::result(v, g, r);  // swapped: .y = x[2m], .x = x[2m + 1]
+          const int idx = base + 2 * P::Last::out_index(j, g, r);
+          if (val.y > best) {
+            best = val.y;
+            best_idx = idx;
+          }
+          if (val.x > best) {
+            best = val.x;
+            best_idx = idx + 1;
+          }
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    if (better(ov, oi, best, best_idx)) {
+      best = ov;
+      best_idx = oi;
+    }
+  }
+  __shared__ float sval[fft2::kThreads / 32];
+  __shared__ int sidx[fft2::kThreads / 32];
+  if ((threadIdx.x & 31) == 0) {
+    sval[threadIdx.x >> 5] = best;
+    sidx[threadIdx.x >> 5] = best_idx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < fft2::kThreads / 32; ++i)
+      if (better(sval[i], sidx[i], best, best_idx)) {
+        best = sval[i];
+        best_idx = sidx[i];
+      }
+    PeakCandidate c;
+    c.val = best;
+    c.idx = best_idx;
+    partial[item * gridDim.x + blockIdx.x] = c;
+  }
+}
+
 // ---- inverse rows + store: tmp[item][y][kx] -> out[item][y][x] real ------------------------------------
 template <int N>
 __global__ void __launch_bounds__(fft2::kThreads)
