@@ -304,6 +304,8 @@ def algorithmic_bytes(cfg, iterations, band_bins, n_patches, plane_elems, whole_
         "rows_forward_poly<1>": t * frame,      # patch XC: mask^1 and mask^2 packed (quirk Q1)
         "rows_forward_poly<2>": t * frame,      # optimiser spectra, two frames packed
         "rows_forward_p2<4096>": t * frame,     # whole-frame XC
+        "rows_forward_real2n<2048>": t * frame,  # whole-frame XC rows as half-length transforms (4096-point rows)
+        "rows_forward_real2n<4096>": t * frame,  # the same for 8192-point rows
         "rows_forward_p2": t * frame,
         # column passes: their input is the row pass's intermediate (not algorithmic); they write the band-box spectra
         "cols_forward_p2<1024>": 3 * patch_spectra,  # XC (2 mask powers) + optimiser
@@ -314,7 +316,8 @@ def algorithmic_bytes(cfg, iterations, band_bins, n_patches, plane_elems, whole_
         "local_loss_tile_kernel": 8 * t * n_patches * band_bins,
         # inverse transforms + peak search work on band-limited products only
         "cols_inverse_p2<1024>": None, "cols_inverse_p2<4096>": None, "rows_inverse_argmax_poly": None,
-        "rows_inverse_argmax_p2<4096>": None, "peak_finalize_kernel": None,
+        "rows_inverse_argmax_p2<4096>": None, "rows_inverse_argmax_real2n<2048>": None,
+        "rows_inverse_argmax_real2n<4096>": None, "peak_finalize_kernel": None,
     }
 
 

@@ -9,8 +9,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
     --log-file gpurun_out/launches_${tag}.csv python tools/profile_step.py --iterations 100 > gpurun_out/ncu_launches.log 2>&1
 i=0
 for k in 'local_loss_tile_kernel' 'local_coefficient_kernel' 'rows_forward_poly<.int.1' 'rows_forward_poly<.int.2' 'cols_forward_p2<.int.1024>' \
-         'rows_inverse_argmax_poly' 'cols_inverse_p2<.int.1024>' 'rows_forward_p2<.int.4096' 'cols_forward_p2<.int.4096>' \
-         'cols_inverse_p2<.int.4096>' 'rows_inverse_argmax_p2<.int.4096>' \
+         'rows_inverse_argmax_poly' 'cols_inverse_p2<.int.1024>' 'rows_forward_real2n' 'cols_forward_p2<.int.4096>' \
+         'cols_inverse_p2<.int.4096>' 'rows_inverse_argmax_real2n' \
          'warp_tma_kernel' 'lattice_xinterp_kernel' 'xc_leave_one_out_kernel' 'stats_partial_kernel'; do
   i=$((i+1))
   ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base demangled \

@@ -7,7 +7,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "torch_motion_correction_b200", "libtmc_b200.so")
 HOT = ["warp_tma_kernel", "warp_lattice_kernel", "local_loss_tile_kernel", "local_coefficient_kernel", "rows_forward_poly",
-       "rows_inverse_argmax_poly", "rows_forward_p2", "cols_forward_p2", "cols_inverse_p2", "rows_inverse_argmax_p2",
+       "rows_inverse_argmax_poly", "rows_forward_real2n", "rows_inverse_argmax_real2n", "rows_forward_p2", "cols_forward_p2", "cols_inverse_p2", "rows_inverse_argmax_p2",
        "xc_leave_one_out_kernel", "stats_partial_kernel", "convert_stack_kernel", "lattice_xinterp_kernel"]
 KEYS = ["UTMALDG", "UBLKCP", "SYNCS", "LDGSTS", "FFMA2", "FMUL2", "FADD2", "FFMA", "LDS", "STS", "LDG", "STG", "BAR.SYNC", "SHFL", "MUFU"]
 
