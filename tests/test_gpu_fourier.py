@@ -260,7 +260,7 @@ def test_half_length_row_transforms_agree_with_the_full_length_kernels(dev, monk
     for flag in ("1", "0"):
         monkeypatch.setenv("TMC_FFT_REAL2N", flag)
         out[flag] = as_complex(plan.forward(movie, None, mask, ylo, yhi, jobs, job_mode=2)).clone()
-    scale = float(out["0"].abs().max())
+    scale = float(out["0"][:3].abs().max())  # plane 3 (no second frame in the last job) is never written
     assert float((out["1"][:3] - out["0"][:3]).abs().max()) <= 5e-6 * scale
     ky = (torch.arange(plan.ky, device=dev) + plan.ky_start) % 512
     for plane, (f, y0, x0) in ((0, (0, 100, 4)), (1, (1, 100, 4)), (2, (2, 37, 5))):
