@@ -46,6 +46,10 @@ def test_library_loads_through_the_binding_and_answers_queries():
     assert _lib.query("tmc_fft_supported_length", 13000) == 2  # 4 x 3250: band-limited transforms only
     assert _lib.query("tmc_fft_supported_length", 32768) == 2
     assert _lib.query("tmc_fft_supported_length", 8198) == 0  # 2 x 4099 (prime)
+    # partial-maximum slots per correlation surface: an upper bound over the row kernels that may serve the width
+    assert _lib.query("tmc_xc_peak_partials", 1024, 1024) == 32    # polyphase kernel: 32 rows per CTA
+    assert _lib.query("tmc_xc_peak_partials", 4096, 4096) == 512   # half-length kernel: 2 sequences x 4 rows per CTA
+    assert _lib.query("tmc_xc_peak_partials", 8192, 8192) == 2048  # half-length kernel: 1 sequence x 4 rows per CTA
     assert _lib.query("tmc_fft_plan_elems", 5760) == 2 * 8192 + 2880  # plan of the 2880-point sub-transforms
     assert _lib.query("tmc_fft_plan_elems", 1024) == 1024
     assert _lib.query("tmc_fft_plan_elems", 96) == 2 * 256 + 96
